@@ -1,0 +1,461 @@
+// kernels_fft.cu -- K1/K6 (longitude FFT) and K2/K5 (DCT-II / DCT-III along latitude) for sm_100a.
+//
+// K1  replaces fftw_execute_split_dft + the sqrt(2 pi)/2bw scaling          src/FST_semi_memo.c:81-90
+// K2  replaces the weighting + REDFT10 + orthonormal scaling of DLTSemi    src/legendre_transform/seminaive.c:162-176
+// K5  replaces the scaling + REDFT01 + sin(theta) of InvDLTSemi            src/legendre_transform/seminaive.c:92-114
+//     plus the (-1)^m of negative orders and 1/sqrt(2 pi)                  src/FST_semi_memo.c:294-348
+// K6  replaces the re/im-swapped fftw_execute_split_dft                    src/FST_semi_memo.c:350
+//
+// Layouts (private workspace): S / G spectral planes [f][part][order row m'][latitude j] (the reference's
+// own transposed layout), X / V cosine planes [f][order row m'][part][k < bw].
+// A DCT pair (real and imaginary column of one order) rides on ONE complex FFT of length 2bw: even/odd
+// reordering v[i] = x[2i], v[n-1-i] = x[2i+1] packed as v_re + i v_im, then the two spectra are separated
+// by conjugate symmetry.  Non-power-of-two bandwidths use the direct O(n^2) kernels at the end.
+#include "s2k_fft.cuh"
+#include "s2k_internal.cuh"
+
+namespace s2k {
+
+// ------------------------------------------------------------------------------------------------ K1
+// One CTA transforms LT latitude rows of one function and writes them transposed.
+template <int N, int LT>
+__global__ void __launch_bounds__(N / 8 * LT) k_phi_fft_fwd(const double* __restrict__ rdata,
+                                                            const double* __restrict__ idata, long stride,
+                                                            double* __restrict__ S, double scale, int rows_kept,
+                                                            const double2* __restrict__ tw) {
+    constexpr int T8 = N / 8, NT = T8 * LT;
+    constexpr int RS = ((fft_padded_len(N) + 15) / 16) * 16 + (16 / LT);  // row stride: conflict-free transposed reads
+    extern __shared__ double smem[];
+    double* sre = smem;
+    double* sim = smem + LT * RS;
+    const int tid = threadIdx.x, jj = tid / T8, t = tid % T8;
+    const int j0 = blockIdx.x * LT, f = blockIdx.y;
+    const double* rrow = rdata + (long)f * stride + (long)(j0 + jj) * N;
+    const double* irow = idata + (long)f * stride + (long)(j0 + jj) * N;
+    double xr[8], xi[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        xr[e] = __ldg(rrow + t + e * T8);
+        xi[e] = __ldg(irow + t + e * T8);
+    }
+    fft_block<N>(xr, xi, sre + jj * RS, sim + jj * RS, t, tw);
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        int p = fft_pad(fft_out_index<N>(e, t));
+        sre[jj * RS + p] = xr[e] * scale;
+        sim[jj * RS + p] = xi[e] * scale;
+    }
+    __syncthreads();
+    double* Sr = S + (long)f * 2 * N * N + j0;
+    double* Si = Sr + (long)N * N;
+    // lanes run over the LT latitudes first (contiguous in S), then over order rows
+    for (int flat = tid; flat < N * LT; flat += NT) {
+        int j2 = flat % LT, mp = flat / LT;
+        // REAL format never reads rows >= bw; COMPLEX skips only row bw (rows_kept encodes which)
+        if (rows_kept == N ? (mp != N / 2) : (mp < rows_kept)) {
+            int p = fft_pad(mp);
+            Sr[(long)mp * N + j2] = sre[j2 * RS + p];
+            Si[(long)mp * N + j2] = sim[j2 * RS + p];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K6
+template <int N, int LT>
+__global__ void __launch_bounds__(N / 8 * LT) k_phi_fft_inv(const double* __restrict__ G, double* __restrict__ rdata,
+                                                            double* __restrict__ idata, long stride, int real_fmt,
+                                                            const double2* __restrict__ tw) {
+    constexpr int T8 = N / 8, NT = T8 * LT;
+    constexpr int RS = ((fft_padded_len(N) + 15) / 16) * 16 + (16 / LT);
+    extern __shared__ double smem[];
+    double* sre = smem;
+    double* sim = smem + LT * RS;
+    const int tid = threadIdx.x, jj = tid / T8, t = tid % T8;
+    const int j0 = blockIdx.x * LT, f = blockIdx.y;
+    const double* Gr = G + (long)f * 2 * N * N + j0;
+    const double* Gi = Gr + (long)N * N;
+    // inverse DFT through the forward one: feed (im, re), read back (im, re)   (FST_semi_memo.c:350)
+    for (int flat = tid; flat < N * LT; flat += NT) {
+        int j2 = flat % LT, mp = flat / LT;
+        double vr = 0.0, vi = 0.0;
+        if (mp != N / 2) {
+            if (real_fmt && mp > N / 2) {
+                // conjugate mirror of row n - m'   (FST_semi_memo.c:333-341)
+                vr = __ldg(Gr + (long)(N - mp) * N + j2);
+                vi = -__ldg(Gi + (long)(N - mp) * N + j2);
+            } else {
+                vr = __ldg(Gr + (long)mp * N + j2);
+                vi = __ldg(Gi + (long)mp * N + j2);
+            }
+        }
+        int p = fft_pad(mp);
+        sre[j2 * RS + p] = vi;
+        sim[j2 * RS + p] = vr;
+    }
+    __syncthreads();
+    double xr[8], xi[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        int p = fft_pad(fft_in_index<N>(e, t));
+        xr[e] = sre[jj * RS + p];
+        xi[e] = sim[jj * RS + p];
+    }
+    fft_block<N>(xr, xi, sre + jj * RS, sim + jj * RS, t, tw);
+    double* rrow = rdata + (long)f * stride + (long)(j0 + jj) * N;
+    double* irow = idata + (long)f * stride + (long)(j0 + jj) * N;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        int k = fft_out_index<N>(e, t);
+        irow[k] = xr[e];
+        rrow[k] = xi[e];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K2
+__device__ __forceinline__ int ridx_to_row(int ridx, int bw) { return ridx < bw ? ridx : ridx + 1; }
+
+// One CTA handles FPB (function, order row) pairs; each pair = re and im column -> one complex FFT.
+template <int N, int FPB>
+__global__ void __launch_bounds__(N / 8 * FPB) k_dct_fwd(const double* __restrict__ S, double* __restrict__ X,
+                                                         const double* __restrict__ weights, int ridx_lo, int ridx_hi,
+                                                         const double2* __restrict__ tw,
+                                                         const double2* __restrict__ qtab) {
+    constexpr int T8 = N / 8, B = N / 2, NP = fft_padded_len(N);
+    extern __shared__ double smem[];
+    const int tid = threadIdx.x, g = tid / T8, t = tid % T8;
+    double* sre = smem + g * 2 * NP;
+    double* sim = sre + NP;
+    const int ridx = ridx_lo + blockIdx.x * FPB + g, f = blockIdx.y;
+    const bool live = ridx < ridx_hi;
+    const int mp = ridx_to_row(live ? ridx : ridx_lo, B);
+    const int m = mp < B ? mp : N - mp;
+    const double* w = weights + ((m & 1) ? N : 0);
+    const double* Sr = S + ((long)f * 2 * N + mp) * N;
+    const double* Si = Sr + (long)N * N;
+    double xr[8], xi[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        int p = t + e * T8;
+        int j = (p < B) ? 2 * p : 2 * (N - 1 - p) + 1;
+        double wj = __ldg(w + j);
+        xr[e] = __ldg(Sr + j) * wj;
+        xi[e] = __ldg(Si + j) * wj;
+    }
+    fft_block<N>(xr, xi, sre, sim, t, tw);
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        int p = fft_pad(fft_out_index<N>(e, t));
+        sre[p] = xr[e];
+        sim[p] = xi[e];
+    }
+    __syncthreads();
+    if (!live) return;
+    double* Xr = X + (((long)f * N + mp) * 2) * B;
+    double* Xi = Xr + B;
+    const double s_all = rsqrt(2.0 * (double)N);  // 1/sqrt(2*size), seminaive.c:174
+    for (int k = t; k < B; k += T8) {
+        int nk = (N - k) & (N - 1);
+        double ar = sre[fft_pad(k)], ai = sim[fft_pad(k)];
+        double br = sre[fft_pad(nk)], bi = sim[fft_pad(nk)];
+        // V1 = (Z[k] + conj Z[n-k]) / 2 ; V2 = (Z[k] - conj Z[n-k]) / 2i ; REDFT10 = 2 Re(e^{-i pi k/2n} V)
+        double2 q = __ldg(qtab + k);
+        double y1 = q.x * (ar + br) + q.y * (ai - bi);
+        double y2 = q.x * (ai + bi) - q.y * (ar - br);
+        if (k == 0) {
+            y1 *= 0.70710678118654752440;  // M_SQRT1_2, seminaive.c:173
+            y2 *= 0.70710678118654752440;
+        }
+        Xr[k] = y1 * s_all;
+        Xi[k] = y2 * s_all;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K5
+template <int N, int FPB>
+__global__ void __launch_bounds__(N / 8 * FPB) k_dct_inv(const double* __restrict__ V, double* __restrict__ G,
+                                                         const double* __restrict__ sinv, int ridx_lo, int ridx_hi,
+                                                         double out_scale, const double2* __restrict__ tw,
+                                                         const double2* __restrict__ qtab) {
+    constexpr int T8 = N / 8, B = N / 2, NP = fft_padded_len(N);
+    extern __shared__ double smem[];
+    const int tid = threadIdx.x, g = tid / T8, t = tid % T8;
+    double* sre = smem + g * 2 * NP;
+    double* sim = sre + NP;
+    const int ridx = ridx_lo + blockIdx.x * FPB + g, f = blockIdx.y;
+    const bool live = ridx < ridx_hi;
+    const int mp = ridx_to_row(live ? ridx : ridx_lo, B);
+    const int m = mp < B ? mp : N - mp;
+    const double* Va = V + (((long)f * N + mp) * 2) * B;
+    const double* Vb = Va + B;
+    const double c_rest = rsqrt(2.0 * (double)N);  // 0.5/sqrt(bw), seminaive.c:72
+    const double c_zero = rsqrt((double)N);        // fcos[0] / sqrt(2 bw), seminaive.c:98
+    double xr[8], xi[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        int k = t + e * T8;
+        // W[k] = e^{i pi k/2n} (Xa[k] - i Xa[n-k]) + i (same for b), X[k >= bw] = 0
+        double wr = 0.0, wi = 0.0;
+        if (k != B) {
+            int src = k < B ? k : N - k;
+            double sc = (src == 0) ? c_zero : c_rest;
+            double a = __ldg(Va + src) * sc, b = __ldg(Vb + src) * sc;
+            double2 q = __ldg(qtab + k);
+            double ur = (k < B) ? a : b, ui = (k < B) ? b : -a;  // (a + ib) or -i (a + ib)
+            wr = q.x * ur - q.y * ui;
+            wi = q.x * ui + q.y * ur;
+        }
+        xr[e] = wi;  // swapped: inverse DFT through the forward transform
+        xi[e] = wr;
+    }
+    fft_block<N>(xr, xi, sre, sim, t, tw);
+    if (!live) return;
+    double sign = ((mp > B) && (m & 1)) ? -out_scale : out_scale;  // (-1)^m for negative orders
+    double* Gr = G + ((long)f * 2 * N + mp) * N;
+    double* Gi = Gr + (long)N * N;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        int i = fft_out_index<N>(e, t);
+        int j = (i < B) ? 2 * i : 2 * (N - 1 - i) + 1;
+        double s = (m & 1) ? __ldg(sinv + j) * sign : sign;
+        Gr[j] = xi[e] * s;  // Re z -> column a (real part)
+        Gi[j] = xr[e] * s;  // Im z -> column b (imaginary part)
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ direct kernels
+// Any bandwidth: one thread per output, exact-index twiddles.  Used when bw is not a power of two (or < 16).
+__global__ void k_direct_phi_fwd(const double* __restrict__ rdata, const double* __restrict__ idata, long stride,
+                                 double* __restrict__ S, int n, double scale, const double2* __restrict__ tw) {
+    int j = blockIdx.x, f = blockIdx.y;
+    const double* rr = rdata + (long)f * stride + (long)j * n;
+    const double* ii = idata + (long)f * stride + (long)j * n;
+    for (int mp = threadIdx.x; mp < n; mp += blockDim.x) {
+        double sr = 0.0, si = 0.0;
+        for (int k = 0; k < n; ++k) {
+            double2 w = tw[(int)(((long)mp * k) % n)];
+            double a = rr[k], b = ii[k];
+            sr += a * w.x - b * w.y;
+            si += a * w.y + b * w.x;
+        }
+        S[((long)f * 2 * n + mp) * n + j] = sr * scale;
+        S[((long)f * 2 * n + n + mp) * n + j] = si * scale;
+    }
+}
+
+__global__ void k_direct_phi_inv(const double* __restrict__ G, double* __restrict__ rdata, double* __restrict__ idata,
+                                 long stride, int n, int real_fmt, const double2* __restrict__ tw) {
+    int j = blockIdx.x, f = blockIdx.y;
+    const double* Gr = G + (long)f * 2 * n * n;
+    const double* Gi = Gr + (long)n * n;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        double sr = 0.0, si = 0.0;
+        for (int mp = 0; mp < n; ++mp) {
+            if (2 * mp == n) continue;
+            double a, b;
+            if (real_fmt && 2 * mp > n) {
+                a = Gr[(long)(n - mp) * n + j];
+                b = -Gi[(long)(n - mp) * n + j];
+            } else {
+                a = Gr[(long)mp * n + j];
+                b = Gi[(long)mp * n + j];
+            }
+            double2 w = tw[(int)(((long)mp * k) % n)];  // (cos, -sin): conjugate for e^{+i}
+            sr += a * w.x + b * w.y;
+            si += b * w.x - a * w.y;
+        }
+        rdata[(long)f * stride + (long)j * n + k] = sr;
+        idata[(long)f * stride + (long)j * n + k] = si;
+    }
+}
+
+__global__ void k_direct_dct_fwd(const double* __restrict__ S, double* __restrict__ X,
+                                 const double* __restrict__ weights, int bw, int ridx_lo,
+                                 const double2* __restrict__ qtab) {
+    int n = 2 * bw;
+    int mp = ridx_to_row(ridx_lo + blockIdx.x, bw), f = blockIdx.y;
+    int m = mp < bw ? mp : n - mp;
+    const double* w = weights + ((m & 1) ? n : 0);
+    double s_all = 1.0 / sqrt(2.0 * (double)n);
+    for (int o = threadIdx.x; o < 2 * bw; o += blockDim.x) {
+        int part = o / bw, k = o % bw;
+        const double* col = S + (((long)f * 2 + part) * n + mp) * n;
+        double acc = 0.0;
+        for (int j = 0; j < n; ++j) acc += col[j] * w[j] * qtab[(int)(((long)(2 * j + 1) * k) % (4 * n))].x;
+        acc *= 2.0;
+        if (k == 0) acc *= 0.70710678118654752440;
+        X[(((long)f * n + mp) * 2 + part) * bw + k] = acc * s_all;
+    }
+}
+
+__global__ void k_direct_dct_inv(const double* __restrict__ V, double* __restrict__ G, const double* __restrict__ sinv,
+                                 int bw, int ridx_lo, double out_scale, const double2* __restrict__ qtab) {
+    int n = 2 * bw;
+    int mp = ridx_to_row(ridx_lo + blockIdx.x, bw), f = blockIdx.y;
+    int m = mp < bw ? mp : n - mp;
+    double c_rest = 0.5 / sqrt((double)bw), c_zero = 1.0 / sqrt((double)n);
+    double sign = ((mp > bw) && (m & 1)) ? -out_scale : out_scale;
+    for (int o = threadIdx.x; o < 2 * n; o += blockDim.x) {
+        int part = o / n, j = o % n;
+        const double* v = V + (((long)f * n + mp) * 2 + part) * bw;
+        double acc = v[0] * c_zero;
+        for (int k = 1; k < bw; ++k) acc += 2.0 * (v[k] * c_rest) * qtab[(int)(((long)(2 * j + 1) * k) % (4 * n))].x;
+        double s = (m & 1) ? sinv[j] * sign : sign;
+        G[(((long)f * 2 + part) * n + mp) * n + j] = acc * s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+template <typename K>
+static cudaError_t set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    return cudaSuccess;
+}
+
+template <int N>
+static cudaError_t phi_fwd_n(s2kit_cuda_plan* p, const double* rdata, const double* idata, long stride, double* S,
+                             int nfun, int rows_kept) {
+    constexpr int LT = (4096 / N) < 8 ? (4096 / N) : 8;
+    constexpr int RS = ((fft_padded_len(N) + 15) / 16) * 16 + (16 / LT);
+    size_t smem = sizeof(double) * 2 * LT * RS;
+    cudaError_t e = set_smem(k_phi_fft_fwd<N, LT>, smem);
+    if (e != cudaSuccess) return e;
+    double scale = sqrt(2.0 * M_PI) / (double)N;  // FST_semi_memo.c:86
+    k_phi_fft_fwd<N, LT><<<dim3(N / LT, nfun), N / 8 * LT, smem, p->stream>>>(rdata, idata, stride, S, scale,
+                                                                              rows_kept, p->d_tw_n);
+    return cudaGetLastError();
+}
+
+template <int N>
+static cudaError_t phi_inv_n(s2kit_cuda_plan* p, const double* G, double* rdata, double* idata, long stride, int nfun,
+                             int real_fmt) {
+    constexpr int LT = (4096 / N) < 8 ? (4096 / N) : 8;
+    constexpr int RS = ((fft_padded_len(N) + 15) / 16) * 16 + (16 / LT);
+    size_t smem = sizeof(double) * 2 * LT * RS;
+    cudaError_t e = set_smem(k_phi_fft_inv<N, LT>, smem);
+    if (e != cudaSuccess) return e;
+    k_phi_fft_inv<N, LT><<<dim3(N / LT, nfun), N / 8 * LT, smem, p->stream>>>(G, rdata, idata, stride, real_fmt,
+                                                                              p->d_tw_n);
+    return cudaGetLastError();
+}
+
+template <int N>
+static cudaError_t dct_fwd_n(s2kit_cuda_plan* p, const double* S, double* X, int nfun, int lo, int hi) {
+    constexpr int T8 = N / 8;
+    constexpr int FPB = (256 / T8) < 1 ? 1 : ((256 / T8) > 8 ? 8 : (256 / T8));
+    size_t smem = sizeof(double) * 2 * FPB * fft_padded_len(N);
+    cudaError_t e = set_smem(k_dct_fwd<N, FPB>, smem);
+    if (e != cudaSuccess) return e;
+    k_dct_fwd<N, FPB><<<dim3((hi - lo + FPB - 1) / FPB, nfun), T8 * FPB, smem, p->stream>>>(
+        S, X, p->d_weights, lo, hi, p->d_tw_n, p->d_q_n);
+    return cudaGetLastError();
+}
+
+template <int N>
+static cudaError_t dct_inv_n(s2kit_cuda_plan* p, const double* V, double* G, int nfun, int lo, int hi) {
+    constexpr int T8 = N / 8;
+    constexpr int FPB = (256 / T8) < 1 ? 1 : ((256 / T8) > 8 ? 8 : (256 / T8));
+    size_t smem = sizeof(double) * 2 * FPB * fft_padded_len(N);
+    cudaError_t e = set_smem(k_dct_inv<N, FPB>, smem);
+    if (e != cudaSuccess) return e;
+    double out_scale = 1.0 / sqrt(2.0 * M_PI);  // FST_semi_memo.c:344
+    k_dct_inv<N, FPB><<<dim3((hi - lo + FPB - 1) / FPB, nfun), T8 * FPB, smem, p->stream>>>(
+        V, G, p->d_sin, lo, hi, out_scale, p->d_tw_n, p->d_q_n);
+    return cudaGetLastError();
+}
+
+#define S2K_DISPATCH_N(n, CALL)                  \
+    switch (n) {                                 \
+        case 32: return CALL(32);                \
+        case 64: return CALL(64);                \
+        case 128: return CALL(128);              \
+        case 256: return CALL(256);              \
+        case 512: return CALL(512);              \
+        case 1024: return CALL(1024);            \
+        case 2048: return CALL(2048);            \
+        case 4096: return CALL(4096);            \
+        default: return cudaErrorInvalidValue;   \
+    }
+
+cudaError_t launch_phi_fft_fwd(s2kit_cuda_plan* p, const double* rdata, const double* idata, long stride, double* S,
+                               int nfun, int data_format) {
+    int n = p->n;
+    int slot = prof_begin(p, S2KIT_K_PHI_FFT_FWD);
+    cudaError_t e;
+    if (p->fast) {
+        int rows_kept = (data_format == S2KIT_REAL) ? p->bw : n;
+#define CALL(NN) phi_fwd_n<NN>(p, rdata, idata, stride, S, nfun, rows_kept)
+        e = [&]() -> cudaError_t { S2K_DISPATCH_N(n, CALL) }();
+#undef CALL
+    } else {
+        int nt = n < 256 ? ((n + 31) / 32) * 32 : 256;
+        k_direct_phi_fwd<<<dim3(n, nfun), nt, 0, p->stream>>>(rdata, idata, stride, S, n,
+                                                              sqrt(2.0 * M_PI) / (double)n, p->d_tw_n);
+        e = cudaGetLastError();
+    }
+    prof_end(p, slot);
+    return e;
+}
+
+cudaError_t launch_phi_fft_inv(s2kit_cuda_plan* p, const double* G, double* rdata, double* idata, long stride, int nfun,
+                               int data_format) {
+    int n = p->n;
+    int real_fmt = data_format == S2KIT_REAL;
+    int slot = prof_begin(p, S2KIT_K_PHI_FFT_INV);
+    cudaError_t e;
+    if (p->fast) {
+#define CALL(NN) phi_inv_n<NN>(p, G, rdata, idata, stride, nfun, real_fmt)
+        e = [&]() -> cudaError_t { S2K_DISPATCH_N(n, CALL) }();
+#undef CALL
+    } else {
+        int nt = n < 256 ? ((n + 31) / 32) * 32 : 256;
+        k_direct_phi_inv<<<dim3(n, nfun), nt, 0, p->stream>>>(G, rdata, idata, stride, n, real_fmt, p->d_tw_n);
+        e = cudaGetLastError();
+    }
+    prof_end(p, slot);
+    return e;
+}
+
+// rows are addressed by ridx in [0, 2bw-1): ridx < bw -> order row ridx, else row ridx + 1 (row bw unused)
+cudaError_t launch_dct_fwd(s2kit_cuda_plan* p, const double* S, double* X, int nfun, int row_lo, int row_hi,
+                           int data_format) {
+    (void)data_format;
+    if (row_hi <= row_lo) return cudaSuccess;
+    int slot = prof_begin(p, S2KIT_K_DCT_FWD);
+    cudaError_t e;
+    if (p->fast) {
+#define CALL(NN) dct_fwd_n<NN>(p, S, X, nfun, row_lo, row_hi)
+        e = [&]() -> cudaError_t { S2K_DISPATCH_N(p->n, CALL) }();
+#undef CALL
+    } else {
+        int nt = 2 * p->bw < 256 ? ((2 * p->bw + 31) / 32) * 32 : 256;
+        k_direct_dct_fwd<<<dim3(row_hi - row_lo, nfun), nt, 0, p->stream>>>(S, X, p->d_weights, p->bw, row_lo,
+                                                                            p->d_q_n);
+        e = cudaGetLastError();
+    }
+    prof_end(p, slot);
+    return e;
+}
+
+cudaError_t launch_dct_inv(s2kit_cuda_plan* p, const double* V, double* G, int nfun, int row_lo, int row_hi,
+                           int data_format) {
+    (void)data_format;
+    if (row_hi <= row_lo) return cudaSuccess;
+    int slot = prof_begin(p, S2KIT_K_DCT_INV);
+    cudaError_t e;
+    if (p->fast) {
+#define CALL(NN) dct_inv_n<NN>(p, V, G, nfun, row_lo, row_hi)
+        e = [&]() -> cudaError_t { S2K_DISPATCH_N(p->n, CALL) }();
+#undef CALL
+    } else {
+        int nt = 256;
+        k_direct_dct_inv<<<dim3(row_hi - row_lo, nfun), nt, 0, p->stream>>>(V, G, p->d_sin, p->bw, row_lo,
+                                                                            1.0 / sqrt(2.0 * M_PI), p->d_q_n);
+        e = cudaGetLastError();
+    }
+    prof_end(p, slot);
+    return e;
+}
+
+}  // namespace s2k

@@ -1,0 +1,313 @@
+// kernels_legendre.cu -- K3 / K4: the seminaive Legendre contraction on FP64 tensor cores (DMMA).
+//
+// K3 replaces the triangular dot of DLTSemi     src/legendre_transform/seminaive.c:183-197
+//    plus the coefficient placement / (-1)^m / REAL-format symmetry of FSTSemiMemo
+//                                                src/FST_semi_memo.c:96-108,131-145,175-201
+// K4 replaces the transposed dot of InvDLTSemi  src/legendre_transform/seminaive.c:74-95
+//
+// The batched contraction is a real dense GEMM per order m: coefficients[l, col] = sum_k T_m[l,k] X[k,col]
+// with columns = (function, +m / -m, re / im).  T_m is checkerboard-sparse, so it is handled as two
+// lower-trapezoidal parity blocks (s2k_internal.cuh), tiled 8x8 in DMMA fragment order: the table streams
+// from L2/HBM straight into mma.sync.m8n8k4.f64 A fragments with one coalesced 128-bit load per lane and
+// tile, never touching shared memory; the X (or coefficient) panel of the CTA's columns sits in shared
+// memory for the whole order.  The inverse reads the SAME tiles as B fragments (4 rows x 8 columns), so
+// no transposed table is stored (the reference keeps one: cospml.c:301-362).
+#include "s2k_internal.cuh"
+
+namespace s2k {
+
+__device__ __forceinline__ void dmma(double (&d)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d[0]), "+d"(d[1])
+                 : "d"(a), "d"(b));
+}
+
+// index of f^(m,l=|m|) in the coefficient arrays  (IndexOfHarmonicCoeff, util.c:42-49)
+__device__ __forceinline__ int coef_base(int m, int bw) {
+    if (m >= 0) return m * bw - (m * (m - 1)) / 2;
+    int big = bw - 1;
+    return (big * (big + 3)) / 2 + 1 + ((big + m) * (big + m + 1)) / 2;
+}
+
+__host__ __device__ inline int panel_stride(int bw) {
+    int hb = ((bw + 1) / 2 + 7) / 8 * 8;
+    return hb + ((4 - hb % 16) + 16) % 16;  // == 4 (mod 16): conflict-free 64-bit fragment loads
+}
+
+constexpr int LEG_WARPS = 8;
+
+// ------------------------------------------------------------------------------------------------ K3
+// grid: x = column tile, y = order (heavy orders first), z = row split.  NC columns per CTA.
+template <int NC>
+__global__ void __launch_bounds__(LEG_WARPS * 32) k_legendre_fwd(
+    const double* __restrict__ table, const uint64_t* __restrict__ order_start, uint64_t table_shift,
+    const BlockMeta* __restrict__ meta, const uint32_t* __restrict__ rt_start, const double* __restrict__ X,
+    double* __restrict__ rco, double* __restrict__ ico, long coef_stride, int bw, int nfun, int m_lo, int real_fmt) {
+    extern __shared__ double smem[];
+    const int n = 2 * bw, CS = panel_stride(bw);
+    const int m = m_lo + blockIdx.y;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cols_per_fn = real_fmt ? 2 : 4;
+    const int NF = NC / cols_per_fn;
+    const int f0 = blockIdx.x * NF;
+    double* Xs = smem;  // [2][NC][CS]
+
+    // ---- stage the X panel, de-interleaved by cosine-index parity, zero padded
+    for (int i = tid; i < 2 * NC * CS; i += blockDim.x) Xs[i] = 0.0;
+    __syncthreads();
+    for (int col = warp; col < NC; col += LEG_WARPS) {
+        int fl = col / cols_per_fn, sub = col % cols_per_fn;
+        int sgn = real_fmt ? 0 : (sub >> 1), part = sub & 1;
+        int f = f0 + fl;
+        if (f >= nfun || (sgn && m == 0)) continue;
+        int mp = sgn ? n - m : m;
+        const double* src = X + (((long)f * n + mp) * 2 + part) * bw;
+        for (int k = lane; k < bw; k += 32) Xs[((k & 1) * NC + col) * CS + (k >> 1)] = __ldg(src + k);
+    }
+    __syncthreads();
+
+    const BlockMeta mb0 = meta[2 * m], mb1 = meta[2 * m + 1];
+    const int total = mb0.nrt + mb1.nrt;
+    const double* tbase = table + (order_start[m] - table_shift) * 64 + lane * 2;
+    const int g = lane >> 2, q4 = lane & 3;
+    const double sgn_neg = (m & 1) ? -1.0 : 1.0;
+    const int base_pos = coef_base(m, bw), base_neg = coef_base(-m, bw);
+
+    for (int q = blockIdx.z * LEG_WARPS + warp; q < total; q += LEG_WARPS * gridDim.z) {
+        // heavy row tiles (large rt) first
+        const int p = q < mb0.nrt ? 0 : 1;
+        const BlockMeta mb = p ? mb1 : mb0;
+        const int rt = p ? (mb.nrt - 1 - (q - mb0.nrt)) : (mb.nrt - 1 - q);
+        const int last_row = min(8 * rt + 7, mb.rows - 1);
+        const int ctn = (mb.len0 + last_row + 7) >> 3;
+        const double* tp = tbase + (uint64_t)rt_start[mb.rt_base + rt] * 64;
+        const double* xp = Xs + (p * NC + g) * CS + q4;
+
+        double acc[NC / 8][2];
+#pragma unroll
+        for (int j = 0; j < NC / 8; ++j) acc[j][0] = acc[j][1] = 0.0;
+
+        double2 a = __ldg(reinterpret_cast<const double2*>(tp));
+        for (int ct = 0; ct < ctn; ++ct) {
+            double2 an = a;
+            if (ct + 1 < ctn) an = __ldg(reinterpret_cast<const double2*>(tp + (ct + 1) * 64));
+#pragma unroll
+            for (int j = 0; j < NC / 8; ++j) {
+                double b0 = xp[j * 8 * CS + 8 * ct];
+                double b1 = xp[j * 8 * CS + 8 * ct + 4];
+                dmma(acc[j], a.x, b0);
+                dmma(acc[j], a.y, b1);
+            }
+            a = an;
+        }
+
+        // ---- epilogue: lane holds rows r = 8rt + g, columns 8j + 2 q4 + {0,1}
+        const int r = 8 * rt + g;
+        if (r < mb.rows) {
+            const int off = p + 2 * r;  // l - m
+#pragma unroll
+            for (int j = 0; j < NC / 8; ++j) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    int col = 8 * j + 2 * q4 + e;
+                    int fl = col / cols_per_fn, sub = col % cols_per_fn;
+                    int f = f0 + fl;
+                    if (f >= nfun) continue;
+                    double v = acc[j][e];
+                    if (real_fmt) {
+                        int part = sub & 1;
+                        double* dst = (part ? ico : rco) + (long)f * coef_stride;
+                        dst[base_pos + off] = v;
+                        // f^(-m,l) = (-1)^m conj f^(m,l)   (FST_semi_memo.c:131-145)
+                        if (m > 0) dst[base_neg + off] = part ? -sgn_neg * v : sgn_neg * v;
+                    } else {
+                        int sgn = sub >> 1, part = sub & 1;
+                        if (sgn && m == 0) continue;
+                        double* dst = (part ? ico : rco) + (long)f * coef_stride;
+                        if (sgn)
+                            dst[base_neg + off] = sgn_neg * v;  // (-1)^m'  (FST_semi_memo.c:181-186)
+                        else
+                            dst[base_pos + off] = v;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K4
+// V[col, k] = sum_l T_m[l, k] c[l, col]: D(8 cols x 8 k) += A(8 cols x 4 l) * B(4 l x 8 k)
+template <int NC>
+__global__ void __launch_bounds__(LEG_WARPS * 32) k_legendre_inv(
+    const double* __restrict__ table, const uint64_t* __restrict__ order_start, uint64_t table_shift,
+    const BlockMeta* __restrict__ meta, const uint32_t* __restrict__ rt_start, const double* __restrict__ rco,
+    const double* __restrict__ ico, long coef_stride, double* __restrict__ V, int bw, int nfun, int m_lo,
+    int real_fmt) {
+    extern __shared__ double smem[];
+    const int n = 2 * bw, CS = panel_stride(bw);
+    const int m = m_lo + blockIdx.y;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cols_per_fn = real_fmt ? 2 : 4;
+    const int NF = NC / cols_per_fn;
+    const int f0 = blockIdx.x * NF;
+    double* Cs = smem;  // [2][NC][CS], row index r = (l-m)>>1
+
+    for (int i = tid; i < 2 * NC * CS; i += blockDim.x) Cs[i] = 0.0;
+    __syncthreads();
+    const int base_pos = coef_base(m, bw), base_neg = coef_base(-m, bw);
+    for (int col = warp; col < NC; col += LEG_WARPS) {
+        int fl = col / cols_per_fn, sub = col % cols_per_fn;
+        int sgn = real_fmt ? 0 : (sub >> 1), part = sub & 1;
+        int f = f0 + fl;
+        if (f >= nfun || (sgn && m == 0)) continue;
+        const double* src = (part ? ico : rco) + (long)f * coef_stride + (sgn ? base_neg : base_pos);
+        for (int o = lane; o < bw - m; o += 32) Cs[((o & 1) * NC + col) * CS + (o >> 1)] = __ldg(src + o);
+    }
+    __syncthreads();
+
+    const BlockMeta mb0 = meta[2 * m], mb1 = meta[2 * m + 1];
+    const int nct = (((bw + 1) / 2) + 7) >> 3;  // column tiles needed to cover every k < bw of one parity
+    const double* tbase = table + (order_start[m] - table_shift) * 64;
+    const int g = lane >> 2, q4 = lane & 3;
+    // B fragment of k-step s: element (row q4 + 4s, col g) of the 8x8 tile
+    const int boff0 = tile_elem_offset(q4, g), boff1 = tile_elem_offset(q4 + 4, g);
+
+    for (int q = blockIdx.z * LEG_WARPS + warp; q < 2 * nct; q += LEG_WARPS * gridDim.z) {
+        const int p = q & 1, ct = q >> 1;  // low column tiles (most rows) first
+        const BlockMeta mb = p ? mb1 : mb0;
+        double acc[NC / 8][2];
+#pragma unroll
+        for (int j = 0; j < NC / 8; ++j) acc[j][0] = acc[j][1] = 0.0;
+
+        // first row tile whose trapezoid reaches column tile ct: len0 + min(8rt+7, rows-1) > 8ct
+        int rt_min = 0;
+        if (8 * ct >= mb.len0 + 7) rt_min = (8 * ct - mb.len0 - 7) / 8 + 1;
+        const double* cp = Cs + (p * NC + g) * CS + q4;
+        for (int rt = rt_min; rt < mb.nrt; ++rt) {
+            int last_row = min(8 * rt + 7, mb.rows - 1);
+            int ctn = (mb.len0 + last_row + 7) >> 3;
+            if (ct >= ctn) continue;
+            const double* tp = tbase + ((uint64_t)rt_start[mb.rt_base + rt] + ct) * 64;
+            double b0 = __ldg(tp + boff0), b1 = __ldg(tp + boff1);
+#pragma unroll
+            for (int j = 0; j < NC / 8; ++j) {
+                double a0 = cp[j * 8 * CS + 8 * rt];
+                double a1 = cp[j * 8 * CS + 8 * rt + 4];
+                dmma(acc[j], a0, b0);
+                dmma(acc[j], a1, b1);
+            }
+        }
+        // ---- epilogue: lane holds column 8j + g, cosine slots c = 8ct + 2 q4 + {0,1}
+#pragma unroll
+        for (int j = 0; j < NC / 8; ++j) {
+            int col = 8 * j + g;
+            int fl = col / cols_per_fn, sub = col % cols_per_fn;
+            int sgn = real_fmt ? 0 : (sub >> 1), part = sub & 1;
+            int f = f0 + fl;
+            if (f >= nfun || (sgn && m == 0)) continue;
+            int mp = sgn ? n - m : m;
+            double* dst = V + (((long)f * n + mp) * 2 + part) * bw;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                int k = 2 * (8 * ct + 2 * q4 + e) + p;
+                if (k < bw) dst[k] = acc[j][e];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+template <int NC>
+static cudaError_t leg_fwd_nc(s2kit_cuda_plan* p, const double* table, uint64_t shift, const double* X, double* rco,
+                              double* ico, long coef_stride, int nfun, int m_lo, int m_hi, int real_fmt, int rowsplit) {
+    int cols_per_fn = real_fmt ? 2 : 4;
+    int NF = NC / cols_per_fn;
+    size_t smem = sizeof(double) * 2 * NC * panel_stride(p->bw);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_legendre_fwd<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    dim3 grid((nfun + NF - 1) / NF, m_hi - m_lo, rowsplit);
+    k_legendre_fwd<NC><<<grid, LEG_WARPS * 32, smem, p->stream>>>(table, p->d_order_start, shift, p->d_meta,
+                                                                  p->d_rt_start, X, rco, ico, coef_stride, p->bw, nfun,
+                                                                  m_lo, real_fmt);
+    return cudaGetLastError();
+}
+
+template <int NC>
+static cudaError_t leg_inv_nc(s2kit_cuda_plan* p, const double* table, uint64_t shift, const double* rco,
+                              const double* ico, long coef_stride, double* V, int nfun, int m_lo, int m_hi,
+                              int real_fmt, int rowsplit) {
+    int cols_per_fn = real_fmt ? 2 : 4;
+    int NF = NC / cols_per_fn;
+    size_t smem = sizeof(double) * 2 * NC * panel_stride(p->bw);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_legendre_inv<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    dim3 grid((nfun + NF - 1) / NF, m_hi - m_lo, rowsplit);
+    k_legendre_inv<NC><<<grid, LEG_WARPS * 32, smem, p->stream>>>(table, p->d_order_start, shift, p->d_meta,
+                                                                  p->d_rt_start, rco, ico, coef_stride, V, p->bw, nfun,
+                                                                  m_lo, real_fmt);
+    return cudaGetLastError();
+}
+
+// Column-tile width: as wide as the batch and 200 KB of shared memory allow (table reuse per CTA), at
+// least 8 (one MMA n-tile; a single field's 4 columns are padded with zeros).
+static int pick_nc(int bw, int nfun, int real_fmt) {
+    int cols = nfun * (real_fmt ? 2 : 4);
+    size_t per_col = sizeof(double) * 2 * panel_stride(bw);
+    int nc = 32;
+    while (nc > 8 && (nc / 2 >= cols || per_col * nc > 100 * 1024)) nc /= 2;
+    return nc;
+}
+
+// Row split: single-field / small-batch launches have too few CTAs per order; split each order's row
+// tiles over several CTAs so that the grid covers the 148 SMs a few times over.
+static int pick_rowsplit(int bw, int ncoltiles, int norders) {
+    long ctas = (long)ncoltiles * norders;
+    int rs = 1;
+    int max_rs = (bw / 16 + LEG_WARPS - 1) / LEG_WARPS;  // at most one row tile per warp and parity
+    if (max_rs < 1) max_rs = 1;
+    while (ctas * rs < 148 * 4 && rs < max_rs) rs *= 2;
+    return rs;
+}
+
+cudaError_t launch_legendre_fwd(s2kit_cuda_plan* p, const double* table, uint64_t shift, const double* X, double* rco,
+                                double* ico, long coef_stride, int nfun, int m_lo, int m_hi, int data_format) {
+    if (m_hi <= m_lo || nfun <= 0) return cudaSuccess;
+    int real_fmt = data_format == S2KIT_REAL;
+    int nc = pick_nc(p->bw, nfun, real_fmt);
+    int NF = nc / (real_fmt ? 2 : 4);
+    int rs = pick_rowsplit(p->bw, (nfun + NF - 1) / NF, m_hi - m_lo);
+    int slot = prof_begin(p, S2KIT_K_LEGENDRE_FWD);
+    cudaError_t e;
+    switch (nc) {
+        case 8: e = leg_fwd_nc<8>(p, table, shift, X, rco, ico, coef_stride, nfun, m_lo, m_hi, real_fmt, rs); break;
+        case 16: e = leg_fwd_nc<16>(p, table, shift, X, rco, ico, coef_stride, nfun, m_lo, m_hi, real_fmt, rs); break;
+        default: e = leg_fwd_nc<32>(p, table, shift, X, rco, ico, coef_stride, nfun, m_lo, m_hi, real_fmt, rs); break;
+    }
+    prof_end(p, slot);
+    return e;
+}
+
+cudaError_t launch_legendre_inv(s2kit_cuda_plan* p, const double* table, uint64_t shift, const double* rco,
+                                const double* ico, long coef_stride, double* V, int nfun, int m_lo, int m_hi,
+                                int data_format) {
+    if (m_hi <= m_lo || nfun <= 0) return cudaSuccess;
+    int real_fmt = data_format == S2KIT_REAL;
+    int nc = pick_nc(p->bw, nfun, real_fmt);
+    int NF = nc / (real_fmt ? 2 : 4);
+    int rs = pick_rowsplit(p->bw, (nfun + NF - 1) / NF, m_hi - m_lo);
+    int slot = prof_begin(p, S2KIT_K_LEGENDRE_INV);
+    cudaError_t e;
+    switch (nc) {
+        case 8: e = leg_inv_nc<8>(p, table, shift, rco, ico, coef_stride, V, nfun, m_lo, m_hi, real_fmt, rs); break;
+        case 16: e = leg_inv_nc<16>(p, table, shift, rco, ico, coef_stride, V, nfun, m_lo, m_hi, real_fmt, rs); break;
+        default: e = leg_inv_nc<32>(p, table, shift, rco, ico, coef_stride, V, nfun, m_lo, m_hi, real_fmt, rs); break;
+    }
+    prof_end(p, slot);
+    return e;
+}
+
+}  // namespace s2k

@@ -1,0 +1,260 @@
+// kernels_table.cu -- K7: device generation of the cosine-series tables of the associated Legendre functions.
+//
+// Replaces GenerateCosPmlTable                         src/legendre_polynomials/cospml.c:161-242
+// with recurrence coefficients from L2_an / L2_cn     src/legendre_polynomials/util/l2_norms.c:16-38
+// The bit-sensitive inputs -- Chebyshev nodes x_i = cos((2i+1) pi/2bw) (chebyshev_nodes.c:29-34) and the seeds
+// P~_m^m(theta_i) [/ sin theta_i for odd m] (pmm.c:21-33, cospml.c:181-192) -- are computed on the HOST with the
+// same libm and expression order as the reference and uploaded (trap 1).  The three-term
+// recurrence runs here with the reference's operation order and explicitly un-fused multiplies/adds
+// (cospml.c:218-221), so the sampled P~_l^m are bit-identical to the reference's; only the DCT differs in
+// rounding (FFTW there, the radix kernels of s2k_fft.cuh here).
+//
+// Work unit = (order m, LCH consecutive degrees starting at l0): bw/8 threads hold the bw samples of two
+// consecutive degrees in registers, roll the recurrence from l = m up to l0 (cheap), then per pair of
+// degrees run ONE complex FFT of length bw (two real DCT-IIs via even/odd reordering + conjugate symmetry)
+// and scatter the kept entries straight into the DMMA-tiled layout (s2k_internal.cuh).
+#include "s2k_fft.cuh"
+#include "s2k_internal.cuh"
+
+namespace s2k {
+
+__device__ __forceinline__ void rec_step(const double (&x)[8], double (&prev)[8], double (&cur)[8], double2 ac) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        double t1 = __dmul_rn(ac.y, prev[e]);
+        double t2 = __dmul_rn(cur[e], x[e]);
+        double t3 = __dmul_rn(ac.x, t2);
+        prev[e] = cur[e];
+        cur[e] = __dadd_rn(t3, t1);
+    }
+}
+
+__device__ __forceinline__ void tile_store(double* __restrict__ table, uint64_t order_tile0, const BlockMeta& mb,
+                                           const uint32_t* __restrict__ rt_start, int r, int c, double v) {
+    uint64_t tile = order_tile0 + rt_start[mb.rt_base + (r >> 3)] + (uint64_t)(c >> 3);
+    table[tile * 64 + tile_elem_offset(r & 7, c & 7)] = v;
+}
+
+template <int NB, int G>
+__global__ void __launch_bounds__(NB / 8 * G) k_table_gen(double* __restrict__ table,
+                                                          const uint64_t* __restrict__ order_start, uint64_t shift,
+                                                          const BlockMeta* __restrict__ meta,
+                                                          const uint32_t* __restrict__ rt_start,
+                                                          const int* __restrict__ units, int unit_lo, int unit_hi,
+                                                          int lch, const double* __restrict__ nodes,
+                                                          const double* __restrict__ seeds,
+                                                          const double2* __restrict__ rec,
+                                                          const double2* __restrict__ tw,
+                                                          const double2* __restrict__ qtab) {
+    constexpr int T8 = NB / 8, NP = fft_padded_len(NB);
+    extern __shared__ double smem[];
+    const int tid = threadIdx.x, g = tid / T8, t = tid % T8;
+    double* sre = smem + g * 2 * NP;
+    double* sim = sre + NP;
+    int u = unit_lo + blockIdx.x * G + g;
+    const bool live = u < unit_hi;
+    if (!live) u = unit_lo;
+    const int m = units[2 * u], l0 = units[2 * u + 1];
+    const BlockMeta mb0 = meta[2 * m], mb1 = meta[2 * m + 1];
+    const uint64_t tile0 = order_start[m] - shift;
+
+    double x[8], prev[8], cur[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        int p = t + e * T8;
+        int i = (p < NB / 2) ? 2 * p : 2 * (NB - 1 - p) + 1;  // even/odd reordering of the DCT input
+        x[e] = __ldg(nodes + i);
+        cur[e] = __ldg(seeds + (long)m * NB + i);
+        prev[e] = 0.0;
+    }
+    const double2* rc = rec + (long)m * NB;
+    for (int l = m; l < l0; ++l) rec_step(x, prev, cur, __ldg(rc + l));
+
+    const double fudge = 1.0 / sqrt((double)NB);  // cospml.c:206
+    for (int pair = 0; pair < lch / 2; ++pair) {
+        const int l = l0 + 2 * pair;
+        double xr[8], xi[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) xr[e] = cur[e];
+        if (l + 1 < NB) rec_step(x, prev, cur, __ldg(rc + l));
+#pragma unroll
+        for (int e = 0; e < 8; ++e) xi[e] = (l + 1 < NB) ? cur[e] : 0.0;
+        if (l + 2 < NB) rec_step(x, prev, cur, __ldg(rc + l + 1));
+
+        fft_block<NB>(xr, xi, sre, sim, t, tw);
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            int p = fft_pad(fft_out_index<NB>(e, t));
+            sre[p] = xr[e];
+            sim[p] = xi[e];
+        }
+        __syncthreads();
+        if (live && l < NB) {
+            // degree l keeps cosine indices of parity 0 (l0 - m is even), degree l+1 those of parity 1
+            const int ra = (l - m) >> 1;  // row inside either parity block
+            for (int k = t; k < NB; k += T8) {
+                const int pk = k & 1, c = k >> 1;
+                if (pk && l + 1 >= NB) continue;
+                const BlockMeta& mb = pk ? mb1 : mb0;
+                if (c >= mb.len0 + ra) continue;
+                int nk = (NB - k) & (NB - 1);
+                double ar = sre[fft_pad(k)], ai = sim[fft_pad(k)];
+                double br = sre[fft_pad(nk)], bi = sim[fft_pad(nk)];
+                double2 q = __ldg(qtab + k);
+                double y = pk ? (q.x * (ai + bi) - q.y * (ar - br)) : (q.x * (ar + br) + q.y * (ai - bi));
+                if (k == 0) y *= 0.70710678118654752440;  // cospml.c:205
+                tile_store(table, tile0, mb, rt_start, ra, c, y * fudge);
+            }
+        }
+    }
+}
+
+// Any bandwidth <= 1024: one CTA per order, thread i owns node i, DCT by the O(bw^2) definition.
+__global__ void k_table_gen_direct(double* __restrict__ table, const uint64_t* __restrict__ order_start, uint64_t shift,
+                                   const BlockMeta* __restrict__ meta, const uint32_t* __restrict__ rt_start, int m_lo,
+                                   int bw, const double* __restrict__ nodes, const double* __restrict__ seeds,
+                                   const double2* __restrict__ rec, const double2* __restrict__ qtab) {
+    extern __shared__ double sm[];
+    const int m = m_lo + blockIdx.x, i = threadIdx.x;
+    const BlockMeta mb0 = meta[2 * m], mb1 = meta[2 * m + 1];
+    const uint64_t tile0 = order_start[m] - shift;
+    double x = 0.0, prev = 0.0, cur = 0.0;
+    if (i < bw) {
+        x = nodes[i];
+        cur = seeds[(long)m * bw + i];
+    }
+    const double fudge = 1.0 / sqrt((double)bw);
+    for (int l = m; l < bw; ++l) {
+        if (i < bw) sm[i] = cur;
+        __syncthreads();
+        const int k = i, p = (l - m) & 1, r = (l - m) >> 1;
+        const BlockMeta& mb = p ? mb1 : mb0;
+        if (k < bw && (k & 1) == p && (k >> 1) < mb.len0 + r) {
+            double acc = 0.0;
+            for (int s = 0; s < bw; ++s) acc += sm[s] * qtab[(int)(((long)(2 * s + 1) * k) % (4 * bw))].x;
+            acc *= 2.0;
+            if (k == 0) acc *= 0.70710678118654752440;
+            tile_store(table, tile0, mb, rt_start, r, k >> 1, acc * fudge);
+        }
+        __syncthreads();
+        if (i < bw && l + 1 < bw) {
+            double2 ac = rec[(long)m * bw + l];
+            double t1 = __dmul_rn(ac.y, prev);
+            double t2 = __dmul_rn(cur, x);
+            double t3 = __dmul_rn(ac.x, t2);
+            prev = cur;
+            cur = __dadd_rn(t3, t1);
+        }
+    }
+}
+
+// (a_l^m, c_l^m), same expression order as l2_norms.c:16-38, every operation individually rounded
+__global__ void k_rec_coeffs(double2* __restrict__ rec, int bw) {
+    int l = blockIdx.x * blockDim.x + threadIdx.x, m = blockIdx.y;
+    if (l >= bw) return;
+    double2 out = make_double2(0.0, 0.0);
+    if (l >= m) {
+        double dl = (double)l;
+        double two_l = __dmul_rn(2.0, dl);
+        double lm1 = (double)(l - m) + 1.0;       // l - m + 1.
+        double lpm1 = (double)(l + m) + 1.0;      // l + m + 1.
+        double r1 = __ddiv_rn(two_l + 3.0, two_l + 1.0);
+        double r2 = __ddiv_rn(lm1, lpm1);
+        double a = __dmul_rn(__dsqrt_rn(__dmul_rn(r1, r2)), __ddiv_rn(two_l + 1.0, lm1));
+        double c = 0.0;
+        if (l != 0) {
+            double s1 = __ddiv_rn(two_l + 3.0, two_l - 1.0);
+            double s3 = __ddiv_rn((double)l - (double)m, (double)l + (double)m);
+            double prod = __dmul_rn(__dmul_rn(s1, r2), s3);
+            c = __dmul_rn(__dmul_rn(-1.0, __dsqrt_rn(prod)), __ddiv_rn((double)(l + m), lm1));
+        }
+        out = make_double2(a, c);
+    }
+    rec[(long)m * bw + l] = out;
+}
+
+// tile layout -> the reference's packed layout (rows l = m..bw-1, RowSize(m,l) entries each)
+__device__ __forceinline__ int packed_h(int l) {  // sum_{d<l} (d/2 + 1)
+    int h = (l / 2) * (l / 2 + 1);
+    return (l & 1) ? h + l / 2 + 1 : h;
+}
+
+__global__ void k_table_unpack(const double* __restrict__ table, const uint64_t* __restrict__ order_start,
+                               uint64_t shift, const BlockMeta* __restrict__ meta,
+                               const uint32_t* __restrict__ rt_start, int m, int bw, double* __restrict__ out) {
+    const int l = m + blockIdx.x;
+    const int p = (l - m) & 1, r = (l - m) >> 1;
+    const BlockMeta mb = meta[2 * m + p];
+    const int len = mb.len0 + r;
+    // TableOffset(m,l), cospml.c:123-134
+    const int row0 = (m & 1) ? packed_h(l - 1) - packed_h(m - 1) : packed_h(l) - packed_h(m);
+    const uint64_t tile0 = order_start[m] - shift;
+    for (int c = threadIdx.x; c < len; c += blockDim.x) {
+        uint64_t tile = tile0 + rt_start[mb.rt_base + (r >> 3)] + (uint64_t)(c >> 3);
+        out[row0 + c] = table[tile * 64 + tile_elem_offset(r & 7, c & 7)];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+template <int NB>
+static cudaError_t table_gen_nb(s2kit_cuda_plan* p, double* table, uint64_t shift, int unit_lo, int unit_hi, int lch) {
+    constexpr int T8 = NB / 8;
+    constexpr int G = (256 / T8) < 1 ? 1 : ((256 / T8) > 8 ? 8 : (256 / T8));
+    size_t smem = sizeof(double) * 2 * G * fft_padded_len(NB);
+    if (smem > 48 * 1024) {
+        cudaError_t e =
+            cudaFuncSetAttribute(k_table_gen<NB, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    int nunits = unit_hi - unit_lo;
+    k_table_gen<NB, G><<<(nunits + G - 1) / G, T8 * G, smem, p->stream>>>(
+        table, p->d_order_start, shift, p->d_meta, p->d_rt_start, p->d_units, unit_lo, unit_hi, lch, p->d_nodes,
+        p->d_seeds, p->d_rec, p->d_tw_b, p->d_q_b);
+    return cudaGetLastError();
+}
+
+int table_unit_rows(int bw) { return bw <= 512 ? 32 : 64; }
+
+cudaError_t launch_table_gen(s2kit_cuda_plan* p, double* table, uint64_t shift, int m_lo, int m_hi) {
+    if (m_hi <= m_lo) return cudaSuccess;
+    uint64_t t0 = p->h_order_start[m_lo], t1 = p->h_order_start[m_hi];
+    cudaError_t e = cudaMemsetAsync(table + (t0 - shift) * 64, 0, (t1 - t0) * 64 * sizeof(double), p->stream);
+    if (e != cudaSuccess) return e;
+    int slot = prof_begin(p, S2KIT_K_TABLE_GEN);
+    if (p->fast) {
+        int ulo = p->h_unit_first[m_lo], uhi = p->h_unit_first[m_hi], lch = table_unit_rows(p->bw);
+        switch (p->bw) {
+            case 16: e = table_gen_nb<16>(p, table, shift, ulo, uhi, lch); break;
+            case 32: e = table_gen_nb<32>(p, table, shift, ulo, uhi, lch); break;
+            case 64: e = table_gen_nb<64>(p, table, shift, ulo, uhi, lch); break;
+            case 128: e = table_gen_nb<128>(p, table, shift, ulo, uhi, lch); break;
+            case 256: e = table_gen_nb<256>(p, table, shift, ulo, uhi, lch); break;
+            case 512: e = table_gen_nb<512>(p, table, shift, ulo, uhi, lch); break;
+            case 1024: e = table_gen_nb<1024>(p, table, shift, ulo, uhi, lch); break;
+            case 2048: e = table_gen_nb<2048>(p, table, shift, ulo, uhi, lch); break;
+            default: e = cudaErrorInvalidValue;
+        }
+    } else {
+        int nt = ((p->bw + 31) / 32) * 32;
+        k_table_gen_direct<<<m_hi - m_lo, nt, sizeof(double) * p->bw, p->stream>>>(
+            table, p->d_order_start, shift, p->d_meta, p->d_rt_start, m_lo, p->bw, p->d_nodes, p->d_seeds, p->d_rec,
+            p->d_q_b);
+        e = cudaGetLastError();
+    }
+    prof_end(p, slot);
+    return e;
+}
+
+cudaError_t launch_table_unpack(s2kit_cuda_plan* p, const double* table, uint64_t shift, int m, double* out) {
+    k_table_unpack<<<p->bw - m, 128, 0, p->stream>>>(table, p->d_order_start, shift, p->d_meta, p->d_rt_start, m, p->bw,
+                                                     out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rec_coeffs(s2kit_cuda_plan* p) {
+    k_rec_coeffs<<<dim3((p->bw + 127) / 128, p->bw), 128, 0, p->stream>>>(p->d_rec, p->bw);
+    return cudaGetLastError();
+}
+
+}  // namespace s2k

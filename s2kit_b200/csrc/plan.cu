@@ -1,0 +1,749 @@
+// plan.cu -- plan object, table/workspace management and the s2kit_cuda_* C-ABI (include/s2kit_cuda.h).
+//
+// A plan owns everything the reference makes the caller carry around: the quadrature weights
+// (GenerateWeightsForDLT), the cosine tables (Spharmonic_Pml_Table & co., src/legendre_polynomials/cospml.c:387-518),
+// the FFT/DCT "plans" (FFTW descriptors in the reference) and the workspaces.  Device tables are generated
+// once per plan (Memo) or per call into a bounded scratch ring (Fly, the reference's O(bw^2)-memory
+// variant, src/FST_semi_fly.c:96,259-261).
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+
+#include "host_setup.h"
+#include "s2k_internal.cuh"
+
+static thread_local std::string g_last_error;
+
+static int fail(const char* what, cudaError_t e) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+    g_last_error = buf;
+    return 1;
+}
+static int fail_msg(const char* what) {
+    g_last_error = what;
+    return 2;
+}
+
+#define CK(call)                                                 \
+    do {                                                         \
+        cudaError_t e__ = (call);                                \
+        if (e__ != cudaSuccess) return fail(#call, e__);         \
+    } while (0)
+
+extern "C" const char* s2kit_cuda_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char* s2kit_cuda_version(void) { return "s2kit_b200 0.1 (sm_100a, FP64 DMMA)"; }
+
+// ------------------------------------------------------------------------------------------------ profiling
+namespace s2k {
+int prof_begin(s2kit_cuda_plan* p, int kind) {
+    if (!p->profiling) return -1;
+    if (p->prof_used == p->prof_slots.size()) {
+        ProfileSlot s;
+        cudaEventCreate(&s.a);
+        cudaEventCreate(&s.b);
+        s.kind = kind;
+        p->prof_slots.push_back(s);
+    }
+    int idx = (int)p->prof_used++;
+    p->prof_slots[idx].kind = kind;
+    cudaEventRecord(p->prof_slots[idx].a, p->stream);
+    return idx;
+}
+void prof_end(s2kit_cuda_plan* p, int slot) {
+    if (slot >= 0) cudaEventRecord(p->prof_slots[slot].b, p->stream);
+}
+}  // namespace s2k
+
+static void prof_collect(s2kit_cuda_plan* p) {
+    for (size_t i = 0; i < p->prof_used; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p->prof_slots[i].a, p->prof_slots[i].b) == cudaSuccess) {
+            p->prof_ms[p->prof_slots[i].kind] += ms;
+            p->prof_launches[p->prof_slots[i].kind] += 1;
+        }
+    }
+    p->prof_used = 0;
+}
+
+extern "C" int s2kit_cuda_profile_enable(s2kit_cuda_plan* p, int on) {
+    if (!p) return fail_msg("null plan");
+    p->profiling = on != 0;
+    return 0;
+}
+extern "C" int s2kit_cuda_profile_reset(s2kit_cuda_plan* p) {
+    if (!p) return fail_msg("null plan");
+    CK(cudaStreamSynchronize(p->stream));
+    p->prof_used = 0;
+    for (int k = 0; k < S2KIT_K_COUNT; ++k) {
+        p->prof_ms[k] = 0;
+        p->prof_launches[k] = 0;
+    }
+    return 0;
+}
+extern "C" int s2kit_cuda_profile_get(s2kit_cuda_plan* p, double* ms, long* launches) {
+    if (!p) return fail_msg("null plan");
+    CK(cudaStreamSynchronize(p->stream));
+    prof_collect(p);
+    for (int k = 0; k < S2KIT_K_COUNT; ++k) {
+        if (ms) ms[k] = p->prof_ms[k];
+        if (launches) launches[k] = p->prof_launches[k];
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ layout
+static int row_size(int m, int l) {  // RowSize, cospml.c:250-258
+    if (l < m) return 0;
+    return (m & 1) ? (l - 1) / 2 + 1 : l / 2 + 1;
+}
+
+static void build_layout(s2kit_cuda_plan* p, const std::vector<char>& owned) {
+    const int bw = p->bw;
+    p->h_meta.assign(2 * bw, s2k::BlockMeta{0, 0, 0, 0});
+    p->h_rt_start.clear();
+    p->h_order_start.assign(bw + 1, 0);
+    for (int m = 0; m < bw; ++m) {
+        uint32_t cur = 0;
+        for (int par = 0; par < 2; ++par) {
+            s2k::BlockMeta& mb = p->h_meta[2 * m + par];
+            int rows = (bw - m - par + 1) / 2;
+            if (rows < 0) rows = 0;
+            mb.rows = rows;
+            mb.len0 = row_size(m, m + par);
+            mb.nrt = (rows + 7) / 8;
+            mb.rt_base = (int)p->h_rt_start.size();
+            for (int rt = 0; rt < mb.nrt; ++rt) {
+                p->h_rt_start.push_back(cur);
+                int last_row = std::min(8 * rt + 7, rows - 1);
+                cur += (uint32_t)((mb.len0 + last_row + 7) >> 3);
+            }
+        }
+        p->h_order_start[m + 1] = p->h_order_start[m] + (owned[m] ? cur : 0);
+    }
+    const int lch = s2k::table_unit_rows(bw);
+    p->h_units.clear();
+    p->h_unit_first.assign(bw + 1, 0);
+    for (int m = 0; m < bw; ++m) {
+        p->h_unit_first[m] = (int)p->h_units.size() / 2;
+        for (int l0 = m; l0 < bw; l0 += lch) {
+            p->h_units.push_back(m);
+            p->h_units.push_back(l0);
+        }
+    }
+    p->h_unit_first[bw] = (int)p->h_units.size() / 2;
+}
+
+template <typename T>
+static cudaError_t upload(T** dptr, const void* host, size_t count) {
+    cudaError_t e = cudaMalloc((void**)dptr, count * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dptr, host, count * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+static int plan_create_impl(s2kit_cuda_plan** out, int bw, int variant, int max_batch, int device, int rank,
+                            int nranks) {
+    if (!out) return fail_msg("null output pointer");
+    *out = nullptr;
+    if (bw < 2 || bw > 2048) return fail_msg("bandwidth must be in [2, 2048]");
+    if (variant != S2KIT_CUDA_MEMO && variant != S2KIT_CUDA_FLY) return fail_msg("unknown variant");
+    int ndev = 0;
+    cudaError_t e0 = cudaGetDeviceCount(&ndev);
+    if (e0 != cudaSuccess || ndev == 0)
+        return fail_msg("no CUDA device available: s2kit_cuda has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail_msg("invalid device index");
+    CK(cudaSetDevice(device));
+
+    s2kit_cuda_plan* p = new s2kit_cuda_plan();
+    p->bw = bw;
+    p->n = 2 * bw;
+    p->variant = variant;
+    p->device = device;
+    p->rank = rank;
+    p->nranks = nranks;
+    p->fast = is_pow2(bw) && bw >= 16;
+    if (!p->fast && bw > 512) {
+        delete p;
+        return fail_msg("bandwidths above 512 must be powers of two");
+    }
+    CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    const int n = p->n;
+
+    // ---- host-computed seeds (libm), uploaded
+    {
+        std::vector<double> w(4 * bw), s(n), x(bw), tw(2 * (size_t)n), tb(2 * (size_t)bw), qn(8 * (size_t)n),
+            qb(8 * (size_t)bw);
+        s2k_host_weights(bw, w.data());
+        s2k_host_sines(bw, s.data());
+        s2k_host_nodes(bw, x.data());
+        s2k_host_twiddles(n, tw.data());
+        s2k_host_twiddles(bw, tb.data());
+        s2k_host_quarter(n, qn.data());
+        s2k_host_quarter(bw, qb.data());
+        CK(upload(&p->d_weights, w.data(), w.size()));
+        CK(upload(&p->d_sin, s.data(), s.size()));
+        CK(upload(&p->d_nodes, x.data(), x.size()));
+        CK(upload(&p->d_tw_n, tw.data(), (size_t)n));
+        CK(upload(&p->d_tw_b, tb.data(), (size_t)bw));
+        CK(upload(&p->d_q_n, qn.data(), 4 * (size_t)n));
+        CK(upload(&p->d_q_b, qb.data(), 4 * (size_t)bw));
+        std::vector<double> seeds((size_t)bw * bw);
+        s2k_host_seeds(bw, 0, bw, seeds.data());
+        CK(upload(&p->d_seeds, seeds.data(), seeds.size()));
+    }
+    CK(cudaMalloc((void**)&p->d_rec, sizeof(double2) * (size_t)bw * bw));
+
+    // ---- which orders this plan owns
+    std::vector<char> owned(bw, 1);
+    if (nranks > 1) {
+        std::fill(owned.begin(), owned.end(), 0);
+        // pair m with bw-1-m (work ~ bw^2 - m^2): pair q goes to rank q % nranks
+        for (int q = 0; q < (bw + 1) / 2; ++q) {
+            if (q % nranks != rank) continue;
+            owned[q] = 1;
+            owned[bw - 1 - q] = 1;
+        }
+    }
+    for (int m = 0; m < bw; ++m)
+        if (owned[m]) p->my_orders.push_back(m);
+    build_layout(p, owned);
+    CK(upload(&p->d_meta, p->h_meta.data(), p->h_meta.size()));
+    CK(upload(&p->d_rt_start, p->h_rt_start.data(), p->h_rt_start.size()));
+    CK(upload(&p->d_order_start, p->h_order_start.data(), p->h_order_start.size()));
+    CK(upload(&p->d_units, p->h_units.data(), p->h_units.size()));
+    CK(s2k::launch_rec_coeffs(p));
+
+    // ---- tables
+    const uint64_t total_tiles = p->h_order_start[bw];
+    if (variant == S2KIT_CUDA_MEMO) {
+        p->table_tiles = total_tiles;
+        p->table_bytes = total_tiles * 64 * sizeof(double);
+        CK(cudaMalloc((void**)&p->d_table, p->table_bytes));
+        // generate every run of consecutive owned orders
+        int m = 0;
+        while (m < bw) {
+            if (!owned[m]) {
+                ++m;
+                continue;
+            }
+            int hi = m;
+            while (hi < bw && owned[hi]) ++hi;
+            CK(s2k::launch_table_gen(p, p->d_table, 0, m, hi));
+            m = hi;
+        }
+    } else {
+        // Fly: scratch ring sized for the largest order (order 0) times a few, at most ~64 MiB so it stays in L2
+        uint64_t biggest = 0;
+        for (int m = 0; m < bw; ++m) biggest = std::max(biggest, p->h_order_start[m + 1] - p->h_order_start[m]);
+        uint64_t cap = std::max<uint64_t>(biggest, (64ull << 20) / 512);
+        p->fly_tiles = std::min<uint64_t>(cap, total_tiles);
+        p->table_bytes = p->fly_tiles * 64 * sizeof(double);
+        CK(cudaMalloc((void**)&p->d_table, p->table_bytes));
+    }
+
+    // ---- workspace
+    size_t per_fn = sizeof(double) * ((size_t)2 * n * n + (size_t)n * 2 * bw);
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    int chunk = std::max(1, max_batch);
+    size_t budget = free_b / 3;  // leave room for the caller's data
+    if ((size_t)chunk * per_fn > budget) chunk = (int)std::max<size_t>(1, budget / per_fn);
+    p->chunk = chunk;
+    CK(cudaMalloc((void**)&p->d_S, sizeof(double) * (size_t)chunk * 2 * n * n));
+    CK(cudaMalloc((void**)&p->d_X, sizeof(double) * (size_t)chunk * n * 2 * bw));
+    CK(cudaStreamSynchronize(p->stream));
+    *out = p;
+    return 0;
+}
+
+extern "C" int s2kit_cuda_plan_create(s2kit_cuda_plan** out, int bw, int variant, int max_batch, int device) {
+    return plan_create_impl(out, bw, variant, max_batch, device, 0, 1);
+}
+
+extern "C" int s2kit_cuda_plan_destroy(s2kit_cuda_plan* p) {
+    if (!p) return 0;
+    cudaSetDevice(p->device);
+    cudaStreamSynchronize(p->stream);
+    void* ptrs[] = {p->d_weights, p->d_sin,      p->d_tw_n,       p->d_tw_b, p->d_q_n,  p->d_q_b,
+                    p->d_nodes,   p->d_seeds,    p->d_rec,        p->d_table, p->d_meta, p->d_rt_start,
+                    p->d_order_start, p->d_units, p->d_S,          p->d_X,    p->d_coef, p->d_coef2,
+                    p->d_filt,    p->d_stage_grid, p->d_stage_coef};
+    for (void* q : ptrs)
+        if (q) cudaFree(q);
+    for (auto& s : p->prof_slots) {
+        cudaEventDestroy(s.a);
+        cudaEventDestroy(s.b);
+    }
+    if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+    return 0;
+}
+
+extern "C" int s2kit_cuda_plan_set_stream(s2kit_cuda_plan* p, void* stream) {
+    if (!p) return fail_msg("null plan");
+    CK(cudaStreamSynchronize(p->stream));
+    if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
+    p->stream = (cudaStream_t)stream;
+    p->own_stream = false;
+    return 0;
+}
+extern "C" void* s2kit_cuda_plan_stream(s2kit_cuda_plan* p) { return p ? (void*)p->stream : nullptr; }
+extern "C" int s2kit_cuda_synchronize(s2kit_cuda_plan* p) {
+    if (!p) return fail_msg("null plan");
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+extern "C" int s2kit_cuda_plan_bw(const s2kit_cuda_plan* p) { return p ? p->bw : 0; }
+extern "C" size_t s2kit_cuda_plan_table_bytes(const s2kit_cuda_plan* p) { return p ? p->table_bytes : 0; }
+
+// ------------------------------------------------------------------------------------------------ order groups
+// Memo: one group covering [0, bw) on the resident table.  Fly: groups that fit the scratch ring; the table
+// of each group is generated right before it is consumed.
+struct OrderGroup {
+    int lo, hi;
+    uint64_t shift;
+};
+
+static std::vector<OrderGroup> order_groups(const s2kit_cuda_plan* p, int m_lo, int m_hi) {
+    std::vector<OrderGroup> g;
+    if (p->variant == S2KIT_CUDA_MEMO) {
+        g.push_back({m_lo, m_hi, 0});
+        return g;
+    }
+    int m = m_lo;
+    while (m < m_hi) {
+        int hi = m + 1;
+        while (hi < m_hi && p->h_order_start[hi + 1] - p->h_order_start[m] <= p->fly_tiles) ++hi;
+        g.push_back({m, hi, p->h_order_start[m]});
+        m = hi;
+    }
+    return g;
+}
+
+static int ensure(double** ptr, size_t doubles) {
+    if (*ptr) return 0;
+    CK(cudaMalloc((void**)ptr, doubles * sizeof(double)));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ device paths
+static int fst_device(s2kit_cuda_plan* p, const double* rdata, const double* idata, double* rco, double* ico,
+                      int batch, long data_stride, long coef_stride, int fmt) {
+    const int bw = p->bw;
+    const int nrows = (fmt == S2KIT_REAL) ? bw : 2 * bw - 1;
+    for (int c0 = 0; c0 < batch; c0 += p->chunk) {
+        int nf = std::min(p->chunk, batch - c0);
+        const double* rd = rdata + (long)c0 * data_stride;
+        const double* id = idata + (long)c0 * data_stride;
+        double* rc = rco + (long)c0 * coef_stride;
+        double* ic = ico + (long)c0 * coef_stride;
+        CK(s2k::launch_phi_fft_fwd(p, rd, id, data_stride, p->d_S, nf, fmt));
+        CK(s2k::launch_dct_fwd(p, p->d_S, p->d_X, nf, 0, nrows, fmt));
+        for (const OrderGroup& g : order_groups(p, 0, bw)) {
+            if (p->variant == S2KIT_CUDA_FLY) CK(s2k::launch_table_gen(p, p->d_table, g.shift, g.lo, g.hi));
+            CK(s2k::launch_legendre_fwd(p, p->d_table, g.shift, p->d_X, rc, ic, coef_stride, nf, g.lo, g.hi, fmt));
+        }
+    }
+    return 0;
+}
+
+static int inv_fst_device(s2kit_cuda_plan* p, const double* rco, const double* ico, double* rdata, double* idata,
+                          int batch, long coef_stride, long data_stride, int fmt) {
+    const int bw = p->bw;
+    const int nrows = (fmt == S2KIT_REAL) ? bw : 2 * bw - 1;
+    for (int c0 = 0; c0 < batch; c0 += p->chunk) {
+        int nf = std::min(p->chunk, batch - c0);
+        const double* rc = rco + (long)c0 * coef_stride;
+        const double* ic = ico + (long)c0 * coef_stride;
+        double* rd = rdata + (long)c0 * data_stride;
+        double* id = idata + (long)c0 * data_stride;
+        for (const OrderGroup& g : order_groups(p, 0, bw)) {
+            if (p->variant == S2KIT_CUDA_FLY) CK(s2k::launch_table_gen(p, p->d_table, g.shift, g.lo, g.hi));
+            CK(s2k::launch_legendre_inv(p, p->d_table, g.shift, rc, ic, coef_stride, p->d_X, nf, g.lo, g.hi, fmt));
+        }
+        CK(s2k::launch_dct_inv(p, p->d_X, p->d_S, nf, 0, nrows, fmt));
+        CK(s2k::launch_phi_fft_inv(p, p->d_S, rd, id, data_stride, nf, fmt));
+    }
+    return 0;
+}
+
+static int fzt_device(s2kit_cuda_plan* p, const double* rdata, const double* idata, double* rres, double* ires,
+                      int batch, long data_stride, long res_stride, int fmt) {
+    const int bw = p->bw;
+    for (int c0 = 0; c0 < batch; c0 += p->chunk) {
+        int nf = std::min(p->chunk, batch - c0);
+        CK(s2k::launch_zonal_rowsum(p, rdata + (long)c0 * data_stride, idata + (long)c0 * data_stride, data_stride,
+                                    p->d_S, nf));
+        CK(s2k::launch_dct_fwd(p, p->d_S, p->d_X, nf, 0, 1, S2KIT_COMPLEX));
+        double* rr = rres + (long)c0 * res_stride;
+        double* ir = ires + (long)c0 * res_stride;
+        for (const OrderGroup& g : order_groups(p, 0, 1)) {
+            if (p->variant == S2KIT_CUDA_FLY) CK(s2k::launch_table_gen(p, p->d_table, g.shift, g.lo, g.hi));
+            // order 0 lands at positions l of the output (IndexOfHarmonicCoeff(0,l) = l)
+            CK(s2k::launch_legendre_fwd(p, p->d_table, g.shift, p->d_X, rr, ir, res_stride, nf, 0, 1, S2KIT_COMPLEX));
+        }
+        if (fmt == S2KIT_REAL)  // FST_semi_memo.c:405-406 (bw entries; the reference clears 2bw)
+            CK(cudaMemset2DAsync(ir, res_stride * sizeof(double), 0, bw * sizeof(double), nf, p->stream));
+    }
+    return 0;
+}
+
+static int conv_device(s2kit_cuda_plan* p, const double* rdata, const double* idata, const double* rfilter,
+                       const double* ifilter, double* rres, double* ires, int batch, long data_stride,
+                       long filter_stride) {
+    const int bw = p->bw;
+    const long cs = (long)bw * bw;
+    if (ensure(&p->d_coef, (size_t)p->chunk * 2 * cs)) return 1;
+    if (ensure(&p->d_coef2, (size_t)p->chunk * 2 * cs)) return 1;
+    if (ensure(&p->d_filt, (size_t)p->chunk * 2 * bw)) return 1;
+    double* fr = p->d_coef;
+    double* fi = p->d_coef + (size_t)p->chunk * cs;
+    double* tr = p->d_coef2;
+    double* ti = p->d_coef2 + (size_t)p->chunk * cs;
+    double* hr = p->d_filt;
+    double* hi = p->d_filt + (size_t)p->chunk * bw;
+    for (int c0 = 0; c0 < batch; c0 += p->chunk) {
+        int nf = std::min(p->chunk, batch - c0);
+        // ConvOn2SphereSemiMemo, FST_semi_memo.c:502-508: everything in REAL format, cutoff = bw
+        if (filter_stride != 0 || c0 == 0) {
+            int nfilt = filter_stride ? nf : 1;
+            if (fzt_device(p, rfilter + (long)c0 * filter_stride, ifilter + (long)c0 * filter_stride, hr, hi, nfilt,
+                           filter_stride ? filter_stride : (long)p->n * p->n, bw, S2KIT_REAL))
+                return 1;
+        }
+        if (fst_device(p, rdata + (long)c0 * data_stride, idata + (long)c0 * data_stride, fr, fi, nf, data_stride, cs,
+                       S2KIT_REAL))
+            return 1;
+        CK(s2k::launch_spectral_mul(p, fr, fi, cs, hr, hi, filter_stride ? bw : 0, tr, ti, cs, nf));
+        if (inv_fst_device(p, tr, ti, rres + (long)c0 * data_stride, ires + (long)c0 * data_stride, nf, cs,
+                           data_stride, S2KIT_REAL))
+            return 1;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ host staging
+static cudaError_t copy_in(double* dst, long dst_pitch, const double* src, long src_stride, long len, int count,
+                           cudaStream_t s) {
+    return cudaMemcpy2DAsync(dst, dst_pitch * sizeof(double), src, src_stride * sizeof(double), len * sizeof(double),
+                             count, cudaMemcpyHostToDevice, s);
+}
+static cudaError_t copy_out(double* dst, long dst_stride, const double* src, long src_pitch, long len, int count,
+                            cudaStream_t s) {
+    return cudaMemcpy2DAsync(dst, dst_stride * sizeof(double), src, src_pitch * sizeof(double), len * sizeof(double),
+                             count, cudaMemcpyDeviceToHost, s);
+}
+
+static int check_common(s2kit_cuda_plan* p, int batch, int fmt) {
+    if (!p) return fail_msg("null plan");
+    if (batch < 0) return fail_msg("negative batch");
+    if (fmt != S2KIT_COMPLEX && fmt != S2KIT_REAL) return fail_msg("unknown data format");
+    if (cudaSetDevice(p->device) != cudaSuccess) return fail_msg("cudaSetDevice failed");
+    return 0;
+}
+
+extern "C" int s2kit_cuda_fst(s2kit_cuda_plan* p, const double* rdata, const double* idata, double* rco, double* ico,
+                              int batch, long data_stride, long coef_stride, int fmt, int where) {
+    if (int r = check_common(p, batch, fmt)) return r;
+    if (batch == 0) return 0;
+    if (where == S2KIT_CUDA_DEVICE) return fst_device(p, rdata, idata, rco, ico, batch, data_stride, coef_stride, fmt);
+    const long gs = (long)p->n * p->n, cs = (long)p->bw * p->bw;
+    if (ensure(&p->d_stage_grid, (size_t)p->chunk * 2 * gs)) return 1;
+    if (ensure(&p->d_stage_coef, (size_t)p->chunk * 2 * cs)) return 1;
+    double *gr = p->d_stage_grid, *gi = gr + (size_t)p->chunk * gs;
+    double *cr = p->d_stage_coef, *ci = cr + (size_t)p->chunk * cs;
+    for (int c0 = 0; c0 < batch; c0 += p->chunk) {
+        int nf = std::min(p->chunk, batch - c0);
+        CK(copy_in(gr, gs, rdata + (long)c0 * data_stride, data_stride, gs, nf, p->stream));
+        CK(copy_in(gi, gs, idata + (long)c0 * data_stride, data_stride, gs, nf, p->stream));
+        if (fst_device(p, gr, gi, cr, ci, nf, gs, cs, fmt)) return 1;
+        CK(copy_out(rco + (long)c0 * coef_stride, coef_stride, cr, cs, cs, nf, p->stream));
+        CK(copy_out(ico + (long)c0 * coef_stride, coef_stride, ci, cs, cs, nf, p->stream));
+        CK(cudaStreamSynchronize(p->stream));
+    }
+    return 0;
+}
+
+extern "C" int s2kit_cuda_inv_fst(s2kit_cuda_plan* p, const double* rco, const double* ico, double* rdata,
+                                  double* idata, int batch, long coef_stride, long data_stride, int fmt, int where) {
+    if (int r = check_common(p, batch, fmt)) return r;
+    if (batch == 0) return 0;
+    if (where == S2KIT_CUDA_DEVICE)
+        return inv_fst_device(p, rco, ico, rdata, idata, batch, coef_stride, data_stride, fmt);
+    const long gs = (long)p->n * p->n, cs = (long)p->bw * p->bw;
+    if (ensure(&p->d_stage_grid, (size_t)p->chunk * 2 * gs)) return 1;
+    if (ensure(&p->d_stage_coef, (size_t)p->chunk * 2 * cs)) return 1;
+    double *gr = p->d_stage_grid, *gi = gr + (size_t)p->chunk * gs;
+    double *cr = p->d_stage_coef, *ci = cr + (size_t)p->chunk * cs;
+    for (int c0 = 0; c0 < batch; c0 += p->chunk) {
+        int nf = std::min(p->chunk, batch - c0);
+        CK(copy_in(cr, cs, rco + (long)c0 * coef_stride, coef_stride, cs, nf, p->stream));
+        CK(copy_in(ci, cs, ico + (long)c0 * coef_stride, coef_stride, cs, nf, p->stream));
+        if (inv_fst_device(p, cr, ci, gr, gi, nf, cs, gs, fmt)) return 1;
+        CK(copy_out(rdata + (long)c0 * data_stride, data_stride, gr, gs, gs, nf, p->stream));
+        CK(copy_out(idata + (long)c0 * data_stride, data_stride, gi, gs, gs, nf, p->stream));
+        CK(cudaStreamSynchronize(p->stream));
+    }
+    return 0;
+}
+
+extern "C" int s2kit_cuda_fzt(s2kit_cuda_plan* p, const double* rdata, const double* idata, double* rres, double* ires,
+                              int batch, long data_stride, long res_stride, int fmt, int where) {
+    if (int r = check_common(p, batch, fmt)) return r;
+    if (batch == 0) return 0;
+    if (where == S2KIT_CUDA_DEVICE) return fzt_device(p, rdata, idata, rres, ires, batch, data_stride, res_stride, fmt);
+    const long gs = (long)p->n * p->n;
+    const int bw = p->bw;
+    if (ensure(&p->d_stage_grid, (size_t)p->chunk * 2 * gs)) return 1;
+    if (ensure(&p->d_filt, (size_t)p->chunk * 2 * bw)) return 1;
+    double *gr = p->d_stage_grid, *gi = gr + (size_t)p->chunk * gs;
+    double *hr = p->d_filt, *hi = hr + (size_t)p->chunk * bw;
+    for (int c0 = 0; c0 < batch; c0 += p->chunk) {
+        int nf = std::min(p->chunk, batch - c0);
+        CK(copy_in(gr, gs, rdata + (long)c0 * data_stride, data_stride, gs, nf, p->stream));
+        CK(copy_in(gi, gs, idata + (long)c0 * data_stride, data_stride, gs, nf, p->stream));
+        if (fzt_device(p, gr, gi, hr, hi, nf, gs, bw, fmt)) return 1;
+        CK(copy_out(rres + (long)c0 * res_stride, res_stride, hr, bw, bw, nf, p->stream));
+        CK(copy_out(ires + (long)c0 * res_stride, res_stride, hi, bw, bw, nf, p->stream));
+        CK(cudaStreamSynchronize(p->stream));
+    }
+    return 0;
+}
+
+extern "C" int s2kit_cuda_conv(s2kit_cuda_plan* p, const double* rdata, const double* idata, const double* rfilter,
+                               const double* ifilter, double* rres, double* ires, int batch, long data_stride,
+                               long filter_stride, int where) {
+    if (int r = check_common(p, batch, S2KIT_REAL)) return r;
+    if (batch == 0) return 0;
+    if (where == S2KIT_CUDA_DEVICE)
+        return conv_device(p, rdata, idata, rfilter, ifilter, rres, ires, batch, data_stride, filter_stride);
+    // host pointers: stage signal and filter grids, run on the device, copy the result grids back
+    const long gs = (long)p->n * p->n;
+    double* d = nullptr;
+    CK(cudaMalloc((void**)&d, sizeof(double) * 6 * (size_t)gs));
+    double *sr = d, *si = d + gs, *fr = d + 2 * gs, *fi = d + 3 * gs, *orr = d + 4 * gs, *oi = d + 5 * gs;
+    int rc = 0;
+    for (int f = 0; f < batch && !rc; ++f) {
+        cudaError_t e = cudaMemcpyAsync(sr, rdata + (long)f * data_stride, gs * 8, cudaMemcpyHostToDevice, p->stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(si, idata + (long)f * data_stride, gs * 8, cudaMemcpyHostToDevice, p->stream);
+        if (e == cudaSuccess && (f == 0 || filter_stride != 0)) {
+            e = cudaMemcpyAsync(fr, rfilter + (long)f * filter_stride, gs * 8, cudaMemcpyHostToDevice, p->stream);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(fi, ifilter + (long)f * filter_stride, gs * 8, cudaMemcpyHostToDevice, p->stream);
+        }
+        if (e != cudaSuccess) {
+            rc = fail("conv H2D", e);
+            break;
+        }
+        rc = conv_device(p, sr, si, fr, fi, orr, oi, 1, gs, gs);
+        if (rc) break;
+        e = cudaMemcpyAsync(rres + (long)f * data_stride, orr, gs * 8, cudaMemcpyDeviceToHost, p->stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(ires + (long)f * data_stride, oi, gs * 8, cudaMemcpyDeviceToHost, p->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+        if (e != cudaSuccess) rc = fail("conv D2H", e);
+    }
+    cudaFree(d);
+    return rc;
+}
+
+extern "C" int s2kit_cuda_trans_mult(s2kit_cuda_plan* p, const double* rd, const double* id, const double* rf,
+                                     const double* ifl, double* rres, double* ires, int batch, long coef_stride,
+                                     int where) {
+    if (int r = check_common(p, batch, S2KIT_COMPLEX)) return r;
+    if (batch == 0) return 0;
+    const int bw = p->bw;
+    const long cs = (long)bw * bw;
+    if (where == S2KIT_CUDA_DEVICE) {
+        CK(s2k::launch_spectral_mul(p, rd, id, coef_stride, rf, ifl, bw, rres, ires, coef_stride, batch));
+        return 0;
+    }
+    double* d = nullptr;
+    CK(cudaMalloc((void**)&d, sizeof(double) * (4 * (size_t)cs + 2 * bw)));
+    double *a = d, *b = d + cs, *c = d + 2 * cs, *e2 = d + 3 * cs, *hr = d + 4 * cs, *hi = hr + bw;
+    int rc = 0;
+    for (int f = 0; f < batch && !rc; ++f) {
+        cudaMemcpyAsync(a, rd + (long)f * coef_stride, cs * 8, cudaMemcpyHostToDevice, p->stream);
+        cudaMemcpyAsync(b, id + (long)f * coef_stride, cs * 8, cudaMemcpyHostToDevice, p->stream);
+        cudaMemcpyAsync(hr, rf + (long)f * bw, bw * 8, cudaMemcpyHostToDevice, p->stream);
+        cudaMemcpyAsync(hi, ifl + (long)f * bw, bw * 8, cudaMemcpyHostToDevice, p->stream);
+        cudaError_t e = s2k::launch_spectral_mul(p, a, b, cs, hr, hi, bw, c, e2, cs, 1);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(rres + (long)f * coef_stride, c, cs * 8, cudaMemcpyDeviceToHost, p->stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(ires + (long)f * coef_stride, e2, cs * 8, cudaMemcpyDeviceToHost, p->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+        if (e != cudaSuccess) rc = fail("trans_mult", e);
+    }
+    cudaFree(d);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ 1-D entry points
+// DLTSemi / InvDLTSemi on ncols independent real columns of one order: columns are fed through the batched
+// kernels as the real parts of ncols "functions" whose imaginary parts are zero.
+extern "C" int s2kit_cuda_dlt_semi(s2kit_cuda_plan* p, const double* data, int m, double* result, int ncols, int where) {
+    if (int r = check_common(p, ncols, S2KIT_COMPLEX)) return r;
+    if (m < 0 || m >= p->bw) return fail_msg("order out of range");
+    if (ncols == 0) return 0;
+    const int bw = p->bw, n = p->n;
+    const long cs = (long)bw * bw;
+    double *dcoef = nullptr;
+    CK(cudaMalloc((void**)&dcoef, sizeof(double) * 2 * (size_t)cs));
+    int rc = 0;
+    for (int c = 0; c < ncols && !rc; ++c) {
+        // place the column as order row m of function 0 (real part), imaginary part zero
+        cudaError_t e = cudaMemsetAsync(p->d_S, 0, sizeof(double) * 2 * (size_t)n * n, p->stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(p->d_S + (size_t)m * n, data + (long)c * n, n * 8,
+                                where == S2KIT_CUDA_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                                p->stream);
+        if (e == cudaSuccess) e = s2k::launch_dct_fwd(p, p->d_S, p->d_X, 1, m, m + 1, S2KIT_COMPLEX);
+        for (const OrderGroup& g : order_groups(p, m, m + 1)) {
+            if (e == cudaSuccess && p->variant == S2KIT_CUDA_FLY) e = s2k::launch_table_gen(p, p->d_table, g.shift, g.lo, g.hi);
+            if (e == cudaSuccess)
+                e = s2k::launch_legendre_fwd(p, p->d_table, g.shift, p->d_X, dcoef, dcoef + cs, cs, 1, m, m + 1,
+                                             S2KIT_REAL);
+        }
+        long at = (long)m * bw - ((long)m * (m - 1)) / 2;
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(result + (long)c * (bw - m), dcoef + at, (bw - m) * 8,
+                                where == S2KIT_CUDA_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                                p->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+        if (e != cudaSuccess) rc = fail("dlt_semi", e);
+    }
+    cudaFree(dcoef);
+    return rc;
+}
+
+extern "C" int s2kit_cuda_inv_dlt_semi(s2kit_cuda_plan* p, const double* coeffs, int m, double* result, int ncols,
+                                       int where) {
+    if (int r = check_common(p, ncols, S2KIT_COMPLEX)) return r;
+    if (m < 0 || m >= p->bw) return fail_msg("order out of range");
+    if (ncols == 0) return 0;
+    const int bw = p->bw, n = p->n;
+    const long cs = (long)bw * bw;
+    double* dcoef = nullptr;
+    CK(cudaMalloc((void**)&dcoef, sizeof(double) * 2 * (size_t)cs));
+    int rc = 0;
+    const double undo = sqrt(2.0 * M_PI);  // K5 folds in the 1/sqrt(2 pi) of InvFST; DLT alone has none
+    for (int c = 0; c < ncols && !rc; ++c) {
+        cudaError_t e = cudaMemsetAsync(dcoef, 0, sizeof(double) * 2 * (size_t)cs, p->stream);
+        long at = (long)m * bw - ((long)m * (m - 1)) / 2;
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(dcoef + at, coeffs + (long)c * (bw - m), (bw - m) * 8,
+                                where == S2KIT_CUDA_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                                p->stream);
+        for (const OrderGroup& g : order_groups(p, m, m + 1)) {
+            if (e == cudaSuccess && p->variant == S2KIT_CUDA_FLY) e = s2k::launch_table_gen(p, p->d_table, g.shift, g.lo, g.hi);
+            if (e == cudaSuccess)
+                e = s2k::launch_legendre_inv(p, p->d_table, g.shift, dcoef, dcoef + cs, cs, p->d_X, 1, m, m + 1,
+                                             S2KIT_REAL);
+        }
+        if (e == cudaSuccess) e = s2k::launch_dct_inv(p, p->d_X, p->d_S, 1, m, m + 1, S2KIT_COMPLEX);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+        if (e != cudaSuccess) {
+            rc = fail("inv_dlt_semi", e);
+            break;
+        }
+        std::vector<double> row(n);
+        e = cudaMemcpy(row.data(), p->d_S + (size_t)m * n, n * 8, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            rc = fail("inv_dlt_semi D2H", e);
+            break;
+        }
+        for (int j = 0; j < n; ++j) row[j] *= undo;
+        e = cudaMemcpy(result + (long)c * n, row.data(), n * 8,
+                       where == S2KIT_CUDA_DEVICE ? cudaMemcpyHostToDevice : cudaMemcpyHostToHost);
+        if (e != cudaSuccess) rc = fail("inv_dlt_semi out", e);
+    }
+    cudaFree(dcoef);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ tables
+static int table_to_host(s2kit_cuda_plan* p, const double* table, uint64_t shift, int m, double* host_out) {
+    int size = 0;
+    for (int l = m; l < p->bw; ++l) size += row_size(m, l);
+    double* d = nullptr;
+    CK(cudaMalloc((void**)&d, sizeof(double) * (size_t)size));
+    cudaError_t e = s2k::launch_table_unpack(p, table, shift, m, d);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host_out, d, sizeof(double) * (size_t)size, cudaMemcpyDeviceToHost, p->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail("table export", e);
+    return 0;
+}
+
+extern "C" int s2kit_cuda_table_export(s2kit_cuda_plan* p, int m, double* host_out) {
+    if (int r = check_common(p, 0, S2KIT_COMPLEX)) return r;
+    if (m < 0 || m >= p->bw) return fail_msg("order out of range");
+    if (p->variant != S2KIT_CUDA_MEMO) return s2kit_cuda_table_generate(p, m, host_out);
+    if (p->h_order_start[m + 1] == p->h_order_start[m]) return fail_msg("order not resident on this rank");
+    return table_to_host(p, p->d_table, 0, m, host_out);
+}
+
+extern "C" int s2kit_cuda_table_generate(s2kit_cuda_plan* p, int m, double* host_out) {
+    if (int r = check_common(p, 0, S2KIT_COMPLEX)) return r;
+    if (m < 0 || m >= p->bw) return fail_msg("order out of range");
+    uint64_t tiles = 0;
+    {
+        // size of order m in a full layout (independent of ownership)
+        for (int par = 0; par < 2; ++par) {
+            const s2k::BlockMeta& mb = p->h_meta[2 * m + par];
+            for (int rt = 0; rt < mb.nrt; ++rt)
+                tiles += (uint64_t)((mb.len0 + std::min(8 * rt + 7, mb.rows - 1) + 7) >> 3);
+        }
+    }
+    if (p->h_order_start[m + 1] - p->h_order_start[m] != tiles)
+        return fail_msg("order not owned by this rank");
+    double* scratch = nullptr;
+    CK(cudaMalloc((void**)&scratch, tiles * 64 * sizeof(double)));
+    uint64_t shift = p->h_order_start[m];
+    cudaError_t e = s2k::launch_table_gen(p, scratch, shift, m, m + 1);
+    int rc = 0;
+    if (e != cudaSuccess)
+        rc = fail("table generate", e);
+    else
+        rc = table_to_host(p, scratch, shift, m, host_out);
+    cudaFree(scratch);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ measurement
+extern "C" int s2kit_cuda_measure_fp64_peak(int device, double* fma_tflops, double* dmma_tflops) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail_msg("no CUDA device available");
+    CK(cudaSetDevice(device));
+    double a = 0, b = 0;
+    CK(s2k::measure_fp64(&a, &b));
+    if (fma_tflops) *fma_tflops = a;
+    if (dmma_tflops) *dmma_tflops = b;
+    return 0;
+}
+
+extern "C" int s2kit_cuda_measure_copy_bw(int device, size_t bytes, double* gbs) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail_msg("no CUDA device available");
+    CK(cudaSetDevice(device));
+    double v = 0;
+    CK(s2k::measure_copy(bytes, &v));
+    if (gbs) *gbs = v;
+    return 0;
+}
+
+extern "C" void* s2kit_cuda_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void s2kit_cuda_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}

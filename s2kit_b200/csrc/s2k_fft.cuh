@@ -1,0 +1,173 @@
+// s2k_fft.cuh -- block-level FP64 complex FFT building block for sm_100a.
+//
+// Replaces FFTW's role in the reference (fftw_execute_split_dft at src/FST_semi_memo.c:81,350 and the
+// REDFT10/REDFT01 plans at src/legendre_transform/seminaive.c:107,170, src/legendre_polynomials/cospml.c:203-224).
+//
+// Design: a length-N transform (N = 2^k, 8 <= N <= 4096) is owned by N/8 threads; every thread keeps
+// 8 complex points in registers for the whole transform.  Passes are Stockham autosort radix-8 (plus one
+// final radix-2/4 pass when log2 N is not a multiple of 3), so the result comes out in natural order and
+// the first pass reads / the last pass leaves the SAME eight slots {t + s*N/8}: the first pass can be fed
+// straight from global memory and the last pass can be consumed straight from registers.  Between
+// passes the points are exchanged through shared memory (split re/im arrays, index padded by i>>4, which
+// keeps the 64-bit accesses of all passes within 1.25x of conflict-free).  Twiddles come from a
+// host-computed exact table W[q] = (cos 2 pi q/N, -sin 2 pi q/N).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace s2k {
+
+__host__ __device__ constexpr int fft_pad(int i) { return i + (i >> 4); }
+__host__ __device__ constexpr int fft_padded_len(int n) { return n + (n >> 4) + 1; }
+
+__host__ __device__ constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n >> 1); }
+// last-pass radix: 8 if log2 N % 3 == 0, else 2 or 4
+__host__ __device__ constexpr int fft_last_radix(int n) {
+    return (ilog2(n) % 3 == 0) ? 8 : (1 << (ilog2(n) % 3));
+}
+__host__ __device__ constexpr int fft_num_r8(int n) { return ilog2(n) / 3; }
+
+// ---- small in-register DFTs (forward sign), natural order out
+__device__ __forceinline__ void dft2(double* xr, double* xi) {
+    double ar = xr[0], ai = xi[0];
+    xr[0] = ar + xr[1]; xi[0] = ai + xi[1];
+    xr[1] = ar - xr[1]; xi[1] = ai - xi[1];
+}
+
+__device__ __forceinline__ void dft4(double* xr, double* xi) {
+    double t0r = xr[0] + xr[2], t0i = xi[0] + xi[2];
+    double t1r = xr[0] - xr[2], t1i = xi[0] - xi[2];
+    double t2r = xr[1] + xr[3], t2i = xi[1] + xi[3];
+    // (x1 - x3) * (-i) = (im, -re)
+    double t3r = xi[1] - xi[3], t3i = xr[3] - xr[1];
+    xr[0] = t0r + t2r; xi[0] = t0i + t2i;
+    xr[2] = t0r - t2r; xi[2] = t0i - t2i;
+    xr[1] = t1r + t3r; xi[1] = t1i + t3i;
+    xr[3] = t1r - t3r; xi[3] = t1i - t3i;
+}
+
+__device__ __forceinline__ void dft8(double* xr, double* xi) {
+    constexpr double H = 0.70710678118654752440;
+    double er[4] = {xr[0], xr[2], xr[4], xr[6]}, ei[4] = {xi[0], xi[2], xi[4], xi[6]};
+    double orr[4] = {xr[1], xr[3], xr[5], xr[7]}, oi[4] = {xi[1], xi[3], xi[5], xi[7]};
+    dft4(er, ei);
+    dft4(orr, oi);
+    // odd part times w8^k: w8 = (1 - i)/sqrt2, w8^2 = -i, w8^3 = (-1 - i)/sqrt2
+    double r1 = (orr[1] + oi[1]) * H, i1 = (oi[1] - orr[1]) * H;
+    double r2 = oi[2], i2 = -orr[2];
+    double r3 = (oi[3] - orr[3]) * H, i3 = -(orr[3] + oi[3]) * H;
+    xr[0] = er[0] + orr[0]; xi[0] = ei[0] + oi[0];
+    xr[4] = er[0] - orr[0]; xi[4] = ei[0] - oi[0];
+    xr[1] = er[1] + r1; xi[1] = ei[1] + i1;
+    xr[5] = er[1] - r1; xi[5] = ei[1] - i1;
+    xr[2] = er[2] + r2; xi[2] = ei[2] + i2;
+    xr[6] = er[2] - r2; xi[6] = ei[2] - i2;
+    xr[3] = er[3] + r3; xi[3] = ei[3] + i3;
+    xr[7] = er[3] - r3; xi[7] = ei[3] - i3;
+}
+
+template <int R>
+__device__ __forceinline__ void dftR(double* xr, double* xi) {
+    if constexpr (R == 8) dft8(xr, xi);
+    else if constexpr (R == 4) dft4(xr, xi);
+    else dft2(xr, xi);
+}
+
+// Register e of a pass with radix R belongs to butterfly q = e / R, leg r = e % R and sits at slot
+// s = q + (8/R) r, i.e. at index t + s * N/8.
+template <int R>
+__host__ __device__ constexpr int fft_slot(int e) { return (e / R) + (8 / R) * (e % R); }
+
+// natural index of register e after the whole transform / before the first pass (first radix is 8)
+template <int N>
+__device__ __forceinline__ int fft_out_index(int e, int t) {
+    constexpr int R = fft_last_radix(N);
+    return t + fft_slot<R>(e) * (N / 8);
+}
+template <int N>
+__device__ __forceinline__ int fft_in_index(int e, int t) { return t + e * (N / 8); }
+
+template <int N, int NS, int R>
+__device__ __forceinline__ void fft_pass_compute(double (&xr)[8], double (&xi)[8], int t,
+                                                 const double2* __restrict__ tw) {
+    constexpr int T8 = N / 8, NB = 8 / R, STEP = N / (NS * R);
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+        if constexpr (NS > 1) {
+            int k = (t + q * T8) & (NS - 1);
+#pragma unroll
+            for (int r = 1; r < R; ++r) {
+                double2 w = __ldg(&tw[k * r * STEP]);
+                double a = xr[q * R + r], b = xi[q * R + r];
+                xr[q * R + r] = a * w.x - b * w.y;
+                xi[q * R + r] = a * w.y + b * w.x;
+            }
+        }
+        dftR<R>(&xr[q * R], &xi[q * R]);
+    }
+}
+
+template <int N, int NS, int R>
+__device__ __forceinline__ void fft_pass_write(const double (&xr)[8], const double (&xi)[8], double* sre,
+                                               double* sim, int t) {
+    constexpr int T8 = N / 8, NB = 8 / R;
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+        int j = t + q * T8;
+        int k = j & (NS - 1);
+        int base = (j - k) * R + k;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            int p = fft_pad(base + r * NS);
+            sre[p] = xr[q * R + r];
+            sim[p] = xi[q * R + r];
+        }
+    }
+}
+
+template <int N, int R>
+__device__ __forceinline__ void fft_pass_read(double (&xr)[8], double (&xi)[8], const double* sre,
+                                              const double* sim, int t) {
+    constexpr int T8 = N / 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        int p = fft_pad(t + fft_slot<R>(e) * T8);
+        xr[e] = sre[p];
+        xi[e] = sim[p];
+    }
+}
+
+template <int N, int NS, int LEFT>
+struct FftRest {
+    // LEFT = number of radix-8 passes still to run after the first one
+    __device__ static __forceinline__ void run(double (&xr)[8], double (&xi)[8], double* sre, double* sim, int t,
+                                               const double2* __restrict__ tw) {
+        if constexpr (LEFT > 0) {
+            __syncthreads();
+            fft_pass_write<N, NS / 8, 8>(xr, xi, sre, sim, t);
+            __syncthreads();
+            fft_pass_read<N, 8>(xr, xi, sre, sim, t);
+            fft_pass_compute<N, NS, 8>(xr, xi, t, tw);
+            FftRest<N, NS * 8, LEFT - 1>::run(xr, xi, sre, sim, t, tw);
+        } else if constexpr (NS < N) {
+            constexpr int R = N / NS;  // 2 or 4
+            __syncthreads();
+            fft_pass_write<N, NS / 8, 8>(xr, xi, sre, sim, t);
+            __syncthreads();
+            fft_pass_read<N, R>(xr, xi, sre, sim, t);
+            fft_pass_compute<N, NS, R>(xr, xi, t, tw);
+        }
+    }
+};
+
+// Forward DFT of N points spread over N/8 threads.  On entry register e holds x[t + e*N/8]; on exit it
+// holds X[fft_out_index<N>(e, t)].  sre/sim: this transform's padded exchange rows (fft_padded_len(N)
+// doubles each).  Calls __syncthreads(): every thread of the CTA must call it the same number of times.
+template <int N>
+__device__ __forceinline__ void fft_block(double (&xr)[8], double (&xi)[8], double* sre, double* sim, int t,
+                                          const double2* __restrict__ tw) {
+    static_assert(N >= 8 && (N & (N - 1)) == 0, "power of two >= 8");
+    fft_pass_compute<N, 1, 8>(xr, xi, t, tw);
+    FftRest<N, 8, fft_num_r8(N) - 1>::run(xr, xi, sre, sim, t, tw);
+}
+
+}  // namespace s2k

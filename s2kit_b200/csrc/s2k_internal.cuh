@@ -1,0 +1,133 @@
+// s2k_internal.cuh -- plan object and kernel launch prototypes shared by the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "../../include/s2kit_cuda.h"
+
+namespace s2k {
+
+// ---- private table layout -------------------------------------------------------------------------
+// Order m's cosine table T_m (rows l = m..bw-1) is split by parity p = (l-m)&1 into two
+// lower-trapezoidal blocks: row r <-> l = m+p+2r, column c <-> cosine index k = 2c+p, row r has
+// len0+r entries.  Each block is cut into 8x8 tiles stored row-tile-major; a tile holds 64 doubles in
+// DMMA fragment order: element (row i, col j) sits at 2*(4*i + (j&3)) + (j>>2), so that lane L of a warp
+// reads with ONE 128-bit load the two A-fragment values (row L/4, cols L%4 and L%4+4) of the two
+// mma.m8n8k4 k-steps covering the tile.  Entries outside the trapezoid are zero.
+struct BlockMeta {
+    int rt_base;  // index of this block's first row tile in rt_start[]
+    int rows;     // R_p
+    int len0;     // entries in row 0
+    int nrt;      // number of row tiles = ceil(rows / 8)
+};
+
+__host__ __device__ inline int tile_elem_offset(int i, int j) { return 2 * (4 * i + (j & 3)) + (j >> 2); }
+
+struct ProfileSlot {
+    cudaEvent_t a, b;
+    int kind;
+};
+
+}  // namespace s2k
+
+struct s2kit_cuda_plan {
+    int bw = 0, n = 0, variant = 0, device = 0, chunk = 1;
+    bool fast = false;  // power-of-two bandwidth >= 16: radix FFT kernels; otherwise direct O(n^2) kernels
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+
+    // sharding (single-field multi-GPU); nranks == 1 for ordinary plans
+    int rank = 0, nranks = 1;
+    std::vector<int> my_orders;  // orders owned by this rank (ascending)
+
+    // host-computed constants on the device
+    double* d_weights = nullptr;   // 4 bw   (weights.c:32-47)
+    double* d_sin = nullptr;       // 2 bw   sin((2j+1) pi / 4bw)
+    double2* d_tw_n = nullptr;     // n      (cos, -sin)(2 pi q / n)
+    double2* d_tw_b = nullptr;     // bw     (cos, -sin)(2 pi q / bw)
+    double2* d_q_n = nullptr;      // 4n     (cos, sin)(pi q / 2n)
+    double2* d_q_b = nullptr;      // 4bw    (cos, sin)(pi q / 2bw)
+    double* d_nodes = nullptr;     // bw     cos((2i+1) pi / 2bw)
+    double* d_seeds = nullptr;     // bw*bw  seed[m][i] = P~_m^m(theta_i) (/ sin theta_i for odd m)
+    double2* d_rec = nullptr;      // bw*bw  rec[m*bw + l] = (a_l^m, c_l^m)  (l2_norms.c:16-38)
+
+    // table (private tiled layout)
+    double* d_table = nullptr;
+    size_t table_tiles = 0;             // tiles resident in d_table
+    std::vector<uint64_t> h_order_start;  // [bw+1] tile offset of each order in a full table
+    std::vector<s2k::BlockMeta> h_meta;   // [2*bw]
+    std::vector<uint32_t> h_rt_start;     // row-tile starts relative to the order's start
+    uint64_t* d_order_start = nullptr;
+    s2k::BlockMeta* d_meta = nullptr;
+    uint32_t* d_rt_start = nullptr;
+    // table-generator work units (order, first degree)
+    int* d_units = nullptr;  // pairs (m, l0)
+    std::vector<int> h_units;
+    std::vector<int> h_unit_first;  // first unit of each order, [bw+1]
+    // Fly: scratch table for a group of orders
+    size_t fly_tiles = 0;
+
+    // workspace for `chunk` functions
+    double* d_S = nullptr;  // spectral planes  [chunk][2][n][n]
+    double* d_X = nullptr;  // cosine planes    [chunk][n][2][bw]
+    double* d_coef = nullptr;  // [chunk][2][bw*bw]   conv intermediates / staging
+    double* d_coef2 = nullptr;
+    double* d_filt = nullptr;  // [chunk][2][bw]
+    // staging for host-pointer calls
+    double* d_stage_grid = nullptr;  // [chunk][2][n*n]
+    double* d_stage_coef = nullptr;  // [chunk][2][bw*bw]
+    size_t table_bytes = 0;
+
+    // profiling
+    bool profiling = false;
+    std::vector<s2k::ProfileSlot> prof_slots;
+    size_t prof_used = 0;
+    double prof_ms[S2KIT_K_COUNT] = {0};
+    long prof_launches[S2KIT_K_COUNT] = {0};
+};
+
+namespace s2k {
+
+// RAII-less profiling bracket: begin returns a slot index (or -1)
+int prof_begin(s2kit_cuda_plan* p, int kind);
+void prof_end(s2kit_cuda_plan* p, int slot);
+
+// ---- launchers (each checks cudaGetLastError and returns it) -----------------------------------------
+// K1 / K6: longitude FFT.  S layout [f][part][order row][latitude]
+cudaError_t launch_phi_fft_fwd(s2kit_cuda_plan* p, const double* rdata, const double* idata, long stride,
+                               double* S, int nfun, int data_format);
+cudaError_t launch_phi_fft_inv(s2kit_cuda_plan* p, const double* G, double* rdata, double* idata, long stride,
+                               int nfun, int data_format);
+// K2 / K5: DCT stages.  X layout [f][order row][part][bw]
+cudaError_t launch_dct_fwd(s2kit_cuda_plan* p, const double* S, double* X, int nfun, int row_lo, int row_hi,
+                           int data_format);
+cudaError_t launch_dct_inv(s2kit_cuda_plan* p, const double* V, double* G, int nfun, int row_lo, int row_hi,
+                           int data_format);
+// K3 / K4: Legendre contraction for orders [m_lo, m_hi); table_shift = tile offset subtracted from order starts
+cudaError_t launch_legendre_fwd(s2kit_cuda_plan* p, const double* table, uint64_t table_shift, const double* X,
+                                double* rco, double* ico, long coef_stride, int nfun, int m_lo, int m_hi,
+                                int data_format);
+cudaError_t launch_legendre_inv(s2kit_cuda_plan* p, const double* table, uint64_t table_shift, const double* rco,
+                                const double* ico, long coef_stride, double* V, int nfun, int m_lo, int m_hi,
+                                int data_format);
+// K7: table generation for orders [m_lo, m_hi) into `table` (tile layout, pre-zeroed by the launcher)
+cudaError_t launch_table_gen(s2kit_cuda_plan* p, double* table, uint64_t table_shift, int m_lo, int m_hi);
+// tile layout -> reference packed layout for one order
+cudaError_t launch_table_unpack(s2kit_cuda_plan* p, const double* table, uint64_t table_shift, int m, double* out);
+// recurrence coefficients (a_l^m, c_l^m) for all (m, l)
+cudaError_t launch_rec_coeffs(s2kit_cuda_plan* p);
+// K8
+cudaError_t launch_zonal_rowsum(s2kit_cuda_plan* p, const double* rdata, const double* idata, long stride, double* S,
+                                int nfun);
+cudaError_t launch_spectral_mul(s2kit_cuda_plan* p, const double* rd, const double* id, long coef_stride,
+                                const double* rf, const double* ifl, long filt_stride, double* rres, double* ires,
+                                long res_stride, int nfun);
+int table_unit_rows(int bw);
+
+// peaks
+cudaError_t measure_fp64(double* fma_tflops, double* dmma_tflops);
+cudaError_t measure_copy(size_t bytes, double* gbs);
+
+}  // namespace s2k

@@ -1,0 +1,367 @@
+/*
+ * s2kit_compat.c -- the C host layer: S2kit's public C API on top of the s2kit_cuda_* C-ABI.
+ *
+ * Every function here has the name, argument order and meaning of the reference's declaration so that a C
+ * caller of S2kit can relink against libs2kit_cuda.so:
+ *   include/s2kit/FST_semi_memo.h:8-16   FSTSemiMemo InvFSTSemiMemo FZTSemiMemo ConvOn2SphereSemiMemo
+ *   include/s2kit/FST_semi_fly.h:8-16    FSTSemiFly  InvFSTSemiFly  FZTSemiFly  ConvOn2SphereSemiFly
+ *   include/s2kit/seminaive.h:6-8        DLTSemi InvDLTSemi
+ *   include/s2kit/cospml.h:6-30          TableSize ... Transpose_SemiNaive_Naive_Pml_Table
+ *   include/s2kit/weights.h:4            GenerateWeightsForDLT
+ *   include/s2kit/util.h:15-17           IndexOfHarmonicCoeff TransMult
+ * The transforms run on the GPU through a per-bandwidth plan cache; the `workspace`, FFTW-plan and host
+ * table arguments are accepted and ignored (device tables are keyed by bandwidth), and `cutoff` no longer
+ * switches algorithms: every order uses the seminaive algorithm (the reference's hybrid differs from its
+ * own pure-seminaive result by <= 1.3e-13 at bw = 512).  The reference's functions
+ * return void and never report errors; here an unrecoverable CUDA failure prints the reason and aborts --
+ * there is no CPU fallback.
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/s2kit.h"
+#include "../../include/s2kit_cuda.h"
+#include "host_setup.h"
+
+/* ------------------------------------------------------------------------------------ plan cache */
+#define MAX_CACHED 16
+static struct {
+    int bw, variant;
+    s2kit_cuda_plan* plan;
+} g_cache[MAX_CACHED];
+static int g_ncached = 0;
+static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+
+static void die(const char* where) {
+    fprintf(stderr, "s2kit_cuda: %s failed: %s\n", where, s2kit_cuda_last_error());
+    abort();
+}
+
+static int env_device(void) {
+    const char* s = getenv("S2KIT_CUDA_DEVICE");
+    return s ? atoi(s) : 0;
+}
+
+static s2kit_cuda_plan* plan_for(int bw, int variant) {
+    pthread_mutex_lock(&g_lock);
+    for (int i = 0; i < g_ncached; ++i)
+        if (g_cache[i].bw == bw && g_cache[i].variant == variant) {
+            s2kit_cuda_plan* p = g_cache[i].plan;
+            pthread_mutex_unlock(&g_lock);
+            return p;
+        }
+    if (g_ncached == MAX_CACHED) {
+        s2kit_cuda_plan_destroy(g_cache[0].plan);
+        memmove(&g_cache[0], &g_cache[1], sizeof(g_cache[0]) * (MAX_CACHED - 1));
+        --g_ncached;
+    }
+    s2kit_cuda_plan* p = NULL;
+    if (s2kit_cuda_plan_create(&p, bw, variant, 1, env_device())) {
+        pthread_mutex_unlock(&g_lock);
+        die("plan_create");
+    }
+    g_cache[g_ncached].bw = bw;
+    g_cache[g_ncached].variant = variant;
+    g_cache[g_ncached].plan = p;
+    ++g_ncached;
+    pthread_mutex_unlock(&g_lock);
+    return p;
+}
+
+/* drops every cached plan (frees device memory); not part of the reference API */
+void s2kit_compat_release(void) {
+    pthread_mutex_lock(&g_lock);
+    for (int i = 0; i < g_ncached; ++i) s2kit_cuda_plan_destroy(g_cache[i].plan);
+    g_ncached = 0;
+    pthread_mutex_unlock(&g_lock);
+}
+
+/* ------------------------------------------------------------------------------------ layout arithmetic */
+
+/* entries of degree l in order m's packed table (cospml.c:250-258) */
+int RowSize(const int m, const int l) {
+    if (l < m) return 0;
+    return ((m % 2) ? (l - 1) : l) / 2 + 1;
+}
+
+/* doubles before degree l in order m's packed table (cospml.c:123-134).  H(d) = sum_{j<d} (j/2 + 1); an odd
+   order's rows are those of the even order below it shifted by one degree. */
+static int half_sum(int d) {
+    int q = d / 2;
+    return q * (q + 1) + ((d % 2) ? q + 1 : 0);
+}
+int TableOffset(int m, int l) {
+    if (m % 2) return half_sum(l - 1) - half_sum(m - 1);
+    return half_sum(l) - half_sum(m);
+}
+
+/* doubles in order m's packed table (cospml.c:39-59): all rows m..bw-1 */
+int TableSize(const int m, const int bw) {
+    if (m >= bw) return 0;
+    return TableOffset(m, bw - 1) + RowSize(m, bw - 1);
+}
+
+/* cospml.c:107-115 */
+int Reduced_SpharmonicTableSize(const int bw, const int m) {
+    int total = 0;
+    for (int o = 0; o < m; ++o) total += TableSize(o, bw);
+    return total;
+}
+
+/* cospml.c:85-92: closed-form upper bound up to bw = 512, exact sum above */
+int Spharmonic_TableSize(const int bw) {
+    if (bw > 512) return Reduced_SpharmonicTableSize(bw, bw);
+    return (4 * bw * bw * bw + 6 * bw * bw - 8 * bw) / 24 + bw;
+}
+
+/* cospml.c:434-440: theta-space tables of orders m..bw-1, 2bw samples per degree */
+int Reduced_Naive_TableSize(const int bw, const int m) {
+    int degrees = 0;
+    for (int o = m; o < bw; ++o) degrees += bw - o;
+    return 2 * bw * degrees;
+}
+
+/* entries of cosine index `row` in the transposed table of order m: the degrees l >= max(first, m) of matching
+   parity that carry that index.  Equals cospml.c:270-288 for even bw (the reference's odd-bw values are
+   inconsistent with its own TableSize, SURVEY.md section 0 trap 4). */
+static int transposed_first_degree(int row, int m) {
+    if (m % 2) return row >= m ? row + 1 : m + (row % 2);
+    return row > m ? row : m + (row % 2);
+}
+int Transpose_RowSize(const int row, const int m, const int bw) {
+    if (row >= bw) return 0;
+    if ((m % 2) && row == bw - 1) return 0;
+    int first = transposed_first_degree(row, m);
+    if (first >= bw) return 0;
+    return (bw - 1 - first) / 2 + 1;
+}
+
+/* util.c:42-49 */
+int IndexOfHarmonicCoeff(const int m, const int l, const int bw) {
+    if (m >= 0) return m * bw - (m * (m - 1)) / 2 + (l - m);
+    int a = -m;
+    /* bw(bw+1)/2 entries of the non-negative orders, then orders -(bw-1) .. -(a+1) */
+    return bw * (bw + 1) / 2 + ((bw - 1 - a) * (bw - a)) / 2 + (l - a);
+}
+
+/* ------------------------------------------------------------------------------------ setup */
+
+void GenerateWeightsForDLT(const int bw, double* weights) { s2k_host_weights(bw, weights); }
+
+/* cospml.c:161-242: generated on the device, exported in the reference's packed layout */
+void GenerateCosPmlTable(const int bw, const int m, double* tablespace, double* workspace) {
+    (void)workspace;
+    if (s2kit_cuda_table_export(plan_for(bw, S2KIT_CUDA_MEMO), m, tablespace)) die("GenerateCosPmlTable");
+}
+
+/* cospml.c:301-362: gather each cosine index's column of the packed table (ascending degree) */
+void TransposeCosPmlTable(const int bw, const int m, double* cos_pml_table, double* result) {
+    double* out = result;
+    for (int row = 0; row < bw; ++row) {
+        int count = Transpose_RowSize(row, m, bw);
+        int l = transposed_first_degree(row, m);
+        for (int i = 0; i < count; ++i, l += 2) *out++ = cos_pml_table[TableOffset(m, l) + row / 2];
+    }
+}
+
+double** Spharmonic_Pml_Table(const int bw, double* resultspace, double* workspace) {
+    double** t = (double**)malloc(sizeof(double*) * bw);
+    double* at = resultspace;
+    for (int m = 0; m < bw; ++m) {
+        t[m] = at;
+        GenerateCosPmlTable(bw, m, at, workspace);
+        at += TableSize(m, bw);
+    }
+    return t;
+}
+
+double** Transpose_Spharmonic_Pml_Table(double** spharmonic_pml_table, const int bw, double* resultspace) {
+    double** t = (double**)malloc(sizeof(double*) * bw);
+    double* at = resultspace;
+    for (int m = 0; m < bw; ++m) {
+        t[m] = at;
+        TransposeCosPmlTable(bw, m, spharmonic_pml_table[m], at);
+        at += TableSize(m, bw);
+    }
+    return t;
+}
+
+/* pml.c:41-79: theta-space table of order m at the 2bw Chebyshev nodes (host; only ever read by callers, the
+   GPU engine uses the seminaive algorithm for every order) */
+void GeneratePmlTable(const int bw, const int m, double* pml_table, double* workspace) {
+    (void)workspace;
+    const int n = 2 * bw;
+    double* buf = (double*)malloc(sizeof(double) * 3 * n);
+    double *x = buf, *older = buf + n, *cur = buf + 2 * n;
+    const double den = 2. * n;
+    double c = sqrt(m + 0.5);
+    for (int i = 0; i < m; ++i) c *= sqrt((m - (i / 2.)) / ((double)m - i));
+    if (m) c *= pow(2., -m / 2.);
+    if (m % 2) c *= -1.;
+    for (int i = 0; i < n; ++i) {
+        double theta = (2. * i + 1.) * M_PI / den;
+        x[i] = cos((2. * i + 1.) * M_PI / den);
+        older[i] = 0.;
+        cur[i] = m ? c * pow(sin(theta), m) : M_SQRT1_2;
+    }
+    memcpy(pml_table, cur, sizeof(double) * n);
+    for (int l = m; l + 1 < bw; ++l) {
+        double a = sqrt(((2. * l + 3.) / (2. * l + 1.)) * ((l - m + 1.) / (l + m + 1.))) * ((2. * l + 1.) / (l - m + 1.));
+        double cc = 0.;
+        if (l)
+            cc = -1.0 *
+                 sqrt(((2. * l + 3.) / (2. * l - 1.)) * ((l - m + 1.) / (l + m + 1.)) *
+                      (((double)l - m) / ((double)l + m))) *
+                 ((l + m) / (l - m + 1.));
+        double* next = pml_table + (size_t)(l + 1 - m) * n;
+        for (int i = 0; i < n; ++i) {
+            double t1 = cc * older[i];
+            double t2 = cur[i] * x[i];
+            double t3 = a * t2;
+            next[i] = t3 + t1;
+        }
+        memcpy(older, cur, sizeof(double) * n);
+        memcpy(cur, next, sizeof(double) * n);
+    }
+    free(buf);
+}
+
+/* cospml.c:451-475: cosine tables below the cutoff, theta-space tables from the cutoff on */
+double** SemiNaive_Naive_Pml_Table(const int bw, const int m, double* resultspace, double* workspace) {
+    double** t = (double**)malloc(sizeof(double*) * (bw + 1));
+    double* at = resultspace;
+    for (int o = 0; o < bw; ++o) {
+        t[o] = at;
+        if (o < m) {
+            GenerateCosPmlTable(bw, o, at, workspace);
+            at += TableSize(o, bw);
+        } else {
+            GeneratePmlTable(bw, o, at, workspace);
+            at += 2 * bw * (bw - o);
+        }
+    }
+    t[bw] = at;
+    return t;
+}
+
+/* cospml.c:490-518 */
+double** Transpose_SemiNaive_Naive_Pml_Table(double** seminaive_naive_pml_table, const int bw, const int m,
+                                             double* resultspace, double* workspace) {
+    double** t = (double**)malloc(sizeof(double*) * (bw + 1));
+    double* at = resultspace;
+    for (int o = 0; o < bw; ++o) {
+        t[o] = at;
+        if (o < m) {
+            TransposeCosPmlTable(bw, o, seminaive_naive_pml_table[o], at);
+            at += TableSize(o, bw);
+        } else {
+            GeneratePmlTable(bw, o, at, workspace);
+            at += 2 * bw * (bw - o);
+        }
+    }
+    t[bw] = at;
+    return t;
+}
+
+/* ------------------------------------------------------------------------------------ transforms */
+
+static void run_fst(int variant, double* rdata, double* idata, double* rcoeffs, double* icoeffs, int bw, int fmt) {
+    s2kit_cuda_plan* p = plan_for(bw, variant);
+    long gs = 4L * bw * bw, cs = (long)bw * bw;
+    if (s2kit_cuda_fst(p, rdata, idata, rcoeffs, icoeffs, 1, gs, cs, fmt, S2KIT_CUDA_HOST)) die("FSTSemi");
+}
+
+static void run_inv(int variant, double* rcoeffs, double* icoeffs, double* rdata, double* idata, int bw, int fmt) {
+    s2kit_cuda_plan* p = plan_for(bw, variant);
+    long gs = 4L * bw * bw, cs = (long)bw * bw;
+    if (s2kit_cuda_inv_fst(p, rcoeffs, icoeffs, rdata, idata, 1, cs, gs, fmt, S2KIT_CUDA_HOST)) die("InvFSTSemi");
+}
+
+static void run_fzt(int variant, double* rdata, double* idata, double* rres, double* ires, int bw, int fmt) {
+    s2kit_cuda_plan* p = plan_for(bw, variant);
+    if (s2kit_cuda_fzt(p, rdata, idata, rres, ires, 1, 4L * bw * bw, bw, fmt, S2KIT_CUDA_HOST)) die("FZTSemi");
+}
+
+static void run_conv(int variant, double* rdata, double* idata, double* rfilter, double* ifilter, double* rres,
+                     double* ires, int bw) {
+    s2kit_cuda_plan* p = plan_for(bw, variant);
+    long gs = 4L * bw * bw;
+    if (s2kit_cuda_conv(p, rdata, idata, rfilter, ifilter, rres, ires, 1, gs, gs, S2KIT_CUDA_HOST))
+        die("ConvOn2SphereSemi");
+}
+
+void FSTSemiMemo(double* rdata, double* idata, double* rcoeffs, double* icoeffs, const int bw,
+                 double** seminaive_naive_table, double* workspace, DataFormat data_format, const int cutoff,
+                 fftw_plan* DCT_plan, fftw_plan* FFT_plan, double* weights) {
+    (void)seminaive_naive_table; (void)workspace; (void)cutoff; (void)DCT_plan; (void)FFT_plan; (void)weights;
+    run_fst(S2KIT_CUDA_MEMO, rdata, idata, rcoeffs, icoeffs, bw, (int)data_format);
+}
+
+void InvFSTSemiMemo(double* rcoeffs, double* icoeffs, double* rdata, double* idata, const int bw,
+                    double** transpose_seminaive_naive_table, double* workspace, DataFormat data_format,
+                    const int cutoff, fftw_plan* inv_DCT_plan, fftw_plan* inv_FFT_plan) {
+    (void)transpose_seminaive_naive_table; (void)workspace; (void)cutoff; (void)inv_DCT_plan; (void)inv_FFT_plan;
+    run_inv(S2KIT_CUDA_MEMO, rcoeffs, icoeffs, rdata, idata, bw, (int)data_format);
+}
+
+void FZTSemiMemo(double* rdata, double* idata, double* rres, double* ires, const int bw, double* cos_pml_table,
+                 double* workspace, const DataFormat data_format, fftw_plan* DCT_plan, double* weights) {
+    (void)cos_pml_table; (void)workspace; (void)DCT_plan; (void)weights;
+    run_fzt(S2KIT_CUDA_MEMO, rdata, idata, rres, ires, bw, (int)data_format);
+}
+
+void ConvOn2SphereSemiMemo(double* rdata, double* idata, double* rfilter, double* ifilter, double* rres,
+                           double* ires, const int bw, double* workspace) {
+    (void)workspace;
+    run_conv(S2KIT_CUDA_MEMO, rdata, idata, rfilter, ifilter, rres, ires, bw);
+}
+
+void FSTSemiFly(double* rdata, double* idata, double* rcoeffs, double* icoeffs, const int bw, double* workspace,
+                DataFormat data_format, const int cutoff, fftw_plan* DCT_plan, fftw_plan* FFT_plan,
+                double* weights) {
+    (void)workspace; (void)cutoff; (void)DCT_plan; (void)FFT_plan; (void)weights;
+    run_fst(S2KIT_CUDA_FLY, rdata, idata, rcoeffs, icoeffs, bw, (int)data_format);
+}
+
+void InvFSTSemiFly(double* rcoeffs, double* icoeffs, double* rdata, double* idata, const int bw, double* workspace,
+                   DataFormat data_format, const int cutoff, fftw_plan* inv_DCT_plan, fftw_plan* inv_FFT_plan) {
+    (void)workspace; (void)cutoff; (void)inv_DCT_plan; (void)inv_FFT_plan;
+    run_inv(S2KIT_CUDA_FLY, rcoeffs, icoeffs, rdata, idata, bw, (int)data_format);
+}
+
+void FZTSemiFly(double* rdata, double* idata, double* rres, double* ires, const int bw, double* workspace,
+                DataFormat data_format, fftw_plan* DCT_plan, double* weights) {
+    (void)workspace; (void)DCT_plan; (void)weights;
+    run_fzt(S2KIT_CUDA_FLY, rdata, idata, rres, ires, bw, (int)data_format);
+}
+
+void ConvOn2SphereSemiFly(double* rdata, double* idata, double* rfilter, double* ifilter, double* rres,
+                          double* ires, const int bw, double* workspace) {
+    (void)workspace;
+    run_conv(S2KIT_CUDA_FLY, rdata, idata, rfilter, ifilter, rres, ires, bw);
+}
+
+/* seminaive.c:153-198 / 56-115, single column, single order */
+void DLTSemi(double* data, const int bw, const int m, double* result, double* workspace, double* cos_pml_table,
+             double* weights, fftw_plan* plan) {
+    (void)workspace; (void)cos_pml_table; (void)weights; (void)plan;
+    if (s2kit_cuda_dlt_semi(plan_for(bw, S2KIT_CUDA_MEMO), data, m, result, 1, S2KIT_CUDA_HOST)) die("DLTSemi");
+}
+
+void InvDLTSemi(double* coeffs, const int bw, const int m, double* result, double* trans_cos_pml_table,
+                double* sin_values, double* workspace, fftw_plan* plan) {
+    (void)trans_cos_pml_table; (void)sin_values; (void)workspace; (void)plan;
+    if (s2kit_cuda_inv_dlt_semi(plan_for(bw, S2KIT_CUDA_MEMO), coeffs, m, result, 1, S2KIT_CUDA_HOST))
+        die("InvDLTSemi");
+}
+
+/* util.c:68-103 */
+void TransMult(double* rdatacoeffs, double* idatacoeffs, double* rfiltercoeffs, double* ifiltercoeffs, double* rres,
+               double* ires, const int bw) {
+    if (s2kit_cuda_trans_mult(plan_for(bw, S2KIT_CUDA_MEMO), rdatacoeffs, idatacoeffs, rfiltercoeffs, ifiltercoeffs,
+                              rres, ires, 1, (long)bw * bw, S2KIT_CUDA_HOST))
+        die("TransMult");
+}
