@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- FP64 forward+inverse spherical harmonic transforms per second on B200 (BASELINE.json metric).
+
+One "step" = one pass of the hot path (InvFST then FST, COMPLEX format, Memo tables) over one batch of
+synthetic band-limited functions.  Default workload = BASELINE.json configs[2]: bandwidth 256, 1024 functions
+per GPU (one process per GPU, functions are independent: no data-path collective, weak scaling).
+
+  python bench.py --gpus 1 --steps 5 --warmup 3
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...      # the reference's own CPU implementation on the host cores
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput, `e2e` = the same metric through the
+C-ABI with pinned HOST buffers (H2D/D2H inside the timed region), `roofline` = the dominant kernel against
+its bound, `cpu_baseline` = the reference CPU path on a bounded sample.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fp64_fwd_inv_sht_pairs_per_sec"
+UNIT = "transform pairs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--bw", type=int, default=256)
+    ap.add_argument("--batch", type=int, default=1024, help="functions per GPU per step")
+    ap.add_argument("--chunk", type=int, default=64, help="functions per internal launch group")
+    ap.add_argument("--format", default="complex", choices=["complex", "real"])
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="functions in the CPU sample (0 = auto)")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return f"batched InvFSTSemiMemo+FSTSemiMemo, bw={a.bw}, {a.batch} synthetic band-limited functions per GPU, {a.format.upper()} format"
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_pairs_per_sec(bw, fmt, sample, threads):
+    """The reference's CPU path (oracle/_ref = its unmodified sources + FFTW-API stub; falls back to the port)."""
+    import oracle
+
+    kind = oracle.best_kind()
+    if kind == "ref":
+        O = oracle.Oracle(bw, "ref")
+        O.bench_pairs(min(threads, sample), min(threads, sample), 999, fmt)  # warm caches / page in
+        wall, busy = O.bench_pairs(sample, threads, 1000, fmt)
+        O.close()
+        return sample / wall, "reference", threads
+    # port: single thread, python-driven
+    O = oracle.Oracle(bw, "port")
+    rc, ic = O.gen_coeffs(1000)
+    n = max(2, min(sample, 8))
+    t0 = time.time()
+    for _ in range(n):
+        g = O.inverse(rc, ic, fmt)
+        O.forward(g[0], g[1], fmt)
+    wall = time.time() - t0
+    return n / wall, "port", 1
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    fmt = 0 if a.format == "complex" else 1
+    threads = os.cpu_count() or 1
+    sample = a.cpu_sample or max(threads, 64)
+    vals = []
+    kind, cores = "reference", threads
+    for i in range(a.warmup + a.steps):
+        v, kind, cores = cpu_pairs_per_sec(a.bw, fmt, sample, threads)
+        if i >= a.warmup:
+            vals.append(v)
+        if i == 0 and sample / v > 20:  # keep the whole run within minutes
+            sample = max(cores, int(v * 10))
+    value = len(vals) / sum(1.0 / v for v in vals)
+    sample_txt = (f"{sample} functions (seeds 1000..) per step on {cores} host threads, InvFSTSemiMemo+FSTSemiMemo, "
+                  f"tables excluded; FFTW replaced by oracle/fftw_stub (FFTW not installed)")
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * sample / value, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(a), "bw": a.bw, "format": a.format},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample_txt},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+class ClockSampler:
+    def __init__(self, dev):
+        self.dev, self.rows, self.proc = dev, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.dev)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([x.strip() for x in ln.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i] == "Active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def table_doubles(bw):
+    tot = 0
+    for m in range(bw):
+        tot += sum((l - 1) // 2 + 1 if m % 2 else l // 2 + 1 for l in range(m, bw))
+    return tot
+
+
+def algorithmic_per_function(bw, fmt_real):
+    """algorithmic bytes / flops per function and stage."""
+    B2 = bw * bw
+    S = table_doubles(bw)
+    T0 = sum(l // 2 + 1 for l in range(bw))
+    lg = math.log2(2 * bw)
+    return {
+        "phi_fft": {"bytes": 128 * B2, "flops": 20 * B2 * lg},
+        "dct": {"bytes": (48 if fmt_real else 96) * B2, "flops": (10 if fmt_real else 20) * B2 * lg},
+        "legendre": {"bytes": 48 * B2, "table_bytes": 8 * S, "flops": (4 * S) if fmt_real else (8 * S - 4 * T0)},
+    }
+
+
+def synth_coeffs(torch, bw, batch, device, seed):
+    """Random coefficients of real-valued band-limited fields, symmetry of test_s2_semi_memo.c:156-172."""
+    import numpy as np
+
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    rc = torch.rand(batch, bw * bw, generator=g, device=device, dtype=torch.float64) * 2 - 1
+    ic = torch.rand(batch, bw * bw, generator=g, device=device, dtype=torch.float64) * 2 - 1
+    pos, neg, sgn = [], [], []
+    for m in range(1, bw):
+        l = np.arange(m, bw)
+        pos.append(m * bw - (m * (m - 1)) // 2 + (l - m))
+        big = bw - 1
+        neg.append((big * (big + 3)) // 2 + 1 + ((big - m) * (big - m + 1)) // 2 + (l - m))
+        sgn.append(np.full(l.shape, -1.0 if m % 2 else 1.0))
+    pos = torch.from_numpy(np.concatenate(pos)).to(device)
+    neg = torch.from_numpy(np.concatenate(neg)).to(device)
+    sgn = torch.from_numpy(np.concatenate(sgn)).to(device)
+    rc[:, neg] = rc[:, pos] * sgn
+    ic[:, neg] = -ic[:, pos] * sgn
+    ic[:, :bw] = 0.0
+    return rc, ic
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    import s2kit_b200 as s2
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    fmt = s2.COMPLEX if a.format == "complex" else s2.REAL
+    bw, n, batch = a.bw, 2 * a.bw, a.batch
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    if os.path.exists(peaks_path):
+        hbm_peak, hbm_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs"
+    fp64 = s2.measure_fp64_peak(local)  # FP64 DFMA / DMMA peaks are not in MEASURED_PEAKS.json: measured here
+
+    plan = s2.Plan(bw, s2.MEMO, max_batch=a.chunk, device=local)
+    plan.set_stream(torch.cuda.current_stream().cuda_stream)
+    rc, ic = synth_coeffs(torch, bw, batch, dev, 1000 + rank)
+    rd = torch.empty(batch, n, n, device=dev, dtype=torch.float64)
+    idt = torch.empty_like(rd)
+    rc2, ic2 = torch.empty_like(rc), torch.empty_like(ic)
+
+    def step():
+        plan.inv_fst(rc, ic, rd, idt, fmt)
+        plan.fst(rd, idt, rc2, ic2, fmt)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    err = float(((rc2 - rc).abs().max().item() + (ic2 - ic).abs().max().item()))  # round-trip sanity
+
+    sampler = ClockSampler(local)
+    plan.profile(True)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    prof = plan.profile_get()
+    plan.profile(False)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * batch * a.steps / (ms * 1e-3)
+
+    # ---- end to end through the C-ABI with pinned host buffers
+    e2e = None
+    if not a.no_e2e:
+        hc_r = torch.empty(batch, bw * bw, dtype=torch.float64).pin_memory()
+        hc_i = torch.empty_like(hc_r).pin_memory()
+        hc_r.copy_(rc.cpu())
+        hc_i.copy_(ic.cpu())
+        hg_r = torch.empty(batch, n, n, dtype=torch.float64).pin_memory()
+        hg_i = torch.empty(batch, n, n, dtype=torch.float64).pin_memory()
+        ho_r = torch.empty(batch, bw * bw, dtype=torch.float64).pin_memory()
+        ho_i = torch.empty(batch, bw * bw, dtype=torch.float64).pin_memory()
+
+        def e2e_step():
+            plan.inv_fst(hc_r, hc_i, hg_r, hg_i, fmt)   # H2D coefficients, D2H grids
+            plan.fst(hg_r, hg_i, ho_r, ho_i, fmt)       # H2D grids, D2H coefficients
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.e2e_steps):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e_err = float((ho_r - hc_r).abs().max().item())
+        per = 8 * (2 * bw * bw + 2 * n * n)
+        e2e = {"value": world * batch * a.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": per * batch,
+               "d2h_bytes_per_step": per * batch, "steps": a.e2e_steps, "roundtrip_max_abs_err": e2e_err,
+               "note": "s2kit_cuda_inv_fst + s2kit_cuda_fst with pinned HOST buffers, copies inside the timed region"}
+
+    # ---- roofline of the dominant kernel
+    alg = algorithmic_per_function(bw, fmt == s2.REAL)
+    stages = {}
+    for kind, (kms, cnt) in prof.items():
+        if cnt == 0:
+            continue
+        base = "phi_fft" if kind.startswith("phi_fft") else "dct" if kind.startswith("dct") else \
+            "legendre" if kind.startswith("legendre") else None
+        if base is None:
+            continue
+        fn_per_launch = batch * a.steps / cnt
+        avg_s = kms * 1e-3 / cnt
+        ent = {"ms_total": kms, "launches": cnt, "avg_launch_ms": kms / cnt, "functions_per_launch": fn_per_launch}
+        if base == "legendre":
+            flops = alg[base]["flops"] * fn_per_launch
+            byts = alg[base]["bytes"] * fn_per_launch + alg[base]["table_bytes"]
+            ent.update({"bound": "tensor", "achieved": flops / avg_s / 1e12, "peak": fp64["dmma_tflops"],
+                        "unit": "TFLOP/s", "alg_flops_per_launch": flops, "alg_bytes_per_launch": byts,
+                        "hbm_gbs": byts / avg_s / 1e9})
+        else:
+            byts = alg[base]["bytes"] * fn_per_launch
+            ent.update({"bound": "hbm", "achieved": byts / avg_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "alg_bytes_per_launch": byts, "alg_flops_per_launch": alg[base]["flops"] * fn_per_launch})
+        ent["frac"] = ent["achieved"] / ent["peak"]
+        stages[kind] = ent
+    dom = max(stages, key=lambda k: stages[k]["ms_total"]) if stages else None
+    roofline = None
+    if dom:
+        d = stages[dom]
+        roofline = {"kernel": dom, "bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"], "unit": d["unit"],
+                    "frac": d["frac"], "traffic": None,
+                    "peak_source": (hbm_src if d["bound"] == "hbm" else
+                                    "FP64 DMMA (mma.sync.m8n8k4.f64) micro-benchmark measured in this run; "
+                                    "MEASURED_PEAKS.json has no FP64 figure"),
+                    "share_of_step": d["ms_total"] / ms}
+    launches = int(sum(c for _, c in prof.values()))
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        threads = os.cpu_count() or 1
+        sample = a.cpu_sample or max(threads, 64)
+        v, kind, cores = cpu_pairs_per_sec(bw, 0 if fmt == s2.COMPLEX else 1, sample, threads)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"{sample} functions on {cores} host threads, InvFSTSemiMemo+FSTSemiMemo of the reference "
+                         f"(FFTW replaced by oracle/fftw_stub), tables excluded"}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "bw": bw, "functions_per_gpu": batch, "chunk": a.chunk,
+                       "format": a.format, "variant": "memo",
+                       "l2": "inputs larger than L2 (per step 1 GiB coefficients -> 4 GiB grids -> 1 GiB coefficients)",
+                       "sharding": "independent functions per rank, no collective"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "stages": stages,
+            "fp64_peak_measured": fp64, "cpu_baseline": cpu, "roundtrip_max_abs_err": err,
+        }
+        print(json.dumps(out))
+    plan.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

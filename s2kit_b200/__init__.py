@@ -33,7 +33,7 @@ class S2kitCudaError(RuntimeError):
 
 
 def build(force=False):
-    from . import build as _b
+    from . import buildlib as _b
 
     return _b.build(force=force)
 
@@ -44,7 +44,7 @@ def lib():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
-        raise S2kitCudaError(f"{LIB_PATH} is missing: run `python -m s2kit_b200.build` (no CPU fallback exists)")
+        raise S2kitCudaError(f"{LIB_PATH} is missing: run `python -m s2kit_b200.buildlib` (no CPU fallback exists)")
     L = ctypes.CDLL(LIB_PATH)
     vp, ci, cl, cs = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_size_t
     L.s2kit_cuda_plan_create.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci]

@@ -55,6 +55,14 @@ void s2k_host_seeds(int bw, int m_lo, int m_hi, double* seeds) {
         for (int i = 0; i < m; ++i) c *= sqrt((m - (i / 2.)) / ((double)m - i));
         c *= pow(2., -m / 2.);
         if (m % 2) c *= -1.;
+        if (!isfinite(c)) {
+            /* The reference's running product overflows for m >= 2044 and its tables become NaN (pmm.c:22-30,
+               SURVEY.md section 0 trap 3).  Only there, fold the 2^(-m/2) into the product so it stays finite;
+               orders m <= 2043 keep the reference's exact arithmetic. */
+            c = sqrt(m + 0.5);
+            for (int i = 0; i < m; ++i) c *= sqrt((m - (i / 2.)) / ((double)m - i)) * M_SQRT1_2;
+            if (m % 2) c *= -1.;
+        }
         for (int i = 0; i < bw; ++i) {
             double theta = (2. * i + 1.) * M_PI / den;
             double v = c * pow(sin(theta), m);

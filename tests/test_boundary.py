@@ -1,0 +1,107 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads, exports every symbol the headers declare,
+the host-side layout arithmetic and libm seeds agree with the oracle, and compute entry points fail loudly
+without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def s2():
+    import __graft_entry__ as ge
+
+    ge.build()
+    import s2kit_b200
+
+    return s2kit_b200
+
+
+def declared_functions(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    names = re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{}]*\)\s*;", txt)
+    return sorted(set(n for n in names if n not in ("defined",)))
+
+
+def test_library_exports_every_declared_symbol(s2):
+    L = s2.lib()
+    for header in ("s2kit_cuda.h", "s2kit.h"):
+        names = declared_functions(header)
+        assert len(names) > 15
+        for name in names:
+            assert hasattr(L, name), f"{name} declared in include/{header} but not exported"
+
+
+def test_layout_helpers_match_oracle(s2, oracle_mod):
+    L = s2.lib()
+    for bw in (8, 16, 17, 23, 64, 256):
+        for m in range(bw):
+            assert L.TableSize(m, bw) == oracle_mod.table_size(m, bw)
+            for l in (m, (m + bw) // 2, bw - 1):
+                assert L.IndexOfHarmonicCoeff(m, l, bw) == oracle_mod.coef_index(m, l, bw)
+                assert L.IndexOfHarmonicCoeff(-m, l, bw) == oracle_mod.coef_index(-m, l, bw)
+                assert L.TableOffset(m, l) == sum(L.RowSize(m, d) for d in range(m, l))
+        assert L.Reduced_SpharmonicTableSize(bw, bw) == sum(oracle_mod.table_size(m, bw) for m in range(bw))
+        assert L.Reduced_Naive_TableSize(bw, bw // 2) == 2 * bw * sum(bw - o for o in range(bw // 2, bw))
+        assert L.Spharmonic_TableSize(bw) >= L.Reduced_SpharmonicTableSize(bw, bw)
+        if bw % 2 == 0:
+            for m in range(bw):
+                assert sum(L.Transpose_RowSize(r, m, bw) for r in range(bw)) == L.TableSize(m, bw)
+
+
+def test_layout_helpers_match_reference_build(s2, oracle_mod):
+    if not oracle_mod.have_ref():
+        pytest.skip("oracle/_ref not built")
+    L, R = s2.lib(), ctypes.CDLL(oracle_mod.REF_SO)
+    P = ctypes.POINTER(ctypes.c_double)
+    for bw in (16, 64, 128):
+        for m in range(bw):
+            assert L.TableSize(m, bw) == R.TableSize(m, bw)
+            for l in range(m, bw):
+                assert L.TableOffset(m, l) == R.TableOffset(m, l)
+                assert L.RowSize(m, l) == R.RowSize(m, l)
+            for row in range(bw + 1):
+                assert L.Transpose_RowSize(row, m, bw) == R.Transpose_RowSize(row, m, bw)
+        assert L.Spharmonic_TableSize(bw) == R.Spharmonic_TableSize(bw)
+    # TransposeCosPmlTable is pure index arithmetic on the host: same gather as the reference
+    O = oracle_mod.Oracle(32, "ref")
+    for m in (0, 1, 2, 15, 30, 31):
+        t = O.table(m)
+        want = np.zeros_like(t)
+        R.TransposeCosPmlTable(32, m, t.ctypes.data_as(P), want.ctypes.data_as(P))
+        assert np.array_equal(s2.TransposeCosPmlTable(32, m, t), want)
+
+
+def test_host_seeds_bit_identical_to_oracle(s2, oracle_mod):
+    """weights.c:32-47 through the drop-in symbol; must be bit-identical (same libm, same expression order)."""
+    for bw in (16, 64, 100):
+        O = oracle_mod.Oracle(bw, "port")
+        assert np.array_equal(s2.GenerateWeightsForDLT(bw), O.weights())
+
+
+def test_compute_fails_loudly_without_gpu(s2):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(s2.S2kitCudaError, match="no CUDA device"):
+        s2.Plan(16)
+    with pytest.raises(s2.S2kitCudaError):
+        s2.measure_fp64_peak(0)
+
+
+def test_product_does_not_touch_the_oracle():
+    """The shipped path must never import, link or execute anything under oracle/."""
+    pkg = os.path.join(ROOT, "s2kit_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".c", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "liboracle" not in txt and "libs2kit_ref" not in txt, f
+    out = os.popen(f"ldd {os.path.join(pkg, 'libs2kit_cuda.so')}").read()
+    assert "oracle" not in out and "fftw" not in out
