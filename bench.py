@@ -32,7 +32,7 @@ UNIT = "transform pairs/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--bw", type=int, default=256)
@@ -106,8 +106,11 @@ def run_reference(a):
 
 # ------------------------------------------------------------------------------------------------ GPU arm
 class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms; start() before the warm-up so the tool is up by the
+    time the timed region begins, mark() at its two ends; samples inside the marks are the ones reported."""
+
     def __init__(self, dev):
-        self.dev, self.rows, self.proc = dev, [], None
+        self.dev, self.rows, self.proc, self.t0, self.t1 = dev, [], None, None, None
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -115,24 +118,35 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.dev)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.dev)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.rows.append([x.strip() for x in ln.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in ln.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc:
+            time.sleep(0.06)
             self.proc.terminate()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or 1e30) + 0.05]
+        rows = inside or [r for _, r in self.rows]
+        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
+        pw = [float(r[2]) for r in rows if len(r) > 2 and r[2].replace(".", "", 1).isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i] == "Active"})
+        reasons = sorted({names[i] for r in rows if len(r) >= 7 for i in range(4) if r[3 + i] == "Active"})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(sm),
+                "samples_in_timed_region": len(inside)}
 
 
 def table_doubles(bw):
@@ -219,21 +233,23 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(a.warmup, 3)):
         step()
     torch.cuda.synchronize()
     err = float(((rc2 - rc).abs().max().item() + (ic2 - ic).abs().max().item()))  # round-trip sanity
 
-    sampler = ClockSampler(local)
     plan.profile(True)
     barrier()
-    sampler.start()
+    sampler.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
         step()
     e1.record()
     barrier()
+    sampler.mark_end()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
     prof = plan.profile_get()
@@ -277,29 +293,38 @@ def run_ours(a):
                "d2h_bytes_per_step": per * batch, "steps": a.e2e_steps, "roundtrip_max_abs_err": e2e_err,
                "note": "s2kit_cuda_inv_fst + s2kit_cuda_fst with pinned HOST buffers, copies inside the timed region"}
 
-    # ---- roofline of the dominant kernel
+    # ---- roofline per kernel kind; the dominant one (largest share of the step) is reported as `roofline`
     alg = algorithmic_per_function(bw, fmt == s2.REAL)
+    B2 = bw * bw
+    per_fn = {  # algorithmic (bytes, flops, table bytes per launch) -- SURVEY.md section 8(d)
+        "phi_fft_fwd": (alg["phi_fft"]["bytes"], alg["phi_fft"]["flops"], 0),
+        "phi_fft_inv": (alg["phi_fft"]["bytes"], alg["phi_fft"]["flops"], 0),
+        "dct_fwd": (alg["dct"]["bytes"], alg["dct"]["flops"], 0),
+        "dct_inv": (alg["dct"]["bytes"], alg["dct"]["flops"], 0),
+        "legendre_fwd": (alg["legendre"]["bytes"], alg["legendre"]["flops"], alg["legendre"]["table_bytes"]),
+        "legendre_inv": (alg["legendre"]["bytes"], alg["legendre"]["flops"], alg["legendre"]["table_bytes"]),
+        # fused DCT+Legendre: reads the spectral rows (2/3 of the DCT stage's bytes), writes coefficients
+        "fused_fwd": (alg["dct"]["bytes"] * 2 // 3 + 16 * B2, alg["legendre"]["flops"] + alg["dct"]["flops"],
+                      alg["legendre"]["table_bytes"]),
+        "fused_inv": (alg["dct"]["bytes"] * 2 // 3 + 16 * B2, alg["legendre"]["flops"] + alg["dct"]["flops"],
+                      alg["legendre"]["table_bytes"]),
+    }
     stages = {}
     for kind, (kms, cnt) in prof.items():
-        if cnt == 0:
-            continue
-        base = "phi_fft" if kind.startswith("phi_fft") else "dct" if kind.startswith("dct") else \
-            "legendre" if kind.startswith("legendre") else None
-        if base is None:
+        if cnt == 0 or kind not in per_fn:
             continue
         fn_per_launch = batch * a.steps / cnt
         avg_s = kms * 1e-3 / cnt
-        ent = {"ms_total": kms, "launches": cnt, "avg_launch_ms": kms / cnt, "functions_per_launch": fn_per_launch}
-        if base == "legendre":
-            flops = alg[base]["flops"] * fn_per_launch
-            byts = alg[base]["bytes"] * fn_per_launch + alg[base]["table_bytes"]
-            ent.update({"bound": "tensor", "achieved": flops / avg_s / 1e12, "peak": fp64["dmma_tflops"],
-                        "unit": "TFLOP/s", "alg_flops_per_launch": flops, "alg_bytes_per_launch": byts,
-                        "hbm_gbs": byts / avg_s / 1e9})
+        byts = per_fn[kind][0] * fn_per_launch + per_fn[kind][2]
+        flops = per_fn[kind][1] * fn_per_launch
+        t_hbm, t_fp = byts / (hbm_peak * 1e9), flops / (fp64["dmma_tflops"] * 1e12)
+        ent = {"ms_total": kms, "launches": cnt, "avg_launch_ms": kms / cnt, "functions_per_launch": fn_per_launch,
+               "alg_bytes_per_launch": byts, "alg_flops_per_launch": flops,
+               "hbm_gbs": byts / avg_s / 1e9, "fp64_tflops": flops / avg_s / 1e12}
+        if t_fp > t_hbm:
+            ent.update({"bound": "tensor", "achieved": ent["fp64_tflops"], "peak": fp64["dmma_tflops"], "unit": "TFLOP/s"})
         else:
-            byts = alg[base]["bytes"] * fn_per_launch
-            ent.update({"bound": "hbm", "achieved": byts / avg_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                        "alg_bytes_per_launch": byts, "alg_flops_per_launch": alg[base]["flops"] * fn_per_launch})
+            ent.update({"bound": "hbm", "achieved": ent["hbm_gbs"], "peak": hbm_peak, "unit": "GB/s"})
         ent["frac"] = ent["achieved"] / ent["peak"]
         stages[kind] = ent
     dom = max(stages, key=lambda k: stages[k]["ms_total"]) if stages else None
@@ -309,7 +334,7 @@ def run_ours(a):
         roofline = {"kernel": dom, "bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"], "unit": d["unit"],
                     "frac": d["frac"], "traffic": None,
                     "peak_source": (hbm_src if d["bound"] == "hbm" else
-                                    "FP64 DMMA (mma.sync.m8n8k4.f64) micro-benchmark measured in this run; "
+                                    "FP64 tensor (DMMA mma.sync.m8n8k4.f64) micro-benchmark measured in this run; "
                                     "MEASURED_PEAKS.json has no FP64 figure"),
                     "share_of_step": d["ms_total"] / ms}
     launches = int(sum(c for _, c in prof.values()))

@@ -40,7 +40,9 @@ enum {
     S2KIT_K_TABLE_GEN = 6,     /* K7: recurrence + DCT-II(bw) + pack                     (cospml.c:161-242)       */
     S2KIT_K_ZONAL = 7,         /* K8a: m = 0 row sums                                    (FST_semi_memo.c:386-399)*/
     S2KIT_K_SPECTRAL_MUL = 8,  /* K8b: TransMult                                         (util.c:68-103)          */
-    S2KIT_K_COUNT = 9
+    S2KIT_K_FUSED_FWD = 9,     /* K2+K3 in one kernel (batched path, bw 64..512)         (seminaive.c:153-198)    */
+    S2KIT_K_FUSED_INV = 10,    /* K4+K5 in one kernel                                    (seminaive.c:56-115)     */
+    S2KIT_K_COUNT = 11
 };
 
 /* ---- plans ------------------------------------------------------------------------------------- */

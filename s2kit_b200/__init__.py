@@ -22,7 +22,7 @@ MEMO, FLY = 0, 1
 HOST, DEVICE = 0, 1
 
 KERNEL_KINDS = ["phi_fft_fwd", "dct_fwd", "legendre_fwd", "legendre_inv", "dct_inv", "phi_fft_inv", "table_gen",
-                "zonal", "spectral_mul"]
+                "zonal", "spectral_mul", "fused_fwd", "fused_inv"]
 
 _P = ctypes.POINTER(ctypes.c_double)
 _lib = None

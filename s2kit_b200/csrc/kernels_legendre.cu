@@ -12,29 +12,9 @@
 // tile, never touching shared memory; the X (or coefficient) panel of the CTA's columns sits in shared
 // memory for the whole order.  The inverse reads the SAME tiles as B fragments (4 rows x 8 columns), so
 // no transposed table is stored (the reference keeps one: cospml.c:301-362).
-#include "s2k_internal.cuh"
+#include "s2k_legendre.cuh"
 
 namespace s2k {
-
-__device__ __forceinline__ void dmma(double (&d)[2], double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(d[0]), "+d"(d[1])
-                 : "d"(a), "d"(b));
-}
-
-// index of f^(m,l=|m|) in the coefficient arrays  (IndexOfHarmonicCoeff, util.c:42-49)
-__device__ __forceinline__ int coef_base(int m, int bw) {
-    if (m >= 0) return m * bw - (m * (m - 1)) / 2;
-    int big = bw - 1;
-    return (big * (big + 3)) / 2 + 1 + ((big + m) * (big + m + 1)) / 2;
-}
-
-__host__ __device__ inline int panel_stride(int bw) {
-    int hb = ((bw + 1) / 2 + 7) / 8 * 8;
-    return hb + ((4 - hb % 16) + 16) % 16;  // == 4 (mod 16): conflict-free 64-bit fragment loads
-}
-
-constexpr int LEG_WARPS = 8;
 
 // ------------------------------------------------------------------------------------------------ K3
 // grid: x = column tile, y = order (heavy orders first), z = row split.  NC columns per CTA.
@@ -68,6 +48,10 @@ __global__ void __launch_bounds__(LEG_WARPS * 32) k_legendre_fwd(
 
     const BlockMeta mb0 = meta[2 * m], mb1 = meta[2 * m + 1];
     const int total = mb0.nrt + mb1.nrt;
+    uint32_t* srt = reinterpret_cast<uint32_t*>(Xs + 2 * NC * CS);  // row-tile starts of both parity blocks
+    for (int i = tid; i < total; i += blockDim.x)
+        srt[i] = rt_start[(i < mb0.nrt ? mb0.rt_base : mb1.rt_base - mb0.nrt) + i];
+    __syncthreads();
     const double* tbase = table + (order_start[m] - table_shift) * 64 + lane * 2;
     const int g = lane >> 2, q4 = lane & 3;
     const double sgn_neg = (m & 1) ? -1.0 : 1.0;
@@ -78,28 +62,14 @@ __global__ void __launch_bounds__(LEG_WARPS * 32) k_legendre_fwd(
         const int p = q < mb0.nrt ? 0 : 1;
         const BlockMeta mb = p ? mb1 : mb0;
         const int rt = p ? (mb.nrt - 1 - (q - mb0.nrt)) : (mb.nrt - 1 - q);
-        const int last_row = min(8 * rt + 7, mb.rows - 1);
-        const int ctn = (mb.len0 + last_row + 7) >> 3;
-        const double* tp = tbase + (uint64_t)rt_start[mb.rt_base + rt] * 64;
+        const int ctn = tiles_in_row(mb, rt);
+        const double* tp = tbase + (uint64_t)srt[(p ? mb0.nrt : 0) + rt] * 64;
         const double* xp = Xs + (p * NC + g) * CS + q4;
 
         double acc[NC / 8][2];
 #pragma unroll
         for (int j = 0; j < NC / 8; ++j) acc[j][0] = acc[j][1] = 0.0;
-
-        double2 a = __ldg(reinterpret_cast<const double2*>(tp));
-        for (int ct = 0; ct < ctn; ++ct) {
-            double2 an = a;
-            if (ct + 1 < ctn) an = __ldg(reinterpret_cast<const double2*>(tp + (ct + 1) * 64));
-#pragma unroll
-            for (int j = 0; j < NC / 8; ++j) {
-                double b0 = xp[j * 8 * CS + 8 * ct];
-                double b1 = xp[j * 8 * CS + 8 * ct + 4];
-                dmma(acc[j], a.x, b0);
-                dmma(acc[j], a.y, b1);
-            }
-            a = an;
-        }
+        fwd_row_tile<NC>(tp, xp, CS, ctn, acc);
 
         // ---- epilogue: lane holds rows r = 8rt + g, columns 8j + 2 q4 + {0,1}
         const int r = 8 * rt + g;
@@ -167,6 +137,10 @@ __global__ void __launch_bounds__(LEG_WARPS * 32) k_legendre_inv(
 
     const BlockMeta mb0 = meta[2 * m], mb1 = meta[2 * m + 1];
     const int nct = (((bw + 1) / 2) + 7) >> 3;  // column tiles needed to cover every k < bw of one parity
+    uint32_t* srt = reinterpret_cast<uint32_t*>(Cs + 2 * NC * CS);
+    for (int i = tid; i < mb0.nrt + mb1.nrt; i += blockDim.x)
+        srt[i] = rt_start[(i < mb0.nrt ? mb0.rt_base : mb1.rt_base - mb0.nrt) + i];
+    __syncthreads();
     const double* tbase = table + (order_start[m] - table_shift) * 64;
     const int g = lane >> 2, q4 = lane & 3;
     // B fragment of k-step s: element (row q4 + 4s, col g) of the 8x8 tile
@@ -178,25 +152,7 @@ __global__ void __launch_bounds__(LEG_WARPS * 32) k_legendre_inv(
         double acc[NC / 8][2];
 #pragma unroll
         for (int j = 0; j < NC / 8; ++j) acc[j][0] = acc[j][1] = 0.0;
-
-        // first row tile whose trapezoid reaches column tile ct: len0 + min(8rt+7, rows-1) > 8ct
-        int rt_min = 0;
-        if (8 * ct >= mb.len0 + 7) rt_min = (8 * ct - mb.len0 - 7) / 8 + 1;
-        const double* cp = Cs + (p * NC + g) * CS + q4;
-        for (int rt = rt_min; rt < mb.nrt; ++rt) {
-            int last_row = min(8 * rt + 7, mb.rows - 1);
-            int ctn = (mb.len0 + last_row + 7) >> 3;
-            if (ct >= ctn) continue;
-            const double* tp = tbase + ((uint64_t)rt_start[mb.rt_base + rt] + ct) * 64;
-            double b0 = __ldg(tp + boff0), b1 = __ldg(tp + boff1);
-#pragma unroll
-            for (int j = 0; j < NC / 8; ++j) {
-                double a0 = cp[j * 8 * CS + 8 * rt];
-                double a1 = cp[j * 8 * CS + 8 * rt + 4];
-                dmma(acc[j], a0, b0);
-                dmma(acc[j], a1, b1);
-            }
-        }
+        inv_col_tile<NC>(tbase, srt + (p ? mb0.nrt : 0), mb, ct, Cs + (p * NC + g) * CS + q4, CS, boff0, boff1, acc);
         // ---- epilogue: lane holds column 8j + g, cosine slots c = 8ct + 2 q4 + {0,1}
 #pragma unroll
         for (int j = 0; j < NC / 8; ++j) {
@@ -222,7 +178,7 @@ static cudaError_t leg_fwd_nc(s2kit_cuda_plan* p, const double* table, uint64_t 
                               double* ico, long coef_stride, int nfun, int m_lo, int m_hi, int real_fmt, int rowsplit) {
     int cols_per_fn = real_fmt ? 2 : 4;
     int NF = NC / cols_per_fn;
-    size_t smem = sizeof(double) * 2 * NC * panel_stride(p->bw);
+    size_t smem = sizeof(double) * 2 * NC * panel_stride(p->bw) + sizeof(uint32_t) * (p->bw / 8 + 8);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_legendre_fwd<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -240,7 +196,7 @@ static cudaError_t leg_inv_nc(s2kit_cuda_plan* p, const double* table, uint64_t 
                               int real_fmt, int rowsplit) {
     int cols_per_fn = real_fmt ? 2 : 4;
     int NF = NC / cols_per_fn;
-    size_t smem = sizeof(double) * 2 * NC * panel_stride(p->bw);
+    size_t smem = sizeof(double) * 2 * NC * panel_stride(p->bw) + sizeof(uint32_t) * (p->bw / 8 + 8);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_legendre_inv<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -258,7 +214,8 @@ static int pick_nc(int bw, int nfun, int real_fmt) {
     int cols = nfun * (real_fmt ? 2 : 4);
     size_t per_col = sizeof(double) * 2 * panel_stride(bw);
     int nc = 32;
-    while (nc > 8 && (nc / 2 >= cols || per_col * nc > 100 * 1024)) nc /= 2;
+    // prefer panels <= 110 KB (two CTAs per SM); a single 8-column panel may take up to the whole SM
+    while (nc > 8 && (nc / 2 >= cols || per_col * nc > 110 * 1024)) nc /= 2;
     return nc;
 }
 

@@ -7,6 +7,7 @@
 // variant, src/FST_semi_fly.c:96,259-261).
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -167,6 +168,10 @@ static int plan_create_impl(s2kit_cuda_plan** out, int bw, int variant, int max_
     p->rank = rank;
     p->nranks = nranks;
     p->fast = is_pow2(bw) && bw >= 16;
+    {
+        const char* nf = getenv("S2KIT_CUDA_NO_FUSE");
+        p->fuse = !(nf && nf[0] == '1');
+    }
     if (!p->fast && bw > 512) {
         delete p;
         return fail_msg("bandwidths above 512 must be powers of two");
@@ -343,10 +348,14 @@ static int fst_device(s2kit_cuda_plan* p, const double* rdata, const double* ida
         double* rc = rco + (long)c0 * coef_stride;
         double* ic = ico + (long)c0 * coef_stride;
         CK(s2k::launch_phi_fft_fwd(p, rd, id, data_stride, p->d_S, nf, fmt));
-        CK(s2k::launch_dct_fwd(p, p->d_S, p->d_X, nf, 0, nrows, fmt));
+        const bool fused = s2k::fused_supported(p, nf, fmt);
+        if (!fused) CK(s2k::launch_dct_fwd(p, p->d_S, p->d_X, nf, 0, nrows, fmt));
         for (const OrderGroup& g : order_groups(p, 0, bw)) {
             if (p->variant == S2KIT_CUDA_FLY) CK(s2k::launch_table_gen(p, p->d_table, g.shift, g.lo, g.hi));
-            CK(s2k::launch_legendre_fwd(p, p->d_table, g.shift, p->d_X, rc, ic, coef_stride, nf, g.lo, g.hi, fmt));
+            if (fused)
+                CK(s2k::launch_fused_fwd(p, p->d_table, g.shift, p->d_S, rc, ic, coef_stride, nf, g.lo, g.hi, fmt));
+            else
+                CK(s2k::launch_legendre_fwd(p, p->d_table, g.shift, p->d_X, rc, ic, coef_stride, nf, g.lo, g.hi, fmt));
         }
     }
     return 0;
@@ -362,11 +371,15 @@ static int inv_fst_device(s2kit_cuda_plan* p, const double* rco, const double* i
         const double* ic = ico + (long)c0 * coef_stride;
         double* rd = rdata + (long)c0 * data_stride;
         double* id = idata + (long)c0 * data_stride;
+        const bool fused = s2k::fused_supported(p, nf, fmt);
         for (const OrderGroup& g : order_groups(p, 0, bw)) {
             if (p->variant == S2KIT_CUDA_FLY) CK(s2k::launch_table_gen(p, p->d_table, g.shift, g.lo, g.hi));
-            CK(s2k::launch_legendre_inv(p, p->d_table, g.shift, rc, ic, coef_stride, p->d_X, nf, g.lo, g.hi, fmt));
+            if (fused)
+                CK(s2k::launch_fused_inv(p, p->d_table, g.shift, rc, ic, coef_stride, p->d_S, nf, g.lo, g.hi, fmt));
+            else
+                CK(s2k::launch_legendre_inv(p, p->d_table, g.shift, rc, ic, coef_stride, p->d_X, nf, g.lo, g.hi, fmt));
         }
-        CK(s2k::launch_dct_inv(p, p->d_X, p->d_S, nf, 0, nrows, fmt));
+        if (!fused) CK(s2k::launch_dct_inv(p, p->d_X, p->d_S, nf, 0, nrows, fmt));
         CK(s2k::launch_phi_fft_inv(p, p->d_S, rd, id, data_stride, nf, fmt));
     }
     return 0;

@@ -9,8 +9,8 @@
 // the first pass reads / the last pass leaves the SAME eight slots {t + s*N/8}: the first pass can be fed
 // straight from global memory and the last pass can be consumed straight from registers.  Between
 // passes the points are exchanged through shared memory (split re/im arrays, index padded by i>>4, which
-// keeps the 64-bit accesses of all passes within 1.25x of conflict-free).  Twiddles come from a
-// host-computed exact table W[q] = (cos 2 pi q/N, -sin 2 pi q/N).
+// keeps the 64-bit accesses of all passes within 1.25x of conflict-free).  The base twiddle of each butterfly
+// comes from a host-computed exact table W[q] = (cos 2 pi q/N, -sin 2 pi q/N).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -86,6 +86,13 @@ __device__ __forceinline__ int fft_out_index(int e, int t) {
 template <int N>
 __device__ __forceinline__ int fft_in_index(int e, int t) { return t + e * (N / 8); }
 
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// Twiddles: ONE table load per butterfly (w = W^(k*STEP)); the higher powers w^2..w^7 are formed by at most
+// three chained complex multiplications.  (Loading all seven from the table cost 7 scattered 16-byte L1
+// requests per thread and pass and saturated the LSU data pipe -- profiles/r1_ncu_summary.md.)
 template <int N, int NS, int R>
 __device__ __forceinline__ void fft_pass_compute(double (&xr)[8], double (&xi)[8], int t,
                                                  const double2* __restrict__ tw) {
@@ -94,12 +101,23 @@ __device__ __forceinline__ void fft_pass_compute(double (&xr)[8], double (&xi)[8
     for (int q = 0; q < NB; ++q) {
         if constexpr (NS > 1) {
             int k = (t + q * T8) & (NS - 1);
+            double2 w[R];
+            w[1] = __ldg(&tw[k * STEP]);
+            if constexpr (R >= 4) {
+                w[2] = cmul(w[1], w[1]);
+                w[3] = cmul(w[2], w[1]);
+            }
+            if constexpr (R == 8) {
+                w[4] = cmul(w[2], w[2]);
+                w[5] = cmul(w[4], w[1]);
+                w[6] = cmul(w[3], w[3]);
+                w[7] = cmul(w[4], w[3]);
+            }
 #pragma unroll
             for (int r = 1; r < R; ++r) {
-                double2 w = __ldg(&tw[k * r * STEP]);
                 double a = xr[q * R + r], b = xi[q * R + r];
-                xr[q * R + r] = a * w.x - b * w.y;
-                xi[q * R + r] = a * w.y + b * w.x;
+                xr[q * R + r] = a * w[r].x - b * w[r].y;
+                xi[q * R + r] = a * w[r].y + b * w[r].x;
             }
         }
         dftR<R>(&xr[q * R], &xi[q * R]);

@@ -35,6 +35,7 @@ struct ProfileSlot {
 struct s2kit_cuda_plan {
     int bw = 0, n = 0, variant = 0, device = 0, chunk = 1;
     bool fast = false;  // power-of-two bandwidth >= 16: radix FFT kernels; otherwise direct O(n^2) kernels
+    bool fuse = true;   // fused DCT+Legendre kernels for batched calls (S2KIT_CUDA_NO_FUSE=1 disables)
     cudaStream_t stream = nullptr;
     bool own_stream = true;
 
@@ -125,6 +126,13 @@ cudaError_t launch_spectral_mul(s2kit_cuda_plan* p, const double* rd, const doub
                                 const double* rf, const double* ifl, long filt_stride, double* rres, double* ires,
                                 long res_stride, int nfun);
 int table_unit_rows(int bw);
+// fused K2+K3 / K4+K5 (kernels_fused.cu)
+bool fused_supported(const s2kit_cuda_plan* p, int nfun, int data_format);
+cudaError_t launch_fused_fwd(s2kit_cuda_plan* p, const double* table, uint64_t table_shift, const double* S,
+                             double* rco, double* ico, long coef_stride, int nfun, int m_lo, int m_hi, int data_format);
+cudaError_t launch_fused_inv(s2kit_cuda_plan* p, const double* table, uint64_t table_shift, const double* rco,
+                             const double* ico, long coef_stride, double* G, int nfun, int m_lo, int m_hi,
+                             int data_format);
 
 // peaks
 cudaError_t measure_fp64(double* fma_tflops, double* dmma_tflops);

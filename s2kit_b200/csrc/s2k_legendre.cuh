@@ -1,0 +1,108 @@
+// s2k_legendre.cuh -- helpers shared by the Legendre contraction kernels (kernels_legendre.cu, kernels_fused.cu).
+#pragma once
+#include "s2k_internal.cuh"
+
+namespace s2k {
+
+constexpr int LEG_WARPS = 8;
+constexpr int LEG_PREFETCH = 4;  // table tiles kept in flight per warp
+
+// D(8x8) += A(8x4) * B(4x8), FP64 tensor core (SASS: DMMA.8x8x4)
+__device__ __forceinline__ void dmma(double (&d)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d[0]), "+d"(d[1])
+                 : "d"(a), "d"(b));
+}
+
+// index of f^(m,l=|m|) in the coefficient arrays  (IndexOfHarmonicCoeff, util.c:42-49)
+__device__ __forceinline__ int coef_base(int m, int bw) {
+    if (m >= 0) return m * bw - (m * (m - 1)) / 2;
+    int big = bw - 1;
+    return (big * (big + 3)) / 2 + 1 + ((big + m) * (big + m + 1)) / 2;
+}
+
+// stride (doubles) of one column of the shared-memory panel: holds ceil(bw/2) entries of one parity,
+// == 4 (mod 16) so that the 64-bit MMA fragment loads are bank-conflict free
+__host__ __device__ inline int panel_stride(int bw) {
+    int hb = ((bw + 1) / 2 + 7) / 8 * 8;
+    return hb + ((4 - hb % 16) + 16) % 16;
+}
+
+// number of 8-wide column tiles of row tile rt in a parity block
+__device__ __forceinline__ int tiles_in_row(const BlockMeta& mb, int rt) {
+    return (mb.len0 + min(8 * rt + 7, mb.rows - 1) + 7) >> 3;
+}
+
+// Forward main loop for one (parity, row tile): acc[j] += T_tile * X_panel for NC/8 column tiles.
+// tp: first tile of the row tile (+ 2*lane); xp: panel base of this lane (parity, column g, slot q4).
+template <int NC>
+__device__ __forceinline__ void fwd_row_tile(const double* __restrict__ tp, const double* xp, int CS, int ctn,
+                                             double (&acc)[NC / 8][2]) {
+    double2 abuf[LEG_PREFETCH];
+#pragma unroll
+    for (int u = 0; u < LEG_PREFETCH; ++u)
+        if (u < ctn) abuf[u] = __ldg(reinterpret_cast<const double2*>(tp + u * 64));
+    for (int ct0 = 0; ct0 < ctn; ct0 += LEG_PREFETCH) {
+#pragma unroll
+        for (int u = 0; u < LEG_PREFETCH; ++u) {
+            const int ct = ct0 + u;
+            if (ct < ctn) {
+                const double2 a = abuf[u];
+                if (ct + LEG_PREFETCH < ctn)
+                    abuf[u] = __ldg(reinterpret_cast<const double2*>(tp + (ct + LEG_PREFETCH) * 64));
+#pragma unroll
+                for (int j = 0; j < NC / 8; ++j) {
+                    double b0 = xp[j * 8 * CS + 8 * ct];
+                    double b1 = xp[j * 8 * CS + 8 * ct + 4];
+                    dmma(acc[j], a.x, b0);
+                    dmma(acc[j], a.y, b1);
+                }
+            }
+        }
+    }
+}
+
+// Inverse main loop for one (parity, column tile ct): acc[j] += C_panel * T_tile over the row tiles that reach ct.
+// srt: this parity block's row-tile starts (shared memory); cp: panel base of this lane.
+template <int NC>
+__device__ __forceinline__ void inv_col_tile(const double* __restrict__ tbase, const uint32_t* srt, const BlockMeta& mb,
+                                             int ct, const double* cp, int CS, int boff0, int boff1,
+                                             double (&acc)[NC / 8][2]) {
+    int rt_min = 0;
+    if (8 * ct >= mb.len0 + 7) rt_min = (8 * ct - mb.len0 - 7) / 8 + 1;
+    // rows below rt_min never reach ct; from the first row tile that does, all later ones do (lengths grow)
+    while (rt_min < mb.nrt && ct >= tiles_in_row(mb, rt_min)) ++rt_min;
+    const int cnt = mb.nrt - rt_min;
+    double b0buf[LEG_PREFETCH], b1buf[LEG_PREFETCH];
+#pragma unroll
+    for (int u = 0; u < LEG_PREFETCH; ++u)
+        if (u < cnt) {
+            const double* tp = tbase + ((uint64_t)srt[rt_min + u] + ct) * 64;
+            b0buf[u] = __ldg(tp + boff0);
+            b1buf[u] = __ldg(tp + boff1);
+        }
+    for (int i0 = 0; i0 < cnt; i0 += LEG_PREFETCH) {
+#pragma unroll
+        for (int u = 0; u < LEG_PREFETCH; ++u) {
+            const int i = i0 + u;
+            if (i < cnt) {
+                const int rt = rt_min + i;
+                const double b0 = b0buf[u], b1 = b1buf[u];
+                if (i + LEG_PREFETCH < cnt) {
+                    const double* tp = tbase + ((uint64_t)srt[rt + LEG_PREFETCH] + ct) * 64;
+                    b0buf[u] = __ldg(tp + boff0);
+                    b1buf[u] = __ldg(tp + boff1);
+                }
+#pragma unroll
+                for (int j = 0; j < NC / 8; ++j) {
+                    double a0 = cp[j * 8 * CS + 8 * rt];
+                    double a1 = cp[j * 8 * CS + 8 * rt + 4];
+                    dmma(acc[j], a0, b0);
+                    dmma(acc[j], a1, b1);
+                }
+            }
+        }
+    }
+}
+
+}  // namespace s2k
