@@ -76,22 +76,27 @@ __global__ void __launch_bounds__(N / 8 * LT) k_phi_fft_inv(const double* __rest
     const double* Gr = G + (long)f * 2 * N * N + j0;
     const double* Gi = Gr + (long)N * N;
     // inverse DFT through the forward one: feed (im, re), read back (im, re)   (FST_semi_memo.c:350)
-    for (int flat = tid; flat < N * LT; flat += NT) {
-        int j2 = flat % LT, mp = flat / LT;
-        double vr = 0.0, vi = 0.0;
-        if (mp != N / 2) {
-            if (real_fmt && mp > N / 2) {
-                // conjugate mirror of row n - m'   (FST_semi_memo.c:333-341)
-                vr = __ldg(Gr + (long)(N - mp) * N + j2);
-                vi = -__ldg(Gi + (long)(N - mp) * N + j2);
-            } else {
-                vr = __ldg(Gr + (long)mp * N + j2);
-                vi = __ldg(Gi + (long)mp * N + j2);
-            }
+    // N*LT elements per part and NT = N/8*LT threads: exactly 8 per thread, all loads issued before any use
+    {
+        double vr[8], vi[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            int flat = tid + it * NT;
+            int j2 = flat % LT, mp = flat / LT;
+            int row = (real_fmt && mp > N / 2) ? N - mp : mp;  // conjugate mirror of row n - m' (FST_semi_memo.c:333-341)
+            bool dead = (mp == N / 2);
+            vr[it] = dead ? 0.0 : __ldg(Gr + (long)row * N + j2);
+            vi[it] = dead ? 0.0 : __ldg(Gi + (long)row * N + j2);
+            if (real_fmt && mp > N / 2) vi[it] = -vi[it];
         }
-        int p = fft_pad(mp);
-        sre[j2 * RS + p] = vi;
-        sim[j2 * RS + p] = vr;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            int flat = tid + it * NT;
+            int j2 = flat % LT, mp = flat / LT;
+            int p = fft_pad(mp);
+            sre[j2 * RS + p] = vi[it];
+            sim[j2 * RS + p] = vr[it];
+        }
     }
     __syncthreads();
     double xr[8], xi[8];

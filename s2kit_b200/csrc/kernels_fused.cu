@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_fwd(
     double* ex = smem + 2 * NC * CS;                     // [G][2][NP]   FFT exchange rows
     uint32_t* srt = reinterpret_cast<uint32_t*>(ex + G * 2 * NP);
 
+    prefetch_order_l2(table + (order_start[m] - table_shift) * 64, order_start[m + 1] - order_start[m], tid, FUSED_THREADS);
     const BlockMeta mb0 = meta[2 * m], mb1 = meta[2 * m + 1];
     const int total = mb0.nrt + mb1.nrt;
     for (int i = tid; i < total; i += FUSED_THREADS)
@@ -178,20 +179,28 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_inv(
     uint32_t* srt = reinterpret_cast<uint32_t*>(ex + G * 2 * NP);
     static_assert(NC * VS <= 2 * NC * (B / 2 + 4), "result panel must fit in the coefficient panel");
 
-    for (int i = tid; i < 2 * NC * CS; i += FUSED_THREADS) Cs[i] = 0.0;
+    prefetch_order_l2(table + (order_start[m] - table_shift) * 64, order_start[m + 1] - order_start[m], tid, FUSED_THREADS);
     const BlockMeta mb0 = meta[2 * m], mb1 = meta[2 * m + 1];
     for (int i = tid; i < mb0.nrt + mb1.nrt; i += FUSED_THREADS)
         srt[i] = rt_start[(i < mb0.nrt ? mb0.rt_base : mb1.rt_base - mb0.nrt) + i];
-    __syncthreads();
     const int base_pos = coef_base(m, B), base_neg = coef_base(-m, B);
     for (int col = warp; col < NC; col += LEG_WARPS) {
         int fl = col / cols_per_fn, sub = col % cols_per_fn;
         int sgn = real_fmt ? 0 : (sub >> 1), part = sub & 1;
         int f = f0 + fl;
-        if (f >= nfun || (sgn && m == 0)) continue;
+        double* d0 = Cs + col * CS;
+        double* d1 = Cs + (NC + col) * CS;
+        if (f >= nfun || (sgn && m == 0)) {
+            for (int c = lane; c < CS; c += 32) d0[c] = d1[c] = 0.0;
+            continue;
+        }
         const double* src = (part ? ico : rco) + (long)f * coef_stride + (sgn ? base_neg : base_pos);
-        for (int o = lane; o < B - m; o += 32) Cs[((o & 1) * NC + col) * CS + (o >> 1)] = __ldg(src + o);
+        const int cnt = B - m, h0 = (cnt + 1) / 2, h1 = cnt / 2;
+        for (int o = lane; o < cnt; o += 32) cp_async8(((o & 1) ? d1 : d0) + (o >> 1), src + o);
+        for (int c = h0 + lane; c < CS; c += 32) d0[c] = 0.0;
+        for (int c = h1 + lane; c < CS; c += 32) d1[c] = 0.0;
     }
+    cp_async_wait_all();
     __syncthreads();
 
     const double* tbase = table + (order_start[m] - table_shift) * 64;

@@ -32,18 +32,26 @@ __global__ void __launch_bounds__(LEG_WARPS * 32) k_legendre_fwd(
     const int f0 = blockIdx.x * NF;
     double* Xs = smem;  // [2][NC][CS]
 
-    // ---- stage the X panel, de-interleaved by cosine-index parity, zero padded
-    for (int i = tid; i < 2 * NC * CS; i += blockDim.x) Xs[i] = 0.0;
-    __syncthreads();
+    prefetch_order_l2(table + (order_start[m] - table_shift) * 64, order_start[m + 1] - order_start[m], tid, blockDim.x);
+    // ---- stage the X panel, de-interleaved by cosine-index parity; dead columns and the pad slots are zero
+    const int half = (bw + 1) / 2;
     for (int col = warp; col < NC; col += LEG_WARPS) {
         int fl = col / cols_per_fn, sub = col % cols_per_fn;
         int sgn = real_fmt ? 0 : (sub >> 1), part = sub & 1;
         int f = f0 + fl;
-        if (f >= nfun || (sgn && m == 0)) continue;
+        double* d0 = Xs + col * CS;
+        double* d1 = Xs + (NC + col) * CS;
+        if (f >= nfun || (sgn && m == 0)) {
+            for (int c = lane; c < CS; c += 32) d0[c] = d1[c] = 0.0;
+            continue;
+        }
         int mp = sgn ? n - m : m;
         const double* src = X + (((long)f * n + mp) * 2 + part) * bw;
-        for (int k = lane; k < bw; k += 32) Xs[((k & 1) * NC + col) * CS + (k >> 1)] = __ldg(src + k);
+        for (int k = lane; k < bw; k += 32) cp_async8(((k & 1) ? d1 : d0) + (k >> 1), src + k);
+        for (int c = half + lane; c < CS; c += 32) d0[c] = d1[c] = 0.0;
+        if ((bw & 1) && lane == 0) d1[half - 1] = 0.0;  // odd bw: parity 1 has one entry less
     }
+    cp_async_wait_all();
     __syncthreads();
 
     const BlockMeta mb0 = meta[2 * m], mb1 = meta[2 * m + 1];
@@ -122,17 +130,25 @@ __global__ void __launch_bounds__(LEG_WARPS * 32) k_legendre_inv(
     const int f0 = blockIdx.x * NF;
     double* Cs = smem;  // [2][NC][CS], row index r = (l-m)>>1
 
-    for (int i = tid; i < 2 * NC * CS; i += blockDim.x) Cs[i] = 0.0;
-    __syncthreads();
+    prefetch_order_l2(table + (order_start[m] - table_shift) * 64, order_start[m + 1] - order_start[m], tid, blockDim.x);
     const int base_pos = coef_base(m, bw), base_neg = coef_base(-m, bw);
     for (int col = warp; col < NC; col += LEG_WARPS) {
         int fl = col / cols_per_fn, sub = col % cols_per_fn;
         int sgn = real_fmt ? 0 : (sub >> 1), part = sub & 1;
         int f = f0 + fl;
-        if (f >= nfun || (sgn && m == 0)) continue;
+        double* d0 = Cs + col * CS;
+        double* d1 = Cs + (NC + col) * CS;
+        if (f >= nfun || (sgn && m == 0)) {
+            for (int c = lane; c < CS; c += 32) d0[c] = d1[c] = 0.0;
+            continue;
+        }
         const double* src = (part ? ico : rco) + (long)f * coef_stride + (sgn ? base_neg : base_pos);
-        for (int o = lane; o < bw - m; o += 32) Cs[((o & 1) * NC + col) * CS + (o >> 1)] = __ldg(src + o);
+        const int cnt = bw - m, h0 = (cnt + 1) / 2, h1 = cnt / 2;  // entries of parity 0 / 1
+        for (int o = lane; o < cnt; o += 32) cp_async8(((o & 1) ? d1 : d0) + (o >> 1), src + o);
+        for (int c = h0 + lane; c < CS; c += 32) d0[c] = 0.0;
+        for (int c = h1 + lane; c < CS; c += 32) d1[c] = 0.0;
     }
+    cp_async_wait_all();
     __syncthreads();
 
     const BlockMeta mb0 = meta[2 * m], mb1 = meta[2 * m + 1];

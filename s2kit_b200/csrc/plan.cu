@@ -138,6 +138,29 @@ static void build_layout(s2kit_cuda_plan* p, const std::vector<char>& owned) {
     p->h_unit_first[bw] = (int)p->h_units.size() / 2;
 }
 
+// Keep a Memo table that fits comfortably in L2 resident across launches: the batch streams hundreds of MB through
+// L2 between two uses of the same order's tiles (persisting-L2 access policy window on the plan's stream).
+static void apply_table_l2_policy(s2kit_cuda_plan* p) {
+    if (p->variant != S2KIT_CUDA_MEMO || !p->d_table || !p->l2_persist) return;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, p->device) != cudaSuccess) return;
+    size_t want = p->table_bytes;
+    if (prop.persistingL2CacheMaxSize <= 0 || want > (size_t)prop.persistingL2CacheMaxSize) return;
+    if (want > (size_t)prop.accessPolicyMaxWindowSize) return;
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    attr.accessPolicyWindow.base_ptr = p->d_table;
+    attr.accessPolicyWindow.num_bytes = want;
+    attr.accessPolicyWindow.hitRatio = 1.0f;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(p->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+}
+
 template <typename T>
 static cudaError_t upload(T** dptr, const void* host, size_t count) {
     cudaError_t e = cudaMalloc((void**)dptr, count * sizeof(T));
@@ -171,6 +194,8 @@ static int plan_create_impl(s2kit_cuda_plan** out, int bw, int variant, int max_
     {
         const char* nf = getenv("S2KIT_CUDA_NO_FUSE");
         p->fuse = !(nf && nf[0] == '1');
+        const char* np = getenv("S2KIT_CUDA_NO_L2PERSIST");
+        p->l2_persist = !(np && np[0] == '1');
     }
     if (!p->fast && bw > 512) {
         delete p;
@@ -262,6 +287,7 @@ static int plan_create_impl(s2kit_cuda_plan** out, int bw, int variant, int max_
     CK(cudaMalloc((void**)&p->d_S, sizeof(double) * (size_t)chunk * 2 * n * n));
     CK(cudaMalloc((void**)&p->d_X, sizeof(double) * (size_t)chunk * n * 2 * bw));
     CK(cudaStreamSynchronize(p->stream));
+    apply_table_l2_policy(p);
     *out = p;
     return 0;
 }
@@ -295,6 +321,7 @@ extern "C" int s2kit_cuda_plan_set_stream(s2kit_cuda_plan* p, void* stream) {
     if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
     p->stream = (cudaStream_t)stream;
     p->own_stream = false;
+    apply_table_l2_policy(p);
     return 0;
 }
 extern "C" void* s2kit_cuda_plan_stream(s2kit_cuda_plan* p) { return p ? (void*)p->stream : nullptr; }

@@ -36,6 +36,7 @@ struct s2kit_cuda_plan {
     int bw = 0, n = 0, variant = 0, device = 0, chunk = 1;
     bool fast = false;  // power-of-two bandwidth >= 16: radix FFT kernels; otherwise direct O(n^2) kernels
     bool fuse = true;   // fused DCT+Legendre kernels for batched calls (S2KIT_CUDA_NO_FUSE=1 disables)
+    bool l2_persist = true;  // persisting-L2 window on a Memo table that fits (S2KIT_CUDA_NO_L2PERSIST=1 disables)
     cudaStream_t stream = nullptr;
     bool own_stream = true;
 

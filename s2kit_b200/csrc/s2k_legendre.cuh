@@ -28,6 +28,25 @@ __host__ __device__ inline int panel_stride(int bw) {
     return hb + ((4 - hb % 16) + 16) % 16;
 }
 
+// Pull one order's table (contiguous tiles) into L2 at CTA start.  The table is touched once per launch, in a short
+// window per order, and the streaming traffic of the batch evicts it between launches: without this every tile of
+// the main loop is a first-touch DRAM miss (~1 us) that the few tiles of register prefetch cannot cover
+// (profiles/r1_ncu_summary.md).
+__device__ __forceinline__ void prefetch_order_l2(const double* base, uint64_t tiles, int tid, int nthreads) {
+    const char* p = reinterpret_cast<const char*>(base);
+    const uint64_t lines = tiles * 4;  // 512-byte tiles, 128-byte lines
+    for (uint64_t i = tid; i < lines; i += nthreads) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + i * 128));
+}
+
+// 8-byte asynchronous global -> shared copy (LDGSTS): no register staging, all copies of a thread in flight at once
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+    unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
 // number of 8-wide column tiles of row tile rt in a parity block
 __device__ __forceinline__ int tiles_in_row(const BlockMeta& mb, int rt) {
     return (mb.len0 + min(8 * rt + 7, mb.rows - 1) + 7) >> 3;
@@ -50,13 +69,17 @@ __device__ __forceinline__ void fwd_row_tile(const double* __restrict__ tp, cons
                 const double2 a = abuf[u];
                 if (ct + LEG_PREFETCH < ctn)
                     abuf[u] = __ldg(reinterpret_cast<const double2*>(tp + (ct + LEG_PREFETCH) * 64));
+                double b[NC / 8][2];
 #pragma unroll
                 for (int j = 0; j < NC / 8; ++j) {
-                    double b0 = xp[j * 8 * CS + 8 * ct];
-                    double b1 = xp[j * 8 * CS + 8 * ct + 4];
-                    dmma(acc[j], a.x, b0);
-                    dmma(acc[j], a.y, b1);
+                    b[j][0] = xp[j * 8 * CS + 8 * ct];
+                    b[j][1] = xp[j * 8 * CS + 8 * ct + 4];
                 }
+                // k-step outer: consecutive DMMAs go to different accumulators
+#pragma unroll
+                for (int j = 0; j < NC / 8; ++j) dmma(acc[j], a.x, b[j][0]);
+#pragma unroll
+                for (int j = 0; j < NC / 8; ++j) dmma(acc[j], a.y, b[j][1]);
             }
         }
     }
@@ -93,13 +116,16 @@ __device__ __forceinline__ void inv_col_tile(const double* __restrict__ tbase, c
                     b0buf[u] = __ldg(tp + boff0);
                     b1buf[u] = __ldg(tp + boff1);
                 }
+                double a[NC / 8][2];
 #pragma unroll
                 for (int j = 0; j < NC / 8; ++j) {
-                    double a0 = cp[j * 8 * CS + 8 * rt];
-                    double a1 = cp[j * 8 * CS + 8 * rt + 4];
-                    dmma(acc[j], a0, b0);
-                    dmma(acc[j], a1, b1);
+                    a[j][0] = cp[j * 8 * CS + 8 * rt];
+                    a[j][1] = cp[j * 8 * CS + 8 * rt + 4];
                 }
+#pragma unroll
+                for (int j = 0; j < NC / 8; ++j) dmma(acc[j], a[j][0], b0);
+#pragma unroll
+                for (int j = 0; j < NC / 8; ++j) dmma(acc[j], a[j][1], b1);
             }
         }
     }
