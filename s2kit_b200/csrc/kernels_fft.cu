@@ -314,8 +314,7 @@ __global__ void k_direct_dct_inv(const double* __restrict__ V, double* __restric
 // ------------------------------------------------------------------------------------------------ launchers
 template <typename K>
 static cudaError_t set_smem(K kernel, size_t bytes) {
-    if (bytes > 48 * 1024) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    return cudaSuccess;
+    return ensure_smem(reinterpret_cast<const void*>(kernel), bytes);
 }
 
 template <int N>

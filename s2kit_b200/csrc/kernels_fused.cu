@@ -298,7 +298,7 @@ static cudaError_t fused_fwd_launch(s2kit_cuda_plan* p, const double* table, uin
                                     double* rco, double* ico, long coef_stride, int nfun, int m_lo, int m_hi,
                                     int real_fmt) {
     size_t smem = fused_smem<N, NC>();
-    cudaError_t e = cudaFuncSetAttribute(k_fused_fwd<N, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = ensure_smem(reinterpret_cast<const void*>(k_fused_fwd<N, NC>), smem);
     if (e != cudaSuccess) return e;
     int NF = NC / (real_fmt ? 2 : 4);
     dim3 grid((nfun + NF - 1) / NF, m_hi - m_lo);
@@ -313,7 +313,7 @@ static cudaError_t fused_inv_launch(s2kit_cuda_plan* p, const double* table, uin
                                     const double* ico, long coef_stride, double* G, int nfun, int m_lo, int m_hi,
                                     int real_fmt) {
     size_t smem = fused_smem<N, NC>();
-    cudaError_t e = cudaFuncSetAttribute(k_fused_inv<N, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = ensure_smem(reinterpret_cast<const void*>(k_fused_inv<N, NC>), smem);
     if (e != cudaSuccess) return e;
     int NF = NC / (real_fmt ? 2 : 4);
     dim3 grid((nfun + NF - 1) / NF, m_hi - m_lo);

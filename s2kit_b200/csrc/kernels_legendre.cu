@@ -196,7 +196,7 @@ static cudaError_t leg_fwd_nc(s2kit_cuda_plan* p, const double* table, uint64_t 
     int NF = NC / cols_per_fn;
     size_t smem = sizeof(double) * 2 * NC * panel_stride(p->bw) + sizeof(uint32_t) * (p->bw / 8 + 8);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_legendre_fwd<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = ensure_smem(reinterpret_cast<const void*>(k_legendre_fwd<NC>), smem);
         if (e != cudaSuccess) return e;
     }
     dim3 grid((nfun + NF - 1) / NF, m_hi - m_lo, rowsplit);
@@ -214,7 +214,7 @@ static cudaError_t leg_inv_nc(s2kit_cuda_plan* p, const double* table, uint64_t 
     int NF = NC / cols_per_fn;
     size_t smem = sizeof(double) * 2 * NC * panel_stride(p->bw) + sizeof(uint32_t) * (p->bw / 8 + 8);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_legendre_inv<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = ensure_smem(reinterpret_cast<const void*>(k_legendre_inv<NC>), smem);
         if (e != cudaSuccess) return e;
     }
     dim3 grid((nfun + NF - 1) / NF, m_hi - m_lo, rowsplit);

@@ -204,7 +204,7 @@ static cudaError_t table_gen_nb(s2kit_cuda_plan* p, double* table, uint64_t shif
     size_t smem = sizeof(double) * 2 * G * fft_padded_len(NB);
     if (smem > 48 * 1024) {
         cudaError_t e =
-            cudaFuncSetAttribute(k_table_gen<NB, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            ensure_smem(reinterpret_cast<const void*>(k_table_gen<NB, G>), smem);
         if (e != cudaSuccess) return e;
     }
     int nunits = unit_hi - unit_lo;

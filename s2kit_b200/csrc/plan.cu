@@ -39,7 +39,24 @@ extern "C" const char* s2kit_cuda_last_error(void) { return g_last_error.c_str()
 extern "C" const char* s2kit_cuda_version(void) { return "s2kit_b200 0.1 (sm_100a, FP64 DMMA)"; }
 
 // ------------------------------------------------------------------------------------------------ profiling
+#include <map>
+#include <mutex>
 namespace s2k {
+cudaError_t ensure_smem(const void* kernel, size_t bytes) {
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> done;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_pair(kernel, dev);
+    auto it = done.find(key);
+    if (it != done.end() && it->second >= bytes) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) done[key] = bytes;
+    return e;
+}
+
 int prof_begin(s2kit_cuda_plan* p, int kind) {
     if (!p->profiling) return -1;
     if (p->prof_used == p->prof_slots.size()) {

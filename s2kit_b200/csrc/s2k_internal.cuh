@@ -92,6 +92,10 @@ struct s2kit_cuda_plan {
 
 namespace s2k {
 
+// Opt a kernel into > 48 KB of dynamic shared memory, once per (kernel, device): cudaFuncSetAttribute on every launch
+// costs tens of microseconds of host time and made the launch path CPU-bound.
+cudaError_t ensure_smem(const void* kernel, size_t bytes);
+
 // RAII-less profiling bracket: begin returns a slot index (or -1)
 int prof_begin(s2kit_cuda_plan* p, int kind);
 void prof_end(s2kit_cuda_plan* p, int slot);
