@@ -109,6 +109,9 @@ int s2kit_cuda_fst_rings(s2kit_cuda_plan* plan, const double* rdata, const doubl
 int s2kit_cuda_fst_orders(s2kit_cuda_plan* plan, const double* recvbuf, double* rcoeffs, double* icoeffs);
 int s2kit_cuda_inv_fst_orders(s2kit_cuda_plan* plan, const double* rcoeffs, const double* icoeffs, double* sendbuf);
 int s2kit_cuda_inv_fst_rings(s2kit_cuda_plan* plan, const double* recvbuf, double* rdata, double* idata);
+/* Host-only (no GPU needed): which orders (ascending; returns their count, -1 if the split is not supported) and
+ * which spectral rows (2bw/nranks entries, -1 = unused slot) rank `rank` of `nranks` owns. */
+int s2kit_cuda_shard_layout(int bw, int nranks, int rank, int* orders_out, int* rows_out);
 /* geometry of the exchange: doubles per (src,dst) block, rings per rank, orders rows per rank */
 int s2kit_cuda_shard_info(const s2kit_cuda_plan* plan, long* block_doubles, int* rings_per_rank, int* rows_per_rank);
 

@@ -69,6 +69,7 @@ def lib():
     L.s2kit_cuda_inv_fst_orders.argtypes = [vp, vp, vp, vp]
     L.s2kit_cuda_inv_fst_rings.argtypes = [vp, vp, vp, vp]
     L.s2kit_cuda_shard_info.argtypes = [vp, ctypes.POINTER(cl), ctypes.POINTER(ci), ctypes.POINTER(ci)]
+    L.s2kit_cuda_shard_layout.argtypes = [ci, ci, ci, ctypes.POINTER(ci), ctypes.POINTER(ci)]
     L.s2kit_cuda_table_export.argtypes = [vp, ci, vp]
     L.s2kit_cuda_table_generate.argtypes = [vp, ci, vp]
     L.s2kit_cuda_profile_enable.argtypes = [vp, ci]
@@ -241,6 +242,80 @@ class Plan:
         rd, idt = np.zeros((batch, self.n, self.n)), np.zeros((batch, self.n, self.n))
         self.inv_fst(rco, ico, rd, idt, data_format)
         return (rd[0], idt[0]) if rco.ndim == 1 else (rd, idt)
+
+
+def shard_layout(bw, nranks, rank):
+    """(orders, rows) owned by `rank` -- host-side arithmetic only, no GPU needed (s2kit_cuda_shard_layout)."""
+    orders = (ctypes.c_int * bw)()
+    rows = (ctypes.c_int * (2 * bw))()
+    cnt = lib().s2kit_cuda_shard_layout(bw, nranks, rank, orders, rows)
+    if cnt < 0:
+        raise S2kitCudaError(f"unsupported split: bw={bw} over {nranks} ranks")
+    return list(orders[:cnt]), list(rows[: 2 * bw // nranks])
+
+
+class ShardedPlan:
+    """One rank's share of a single-field transform split over `nranks` GPUs (s2kit_cuda_plan_create_sharded).
+
+    forward : fst_rings(local rings) -> all_to_all(sendbuf -> recvbuf) -> fst_orders(recvbuf) -> own coefficients
+    inverse : inv_fst_orders(coefficients) -> all_to_all -> inv_fst_rings(recvbuf) -> local rings
+    All arrays are torch.float64 CUDA tensors; the exchange buffers have nranks * block_doubles entries.
+    """
+
+    def __init__(self, bw, rank, nranks, device=0):
+        self.bw, self.n, self.rank, self.nranks = bw, 2 * bw, rank, nranks
+        h = ctypes.c_void_p()
+        _check(lib().s2kit_cuda_plan_create_sharded(ctypes.byref(h), bw, MEMO, device, rank, nranks),
+               "plan_create_sharded")
+        self.h = h
+        blk, nr, rows = ctypes.c_long(), ctypes.c_int(), ctypes.c_int()
+        _check(lib().s2kit_cuda_shard_info(h, ctypes.byref(blk), ctypes.byref(nr), ctypes.byref(rows)), "shard_info")
+        self.block_doubles, self.rings = blk.value, nr.value
+        self.orders, self.rows = shard_layout(bw, nranks, rank)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().s2kit_cuda_plan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr):
+        _check(lib().s2kit_cuda_plan_set_stream(self.h, ctypes.c_void_p(cuda_stream_ptr)), "set_stream")
+
+    def synchronize(self):
+        _check(lib().s2kit_cuda_synchronize(self.h), "synchronize")
+
+    def table_bytes(self):
+        return lib().s2kit_cuda_plan_table_bytes(self.h)
+
+    def fst_rings(self, rdata, idata, sendbuf):
+        _check(lib().s2kit_cuda_fst_rings(self.h, rdata.data_ptr(), idata.data_ptr(), sendbuf.data_ptr()), "fst_rings")
+
+    def fst_orders(self, recvbuf, rcoeffs, icoeffs):
+        _check(lib().s2kit_cuda_fst_orders(self.h, recvbuf.data_ptr(), rcoeffs.data_ptr(), icoeffs.data_ptr()),
+               "fst_orders")
+
+    def inv_fst_orders(self, rcoeffs, icoeffs, sendbuf):
+        _check(lib().s2kit_cuda_inv_fst_orders(self.h, rcoeffs.data_ptr(), icoeffs.data_ptr(), sendbuf.data_ptr()),
+               "inv_fst_orders")
+
+    def inv_fst_rings(self, recvbuf, rdata, idata):
+        _check(lib().s2kit_cuda_inv_fst_rings(self.h, recvbuf.data_ptr(), rdata.data_ptr(), idata.data_ptr()),
+               "inv_fst_rings")
+
+    def owned_coefficient_mask(self):
+        """Boolean mask over the bw*bw coefficient positions this rank produces / consumes."""
+        mask = np.zeros(self.bw * self.bw, dtype=bool)
+        for m in self.orders:
+            for sm in ((m,) if m == 0 else (m, -m)):
+                a = index_of_harmonic_coeff(sm, m, self.bw)
+                mask[a:a + self.bw - m] = True
+        return mask
 
 
 def measure_fp64_peak(device=0):

@@ -22,7 +22,7 @@ template <int N, int LT>
 __global__ void __launch_bounds__(N / 8 * LT) k_phi_fft_fwd(const double* __restrict__ rdata,
                                                             const double* __restrict__ idata, long stride,
                                                             double* __restrict__ S, double scale, int rows_kept,
-                                                            const double2* __restrict__ tw) {
+                                                            const double2* __restrict__ tw, PlaneView pv) {
     constexpr int T8 = N / 8, NT = T8 * LT;
     constexpr int RS = ((fft_padded_len(N) + 15) / 16) * 16 + (16 / LT);  // row stride: conflict-free transposed reads
     extern __shared__ double smem[];
@@ -48,15 +48,16 @@ __global__ void __launch_bounds__(N / 8 * LT) k_phi_fft_fwd(const double* __rest
     }
     __syncthreads();
     double* Sr = S + (long)f * 2 * N * N + j0;
-    double* Si = Sr + (long)N * N;
+    double* Si = Sr + pv.part_stride;
     // lanes run over the LT latitudes first (contiguous in S), then over order rows
     for (int flat = tid; flat < N * LT; flat += NT) {
         int j2 = flat % LT, mp = flat / LT;
         // REAL format never reads rows >= bw; COMPLEX skips only row bw (rows_kept encodes which)
         if (rows_kept == N ? (mp != N / 2) : (mp < rows_kept)) {
             int p = fft_pad(mp);
-            Sr[(long)mp * N + j2] = sre[j2 * RS + p];
-            Si[(long)mp * N + j2] = sim[j2 * RS + p];
+            long at = (pv.rowbase ? pv.rowbase[mp] : (long)mp * N) + j2;
+            Sr[at] = sre[j2 * RS + p];
+            Si[at] = sim[j2 * RS + p];
         }
     }
 }
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(N / 8 * LT) k_phi_fft_fwd(const double* __rest
 template <int N, int LT>
 __global__ void __launch_bounds__(N / 8 * LT) k_phi_fft_inv(const double* __restrict__ G, double* __restrict__ rdata,
                                                             double* __restrict__ idata, long stride, int real_fmt,
-                                                            const double2* __restrict__ tw) {
+                                                            const double2* __restrict__ tw, PlaneView pv) {
     constexpr int T8 = N / 8, NT = T8 * LT;
     constexpr int RS = ((fft_padded_len(N) + 15) / 16) * 16 + (16 / LT);
     extern __shared__ double smem[];
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(N / 8 * LT) k_phi_fft_inv(const double* __rest
     const int tid = threadIdx.x, jj = tid / T8, t = tid % T8;
     const int j0 = blockIdx.x * LT, f = blockIdx.y;
     const double* Gr = G + (long)f * 2 * N * N + j0;
-    const double* Gi = Gr + (long)N * N;
+    const double* Gi = Gr + pv.part_stride;
     // inverse DFT through the forward one: feed (im, re), read back (im, re)   (FST_semi_memo.c:350)
     // N*LT elements per part and NT = N/8*LT threads: exactly 8 per thread, all loads issued before any use
     {
@@ -85,8 +86,9 @@ __global__ void __launch_bounds__(N / 8 * LT) k_phi_fft_inv(const double* __rest
             int j2 = flat % LT, mp = flat / LT;
             int row = (real_fmt && mp > N / 2) ? N - mp : mp;  // conjugate mirror of row n - m' (FST_semi_memo.c:333-341)
             bool dead = (mp == N / 2);
-            vr[it] = dead ? 0.0 : __ldg(Gr + (long)row * N + j2);
-            vi[it] = dead ? 0.0 : __ldg(Gi + (long)row * N + j2);
+            long at = (pv.rowbase ? pv.rowbase[row] : (long)row * N) + j2;
+            vr[it] = dead ? 0.0 : __ldg(Gr + at);
+            vi[it] = dead ? 0.0 : __ldg(Gi + at);
             if (real_fmt && mp > N / 2) vi[it] = -vi[it];
         }
 #pragma unroll
@@ -125,7 +127,7 @@ template <int N, int FPB>
 __global__ void __launch_bounds__(N / 8 * FPB) k_dct_fwd(const double* __restrict__ S, double* __restrict__ X,
                                                          const double* __restrict__ weights, int ridx_lo, int ridx_hi,
                                                          const double2* __restrict__ tw,
-                                                         const double2* __restrict__ qtab) {
+                                                         const double2* __restrict__ qtab, PlaneView pv) {
     constexpr int T8 = N / 8, B = N / 2, NP = fft_padded_len(N);
     extern __shared__ double smem[];
     const int tid = threadIdx.x, g = tid / T8, t = tid % T8;
@@ -133,19 +135,21 @@ __global__ void __launch_bounds__(N / 8 * FPB) k_dct_fwd(const double* __restric
     double* sim = sre + NP;
     const int ridx = ridx_lo + blockIdx.x * FPB + g, f = blockIdx.y;
     const bool live = ridx < ridx_hi;
-    const int mp = ridx_to_row(live ? ridx : ridx_lo, B);
+    const int rsel = live ? ridx : ridx_lo;
+    const int mp = pv.rowlist ? pv.rowlist[rsel] : ridx_to_row(rsel, B);
     const int m = mp < B ? mp : N - mp;
     const double* w = weights + ((m & 1) ? N : 0);
-    const double* Sr = S + ((long)f * 2 * N + mp) * N;
-    const double* Si = Sr + (long)N * N;
+    const double* Sr = S + (long)f * 2 * N * N + (long)(pv.rowlist ? rsel : mp) * pv.lrow_stride;
+    const double* Si = Sr + pv.part_stride;
     double xr[8], xi[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         int p = t + e * T8;
         int j = (p < B) ? 2 * p : 2 * (N - 1 - p) + 1;
         double wj = __ldg(w + j);
-        xr[e] = __ldg(Sr + j) * wj;
-        xi[e] = __ldg(Si + j) * wj;
+        long at = (long)(j >> pv.seg_shift) * pv.seg_stride + (j & pv.seg_mask);
+        xr[e] = __ldg(Sr + at) * wj;
+        xi[e] = __ldg(Si + at) * wj;
     }
     fft_block<N>(xr, xi, sre, sim, t, tw);
     __syncthreads();
@@ -182,7 +186,7 @@ template <int N, int FPB>
 __global__ void __launch_bounds__(N / 8 * FPB) k_dct_inv(const double* __restrict__ V, double* __restrict__ G,
                                                          const double* __restrict__ sinv, int ridx_lo, int ridx_hi,
                                                          double out_scale, const double2* __restrict__ tw,
-                                                         const double2* __restrict__ qtab) {
+                                                         const double2* __restrict__ qtab, PlaneView pv) {
     constexpr int T8 = N / 8, B = N / 2, NP = fft_padded_len(N);
     extern __shared__ double smem[];
     const int tid = threadIdx.x, g = tid / T8, t = tid % T8;
@@ -190,7 +194,8 @@ __global__ void __launch_bounds__(N / 8 * FPB) k_dct_inv(const double* __restric
     double* sim = sre + NP;
     const int ridx = ridx_lo + blockIdx.x * FPB + g, f = blockIdx.y;
     const bool live = ridx < ridx_hi;
-    const int mp = ridx_to_row(live ? ridx : ridx_lo, B);
+    const int rsel = live ? ridx : ridx_lo;
+    const int mp = pv.rowlist ? pv.rowlist[rsel] : ridx_to_row(rsel, B);
     const int m = mp < B ? mp : N - mp;
     const double* Va = V + (((long)f * N + mp) * 2) * B;
     const double* Vb = Va + B;
@@ -217,15 +222,16 @@ __global__ void __launch_bounds__(N / 8 * FPB) k_dct_inv(const double* __restric
     fft_block<N>(xr, xi, sre, sim, t, tw);
     if (!live) return;
     double sign = ((mp > B) && (m & 1)) ? -out_scale : out_scale;  // (-1)^m for negative orders
-    double* Gr = G + ((long)f * 2 * N + mp) * N;
-    double* Gi = Gr + (long)N * N;
+    double* Gr = G + (long)f * 2 * N * N + (long)(pv.rowlist ? rsel : mp) * pv.lrow_stride;
+    double* Gi = Gr + pv.part_stride;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         int i = fft_out_index<N>(e, t);
         int j = (i < B) ? 2 * i : 2 * (N - 1 - i) + 1;
         double s = (m & 1) ? __ldg(sinv + j) * sign : sign;
-        Gr[j] = xi[e] * s;  // Re z -> column a (real part)
-        Gi[j] = xr[e] * s;  // Im z -> column b (imaginary part)
+        long at = (long)(j >> pv.seg_shift) * pv.seg_stride + (j & pv.seg_mask);
+        Gr[at] = xi[e] * s;  // Re z -> column a (real part)
+        Gi[at] = xr[e] * s;  // Im z -> column b (imaginary part)
     }
 }
 
@@ -319,45 +325,49 @@ static cudaError_t set_smem(K kernel, size_t bytes) {
 
 template <int N>
 static cudaError_t phi_fwd_n(s2kit_cuda_plan* p, const double* rdata, const double* idata, long stride, double* S,
-                             int nfun, int rows_kept) {
+                             int nfun, int rows_kept, const PlaneView& pv, int nrings) {
     constexpr int LT = (4096 / N) < 8 ? (4096 / N) : 8;
     constexpr int RS = ((fft_padded_len(N) + 15) / 16) * 16 + (16 / LT);
     size_t smem = sizeof(double) * 2 * LT * RS;
     cudaError_t e = set_smem(k_phi_fft_fwd<N, LT>, smem);
     if (e != cudaSuccess) return e;
     double scale = sqrt(2.0 * M_PI) / (double)N;  // FST_semi_memo.c:86
-    k_phi_fft_fwd<N, LT><<<dim3(N / LT, nfun), N / 8 * LT, smem, p->stream>>>(rdata, idata, stride, S, scale,
-                                                                              rows_kept, p->d_tw_n);
+    if (nrings % LT) return cudaErrorInvalidValue;
+    k_phi_fft_fwd<N, LT><<<dim3(nrings / LT, nfun), N / 8 * LT, smem, p->stream>>>(rdata, idata, stride, S, scale,
+                                                                                   rows_kept, p->d_tw_n, pv);
     return cudaGetLastError();
 }
 
 template <int N>
 static cudaError_t phi_inv_n(s2kit_cuda_plan* p, const double* G, double* rdata, double* idata, long stride, int nfun,
-                             int real_fmt) {
+                             int real_fmt, const PlaneView& pv, int nrings) {
     constexpr int LT = (4096 / N) < 8 ? (4096 / N) : 8;
     constexpr int RS = ((fft_padded_len(N) + 15) / 16) * 16 + (16 / LT);
     size_t smem = sizeof(double) * 2 * LT * RS;
     cudaError_t e = set_smem(k_phi_fft_inv<N, LT>, smem);
     if (e != cudaSuccess) return e;
-    k_phi_fft_inv<N, LT><<<dim3(N / LT, nfun), N / 8 * LT, smem, p->stream>>>(G, rdata, idata, stride, real_fmt,
-                                                                              p->d_tw_n);
+    if (nrings % LT) return cudaErrorInvalidValue;
+    k_phi_fft_inv<N, LT><<<dim3(nrings / LT, nfun), N / 8 * LT, smem, p->stream>>>(G, rdata, idata, stride, real_fmt,
+                                                                                   p->d_tw_n, pv);
     return cudaGetLastError();
 }
 
 template <int N>
-static cudaError_t dct_fwd_n(s2kit_cuda_plan* p, const double* S, double* X, int nfun, int lo, int hi) {
+static cudaError_t dct_fwd_n(s2kit_cuda_plan* p, const double* S, double* X, int nfun, int lo, int hi,
+                             const PlaneView& pv) {
     constexpr int T8 = N / 8;
     constexpr int FPB = (256 / T8) < 1 ? 1 : ((256 / T8) > 8 ? 8 : (256 / T8));
     size_t smem = sizeof(double) * 2 * FPB * fft_padded_len(N);
     cudaError_t e = set_smem(k_dct_fwd<N, FPB>, smem);
     if (e != cudaSuccess) return e;
     k_dct_fwd<N, FPB><<<dim3((hi - lo + FPB - 1) / FPB, nfun), T8 * FPB, smem, p->stream>>>(
-        S, X, p->d_weights, lo, hi, p->d_tw_n, p->d_q_n);
+        S, X, p->d_weights, lo, hi, p->d_tw_n, p->d_q_n, pv);
     return cudaGetLastError();
 }
 
 template <int N>
-static cudaError_t dct_inv_n(s2kit_cuda_plan* p, const double* V, double* G, int nfun, int lo, int hi) {
+static cudaError_t dct_inv_n(s2kit_cuda_plan* p, const double* V, double* G, int nfun, int lo, int hi,
+                             const PlaneView& pv) {
     constexpr int T8 = N / 8;
     constexpr int FPB = (256 / T8) < 1 ? 1 : ((256 / T8) > 8 ? 8 : (256 / T8));
     size_t smem = sizeof(double) * 2 * FPB * fft_padded_len(N);
@@ -365,7 +375,7 @@ static cudaError_t dct_inv_n(s2kit_cuda_plan* p, const double* V, double* G, int
     if (e != cudaSuccess) return e;
     double out_scale = 1.0 / sqrt(2.0 * M_PI);  // FST_semi_memo.c:344
     k_dct_inv<N, FPB><<<dim3((hi - lo + FPB - 1) / FPB, nfun), T8 * FPB, smem, p->stream>>>(
-        V, G, p->d_sin, lo, hi, out_scale, p->d_tw_n, p->d_q_n);
+        V, G, p->d_sin, lo, hi, out_scale, p->d_tw_n, p->d_q_n, pv);
     return cudaGetLastError();
 }
 
@@ -382,14 +392,28 @@ static cudaError_t dct_inv_n(s2kit_cuda_plan* p, const double* V, double* G, int
         default: return cudaErrorInvalidValue;   \
     }
 
+static PlaneView default_view(int n) {
+    PlaneView v;
+    v.rowbase = nullptr;
+    v.rowlist = nullptr;
+    v.part_stride = (long)n * n;
+    v.lrow_stride = n;
+    v.seg_stride = 0;
+    v.seg_shift = 30;  // j >> 30 == 0: a row is one segment
+    v.seg_mask = 0x3fffffff;
+    v.nrings = n;
+    return v;
+}
+
 cudaError_t launch_phi_fft_fwd(s2kit_cuda_plan* p, const double* rdata, const double* idata, long stride, double* S,
-                               int nfun, int data_format) {
+                               int nfun, int data_format, const PlaneView* view) {
     int n = p->n;
+    const PlaneView pv = view ? *view : default_view(n);
     int slot = prof_begin(p, S2KIT_K_PHI_FFT_FWD);
     cudaError_t e;
     if (p->fast) {
         int rows_kept = (data_format == S2KIT_REAL) ? p->bw : n;
-#define CALL(NN) phi_fwd_n<NN>(p, rdata, idata, stride, S, nfun, rows_kept)
+#define CALL(NN) phi_fwd_n<NN>(p, rdata, idata, stride, S, nfun, rows_kept, pv, pv.nrings)
         e = [&]() -> cudaError_t { S2K_DISPATCH_N(n, CALL) }();
 #undef CALL
     } else {
@@ -403,13 +427,14 @@ cudaError_t launch_phi_fft_fwd(s2kit_cuda_plan* p, const double* rdata, const do
 }
 
 cudaError_t launch_phi_fft_inv(s2kit_cuda_plan* p, const double* G, double* rdata, double* idata, long stride, int nfun,
-                               int data_format) {
+                               int data_format, const PlaneView* view) {
     int n = p->n;
+    const PlaneView pv = view ? *view : default_view(n);
     int real_fmt = data_format == S2KIT_REAL;
     int slot = prof_begin(p, S2KIT_K_PHI_FFT_INV);
     cudaError_t e;
     if (p->fast) {
-#define CALL(NN) phi_inv_n<NN>(p, G, rdata, idata, stride, nfun, real_fmt)
+#define CALL(NN) phi_inv_n<NN>(p, G, rdata, idata, stride, nfun, real_fmt, pv, pv.nrings)
         e = [&]() -> cudaError_t { S2K_DISPATCH_N(n, CALL) }();
 #undef CALL
     } else {
@@ -423,13 +448,14 @@ cudaError_t launch_phi_fft_inv(s2kit_cuda_plan* p, const double* G, double* rdat
 
 // rows are addressed by ridx in [0, 2bw-1): ridx < bw -> order row ridx, else row ridx + 1 (row bw unused)
 cudaError_t launch_dct_fwd(s2kit_cuda_plan* p, const double* S, double* X, int nfun, int row_lo, int row_hi,
-                           int data_format) {
+                           int data_format, const PlaneView* view) {
     (void)data_format;
+    const PlaneView pv = view ? *view : default_view(p->n);
     if (row_hi <= row_lo) return cudaSuccess;
     int slot = prof_begin(p, S2KIT_K_DCT_FWD);
     cudaError_t e;
     if (p->fast) {
-#define CALL(NN) dct_fwd_n<NN>(p, S, X, nfun, row_lo, row_hi)
+#define CALL(NN) dct_fwd_n<NN>(p, S, X, nfun, row_lo, row_hi, pv)
         e = [&]() -> cudaError_t { S2K_DISPATCH_N(p->n, CALL) }();
 #undef CALL
     } else {
@@ -443,13 +469,14 @@ cudaError_t launch_dct_fwd(s2kit_cuda_plan* p, const double* S, double* X, int n
 }
 
 cudaError_t launch_dct_inv(s2kit_cuda_plan* p, const double* V, double* G, int nfun, int row_lo, int row_hi,
-                           int data_format) {
+                           int data_format, const PlaneView* view) {
     (void)data_format;
+    const PlaneView pv = view ? *view : default_view(p->n);
     if (row_hi <= row_lo) return cudaSuccess;
     int slot = prof_begin(p, S2KIT_K_DCT_INV);
     cudaError_t e;
     if (p->fast) {
-#define CALL(NN) dct_inv_n<NN>(p, V, G, nfun, row_lo, row_hi)
+#define CALL(NN) dct_inv_n<NN>(p, V, G, nfun, row_lo, row_hi, pv)
         e = [&]() -> cudaError_t { S2K_DISPATCH_N(p->n, CALL) }();
 #undef CALL
     } else {

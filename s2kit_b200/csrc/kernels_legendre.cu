@@ -22,10 +22,11 @@ template <int NC>
 __global__ void __launch_bounds__(LEG_WARPS * 32) k_legendre_fwd(
     const double* __restrict__ table, const uint64_t* __restrict__ order_start, uint64_t table_shift,
     const BlockMeta* __restrict__ meta, const uint32_t* __restrict__ rt_start, const double* __restrict__ X,
-    double* __restrict__ rco, double* __restrict__ ico, long coef_stride, int bw, int nfun, int m_lo, int real_fmt) {
+    double* __restrict__ rco, double* __restrict__ ico, long coef_stride, int bw, int nfun, int m_lo, int real_fmt,
+    const int* __restrict__ order_list) {
     extern __shared__ double smem[];
     const int n = 2 * bw, CS = panel_stride(bw);
-    const int m = m_lo + blockIdx.y;
+    const int m = order_list ? order_list[blockIdx.y] : m_lo + blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cols_per_fn = real_fmt ? 2 : 4;
     const int NF = NC / cols_per_fn;
@@ -120,10 +121,10 @@ __global__ void __launch_bounds__(LEG_WARPS * 32) k_legendre_inv(
     const double* __restrict__ table, const uint64_t* __restrict__ order_start, uint64_t table_shift,
     const BlockMeta* __restrict__ meta, const uint32_t* __restrict__ rt_start, const double* __restrict__ rco,
     const double* __restrict__ ico, long coef_stride, double* __restrict__ V, int bw, int nfun, int m_lo,
-    int real_fmt) {
+    int real_fmt, const int* __restrict__ order_list) {
     extern __shared__ double smem[];
     const int n = 2 * bw, CS = panel_stride(bw);
-    const int m = m_lo + blockIdx.y;
+    const int m = order_list ? order_list[blockIdx.y] : m_lo + blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cols_per_fn = real_fmt ? 2 : 4;
     const int NF = NC / cols_per_fn;
@@ -191,7 +192,8 @@ __global__ void __launch_bounds__(LEG_WARPS * 32) k_legendre_inv(
 // ------------------------------------------------------------------------------------------------ launchers
 template <int NC>
 static cudaError_t leg_fwd_nc(s2kit_cuda_plan* p, const double* table, uint64_t shift, const double* X, double* rco,
-                              double* ico, long coef_stride, int nfun, int m_lo, int m_hi, int real_fmt, int rowsplit) {
+                              double* ico, long coef_stride, int nfun, int m_lo, int m_hi, int real_fmt, int rowsplit,
+                              const int* order_list) {
     int cols_per_fn = real_fmt ? 2 : 4;
     int NF = NC / cols_per_fn;
     size_t smem = sizeof(double) * 2 * NC * panel_stride(p->bw) + sizeof(uint32_t) * (p->bw / 8 + 8);
@@ -202,14 +204,14 @@ static cudaError_t leg_fwd_nc(s2kit_cuda_plan* p, const double* table, uint64_t 
     dim3 grid((nfun + NF - 1) / NF, m_hi - m_lo, rowsplit);
     k_legendre_fwd<NC><<<grid, LEG_WARPS * 32, smem, p->stream>>>(table, p->d_order_start, shift, p->d_meta,
                                                                   p->d_rt_start, X, rco, ico, coef_stride, p->bw, nfun,
-                                                                  m_lo, real_fmt);
+                                                                  m_lo, real_fmt, order_list);
     return cudaGetLastError();
 }
 
 template <int NC>
 static cudaError_t leg_inv_nc(s2kit_cuda_plan* p, const double* table, uint64_t shift, const double* rco,
                               const double* ico, long coef_stride, double* V, int nfun, int m_lo, int m_hi,
-                              int real_fmt, int rowsplit) {
+                              int real_fmt, int rowsplit, const int* order_list) {
     int cols_per_fn = real_fmt ? 2 : 4;
     int NF = NC / cols_per_fn;
     size_t smem = sizeof(double) * 2 * NC * panel_stride(p->bw) + sizeof(uint32_t) * (p->bw / 8 + 8);
@@ -220,7 +222,7 @@ static cudaError_t leg_inv_nc(s2kit_cuda_plan* p, const double* table, uint64_t 
     dim3 grid((nfun + NF - 1) / NF, m_hi - m_lo, rowsplit);
     k_legendre_inv<NC><<<grid, LEG_WARPS * 32, smem, p->stream>>>(table, p->d_order_start, shift, p->d_meta,
                                                                   p->d_rt_start, rco, ico, coef_stride, V, p->bw, nfun,
-                                                                  m_lo, real_fmt);
+                                                                  m_lo, real_fmt, order_list);
     return cudaGetLastError();
 }
 
@@ -247,7 +249,8 @@ static int pick_rowsplit(int bw, int ncoltiles, int norders) {
 }
 
 cudaError_t launch_legendre_fwd(s2kit_cuda_plan* p, const double* table, uint64_t shift, const double* X, double* rco,
-                                double* ico, long coef_stride, int nfun, int m_lo, int m_hi, int data_format) {
+                                double* ico, long coef_stride, int nfun, int m_lo, int m_hi, int data_format,
+                                const int* order_list) {
     if (m_hi <= m_lo || nfun <= 0) return cudaSuccess;
     int real_fmt = data_format == S2KIT_REAL;
     int nc = pick_nc(p->bw, nfun, real_fmt);
@@ -256,9 +259,9 @@ cudaError_t launch_legendre_fwd(s2kit_cuda_plan* p, const double* table, uint64_
     int slot = prof_begin(p, S2KIT_K_LEGENDRE_FWD);
     cudaError_t e;
     switch (nc) {
-        case 8: e = leg_fwd_nc<8>(p, table, shift, X, rco, ico, coef_stride, nfun, m_lo, m_hi, real_fmt, rs); break;
-        case 16: e = leg_fwd_nc<16>(p, table, shift, X, rco, ico, coef_stride, nfun, m_lo, m_hi, real_fmt, rs); break;
-        default: e = leg_fwd_nc<32>(p, table, shift, X, rco, ico, coef_stride, nfun, m_lo, m_hi, real_fmt, rs); break;
+        case 8: e = leg_fwd_nc<8>(p, table, shift, X, rco, ico, coef_stride, nfun, m_lo, m_hi, real_fmt, rs, order_list); break;
+        case 16: e = leg_fwd_nc<16>(p, table, shift, X, rco, ico, coef_stride, nfun, m_lo, m_hi, real_fmt, rs, order_list); break;
+        default: e = leg_fwd_nc<32>(p, table, shift, X, rco, ico, coef_stride, nfun, m_lo, m_hi, real_fmt, rs, order_list); break;
     }
     prof_end(p, slot);
     return e;
@@ -266,7 +269,7 @@ cudaError_t launch_legendre_fwd(s2kit_cuda_plan* p, const double* table, uint64_
 
 cudaError_t launch_legendre_inv(s2kit_cuda_plan* p, const double* table, uint64_t shift, const double* rco,
                                 const double* ico, long coef_stride, double* V, int nfun, int m_lo, int m_hi,
-                                int data_format) {
+                                int data_format, const int* order_list) {
     if (m_hi <= m_lo || nfun <= 0) return cudaSuccess;
     int real_fmt = data_format == S2KIT_REAL;
     int nc = pick_nc(p->bw, nfun, real_fmt);
@@ -275,9 +278,9 @@ cudaError_t launch_legendre_inv(s2kit_cuda_plan* p, const double* table, uint64_
     int slot = prof_begin(p, S2KIT_K_LEGENDRE_INV);
     cudaError_t e;
     switch (nc) {
-        case 8: e = leg_inv_nc<8>(p, table, shift, rco, ico, coef_stride, V, nfun, m_lo, m_hi, real_fmt, rs); break;
-        case 16: e = leg_inv_nc<16>(p, table, shift, rco, ico, coef_stride, V, nfun, m_lo, m_hi, real_fmt, rs); break;
-        default: e = leg_inv_nc<32>(p, table, shift, rco, ico, coef_stride, V, nfun, m_lo, m_hi, real_fmt, rs); break;
+        case 8: e = leg_inv_nc<8>(p, table, shift, rco, ico, coef_stride, V, nfun, m_lo, m_hi, real_fmt, rs, order_list); break;
+        case 16: e = leg_inv_nc<16>(p, table, shift, rco, ico, coef_stride, V, nfun, m_lo, m_hi, real_fmt, rs, order_list); break;
+        default: e = leg_inv_nc<32>(p, table, shift, rco, ico, coef_stride, V, nfun, m_lo, m_hi, real_fmt, rs, order_list); break;
     }
     prof_end(p, slot);
     return e;

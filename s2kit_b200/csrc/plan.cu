@@ -187,8 +187,12 @@ static cudaError_t upload(T** dptr, const void* host, size_t count) {
 
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
-static int plan_create_impl(s2kit_cuda_plan** out, int bw, int variant, int max_batch, int device, int rank,
-                            int nranks) {
+void s2k_shard_destroy(s2kit_cuda_plan* p);
+int s2k_fail_msg(const char* what) { return fail_msg(what); }
+int s2k_fail_cuda(const char* what, cudaError_t e) { return fail(what, e); }
+
+int s2k_plan_create_impl(s2kit_cuda_plan** out, int bw, int variant, int max_batch, int device, int rank,
+                         int nranks) {
     if (!out) return fail_msg("null output pointer");
     *out = nullptr;
     if (bw < 2 || bw > 2048) return fail_msg("bandwidth must be in [2, 2048]");
@@ -310,17 +314,18 @@ static int plan_create_impl(s2kit_cuda_plan** out, int bw, int variant, int max_
 }
 
 extern "C" int s2kit_cuda_plan_create(s2kit_cuda_plan** out, int bw, int variant, int max_batch, int device) {
-    return plan_create_impl(out, bw, variant, max_batch, device, 0, 1);
+    return s2k_plan_create_impl(out, bw, variant, max_batch, device, 0, 1);
 }
 
 extern "C" int s2kit_cuda_plan_destroy(s2kit_cuda_plan* p) {
     if (!p) return 0;
     cudaSetDevice(p->device);
     cudaStreamSynchronize(p->stream);
+    s2k_shard_destroy(p);
     void* ptrs[] = {p->d_weights, p->d_sin,      p->d_tw_n,       p->d_tw_b, p->d_q_n,  p->d_q_b,
                     p->d_nodes,   p->d_seeds,    p->d_rec,        p->d_table, p->d_meta, p->d_rt_start,
                     p->d_order_start, p->d_units, p->d_S,          p->d_X,    p->d_coef, p->d_coef2,
-                    p->d_filt,    p->d_stage_grid, p->d_stage_coef};
+                    p->d_filt,    p->d_stage};
     for (void* q : ptrs)
         if (q) cudaFree(q);
     for (auto& s : p->prof_slots) {
@@ -504,26 +509,94 @@ static int check_common(s2kit_cuda_plan* p, int batch, int fmt) {
     return 0;
 }
 
+// Host-pointer calls: a three-stage pipeline over sub-chunks of the batch -- H2D of sub-chunk i+1, the kernels of
+// sub-chunk i and D2H of sub-chunk i-1 run concurrently on three streams with double-buffered device staging, so
+// PCIe runs full duplex and the GPU work hides behind the copies.  (Pinned host memory is needed for true overlap;
+// pageable memory still works, the copies just serialise.)
+struct HostPipe {
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t in_done[2] = {nullptr, nullptr}, comp_done[2] = {nullptr, nullptr}, out_done[2] = {nullptr, nullptr};
+    bool ok = false;
+    HostPipe() {
+        ok = cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking) == cudaSuccess;
+        for (int b = 0; b < 2 && ok; ++b)
+            ok = cudaEventCreateWithFlags(&in_done[b], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&comp_done[b], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&out_done[b], cudaEventDisableTiming) == cudaSuccess;
+    }
+    ~HostPipe() {
+        for (int b = 0; b < 2; ++b) {
+            if (in_done[b]) cudaEventDestroy(in_done[b]);
+            if (comp_done[b]) cudaEventDestroy(comp_done[b]);
+            if (out_done[b]) cudaEventDestroy(out_done[b]);
+        }
+        if (s_in) cudaStreamDestroy(s_in);
+        if (s_out) cudaStreamDestroy(s_out);
+    }
+};
+
+// in0/in1: host inputs (in_len doubles per function, stride in_stride); out0/out1 likewise.
+// compute(nf, din0, din1, dout0, dout1) enqueues the kernels for nf functions on p->stream (device strides = lens).
+template <typename F>
+static int host_pipeline(s2kit_cuda_plan* p, int batch, const double* in0, const double* in1, long in_stride,
+                         long in_len, double* out0, double* out1, long out_stride, long out_len, F compute) {
+    const int sub = std::max(1, std::min(p->chunk, 32));
+    const size_t need = (size_t)2 * sub * 2 * (size_t)(in_len + out_len);
+    if (p->stage_doubles < need) {
+        if (p->d_stage) cudaFree(p->d_stage);
+        p->d_stage = nullptr;
+        p->stage_doubles = 0;
+        CK(cudaMalloc((void**)&p->d_stage, need * sizeof(double)));
+        p->stage_doubles = need;
+    }
+    HostPipe hp;
+    if (!hp.ok) return fail_msg("could not create the copy streams");
+    double* din[2][2];
+    double* dout[2][2];
+    {
+        double* q = p->d_stage;
+        for (int b = 0; b < 2; ++b) {
+            din[b][0] = q; q += (size_t)sub * in_len;
+            din[b][1] = q; q += (size_t)sub * in_len;
+            dout[b][0] = q; q += (size_t)sub * out_len;
+            dout[b][1] = q; q += (size_t)sub * out_len;
+        }
+    }
+    int i = 0;
+    for (int c0 = 0; c0 < batch; c0 += sub, ++i) {
+        const int b = i & 1, nf = std::min(sub, batch - c0);
+        // H2D: the input buffers of slot b are free once the kernels of sub-chunk i-2 are done
+        if (i >= 2) CK(cudaStreamWaitEvent(hp.s_in, hp.comp_done[b], 0));
+        CK(copy_in(din[b][0], in_len, in0 + (long)c0 * in_stride, in_stride, in_len, nf, hp.s_in));
+        CK(copy_in(din[b][1], in_len, in1 + (long)c0 * in_stride, in_stride, in_len, nf, hp.s_in));
+        CK(cudaEventRecord(hp.in_done[b], hp.s_in));
+        // kernels: need the inputs, and the output buffers of slot b drained (sub-chunk i-2)
+        CK(cudaStreamWaitEvent(p->stream, hp.in_done[b], 0));
+        if (i >= 2) CK(cudaStreamWaitEvent(p->stream, hp.out_done[b], 0));
+        if (int rc = compute(nf, din[b][0], din[b][1], dout[b][0], dout[b][1])) return rc;
+        CK(cudaEventRecord(hp.comp_done[b], p->stream));
+        // D2H
+        CK(cudaStreamWaitEvent(hp.s_out, hp.comp_done[b], 0));
+        CK(copy_out(out0 + (long)c0 * out_stride, out_stride, dout[b][0], out_len, out_len, nf, hp.s_out));
+        CK(copy_out(out1 + (long)c0 * out_stride, out_stride, dout[b][1], out_len, out_len, nf, hp.s_out));
+        CK(cudaEventRecord(hp.out_done[b], hp.s_out));
+    }
+    CK(cudaStreamSynchronize(hp.s_out));
+    CK(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
 extern "C" int s2kit_cuda_fst(s2kit_cuda_plan* p, const double* rdata, const double* idata, double* rco, double* ico,
                               int batch, long data_stride, long coef_stride, int fmt, int where) {
     if (int r = check_common(p, batch, fmt)) return r;
     if (batch == 0) return 0;
     if (where == S2KIT_CUDA_DEVICE) return fst_device(p, rdata, idata, rco, ico, batch, data_stride, coef_stride, fmt);
     const long gs = (long)p->n * p->n, cs = (long)p->bw * p->bw;
-    if (ensure(&p->d_stage_grid, (size_t)p->chunk * 2 * gs)) return 1;
-    if (ensure(&p->d_stage_coef, (size_t)p->chunk * 2 * cs)) return 1;
-    double *gr = p->d_stage_grid, *gi = gr + (size_t)p->chunk * gs;
-    double *cr = p->d_stage_coef, *ci = cr + (size_t)p->chunk * cs;
-    for (int c0 = 0; c0 < batch; c0 += p->chunk) {
-        int nf = std::min(p->chunk, batch - c0);
-        CK(copy_in(gr, gs, rdata + (long)c0 * data_stride, data_stride, gs, nf, p->stream));
-        CK(copy_in(gi, gs, idata + (long)c0 * data_stride, data_stride, gs, nf, p->stream));
-        if (fst_device(p, gr, gi, cr, ci, nf, gs, cs, fmt)) return 1;
-        CK(copy_out(rco + (long)c0 * coef_stride, coef_stride, cr, cs, cs, nf, p->stream));
-        CK(copy_out(ico + (long)c0 * coef_stride, coef_stride, ci, cs, cs, nf, p->stream));
-        CK(cudaStreamSynchronize(p->stream));
-    }
-    return 0;
+    return host_pipeline(p, batch, rdata, idata, data_stride, gs, rco, ico, coef_stride, cs,
+                         [&](int nf, double* gr, double* gi, double* cr, double* ci) {
+                             return fst_device(p, gr, gi, cr, ci, nf, gs, cs, fmt);
+                         });
 }
 
 extern "C" int s2kit_cuda_inv_fst(s2kit_cuda_plan* p, const double* rco, const double* ico, double* rdata,
@@ -533,20 +606,10 @@ extern "C" int s2kit_cuda_inv_fst(s2kit_cuda_plan* p, const double* rco, const d
     if (where == S2KIT_CUDA_DEVICE)
         return inv_fst_device(p, rco, ico, rdata, idata, batch, coef_stride, data_stride, fmt);
     const long gs = (long)p->n * p->n, cs = (long)p->bw * p->bw;
-    if (ensure(&p->d_stage_grid, (size_t)p->chunk * 2 * gs)) return 1;
-    if (ensure(&p->d_stage_coef, (size_t)p->chunk * 2 * cs)) return 1;
-    double *gr = p->d_stage_grid, *gi = gr + (size_t)p->chunk * gs;
-    double *cr = p->d_stage_coef, *ci = cr + (size_t)p->chunk * cs;
-    for (int c0 = 0; c0 < batch; c0 += p->chunk) {
-        int nf = std::min(p->chunk, batch - c0);
-        CK(copy_in(cr, cs, rco + (long)c0 * coef_stride, coef_stride, cs, nf, p->stream));
-        CK(copy_in(ci, cs, ico + (long)c0 * coef_stride, coef_stride, cs, nf, p->stream));
-        if (inv_fst_device(p, cr, ci, gr, gi, nf, cs, gs, fmt)) return 1;
-        CK(copy_out(rdata + (long)c0 * data_stride, data_stride, gr, gs, gs, nf, p->stream));
-        CK(copy_out(idata + (long)c0 * data_stride, data_stride, gi, gs, gs, nf, p->stream));
-        CK(cudaStreamSynchronize(p->stream));
-    }
-    return 0;
+    return host_pipeline(p, batch, rco, ico, coef_stride, cs, rdata, idata, data_stride, gs,
+                         [&](int nf, double* cr, double* ci, double* gr, double* gi) {
+                             return inv_fst_device(p, cr, ci, gr, gi, nf, cs, gs, fmt);
+                         });
 }
 
 extern "C" int s2kit_cuda_fzt(s2kit_cuda_plan* p, const double* rdata, const double* idata, double* rres, double* ires,
@@ -556,20 +619,10 @@ extern "C" int s2kit_cuda_fzt(s2kit_cuda_plan* p, const double* rdata, const dou
     if (where == S2KIT_CUDA_DEVICE) return fzt_device(p, rdata, idata, rres, ires, batch, data_stride, res_stride, fmt);
     const long gs = (long)p->n * p->n;
     const int bw = p->bw;
-    if (ensure(&p->d_stage_grid, (size_t)p->chunk * 2 * gs)) return 1;
-    if (ensure(&p->d_filt, (size_t)p->chunk * 2 * bw)) return 1;
-    double *gr = p->d_stage_grid, *gi = gr + (size_t)p->chunk * gs;
-    double *hr = p->d_filt, *hi = hr + (size_t)p->chunk * bw;
-    for (int c0 = 0; c0 < batch; c0 += p->chunk) {
-        int nf = std::min(p->chunk, batch - c0);
-        CK(copy_in(gr, gs, rdata + (long)c0 * data_stride, data_stride, gs, nf, p->stream));
-        CK(copy_in(gi, gs, idata + (long)c0 * data_stride, data_stride, gs, nf, p->stream));
-        if (fzt_device(p, gr, gi, hr, hi, nf, gs, bw, fmt)) return 1;
-        CK(copy_out(rres + (long)c0 * res_stride, res_stride, hr, bw, bw, nf, p->stream));
-        CK(copy_out(ires + (long)c0 * res_stride, res_stride, hi, bw, bw, nf, p->stream));
-        CK(cudaStreamSynchronize(p->stream));
-    }
-    return 0;
+    return host_pipeline(p, batch, rdata, idata, data_stride, gs, rres, ires, res_stride, (long)bw,
+                         [&](int nf, double* gr, double* gi, double* hr, double* hi) {
+                             return fzt_device(p, gr, gi, hr, hi, nf, gs, bw, fmt);
+                         });
 }
 
 extern "C" int s2kit_cuda_conv(s2kit_cuda_plan* p, const double* rdata, const double* idata, const double* rfilter,

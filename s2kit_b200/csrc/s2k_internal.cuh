@@ -25,6 +25,19 @@ struct BlockMeta {
 
 __host__ __device__ inline int tile_elem_offset(int i, int j) { return 2 * (4 * i + (j & 3)) + (j >> 2); }
 
+// How a spectral plane is addressed.  The default describes the ordinary [part][order row][latitude] plane; the
+// sharded single-field path points the same kernels at all-to-all send / receive blocks instead
+// ([peer][part][local row][local ring], shard.cu).
+struct PlaneView {
+    const long* rowbase;  // K1/K6: offset (doubles) of order row m' inside the plane; null -> m' * n
+    const int* rowlist;   // K2/K5: local row index -> order row m'; null -> all rows of the plane
+    long part_stride;     // offset of the imaginary plane
+    long lrow_stride;     // K2/K5: doubles between consecutive (local) rows
+    long seg_stride;      // K2/K5: a row of 2bw latitudes is cut into segments of (seg_mask+1) entries, this far apart
+    int seg_shift, seg_mask;
+    int nrings;           // K1/K6: latitude rows handled by this launch
+};
+
 struct ProfileSlot {
     cudaEvent_t a, b;
     int kind;
@@ -43,6 +56,7 @@ struct s2kit_cuda_plan {
     // sharding (single-field multi-GPU); nranks == 1 for ordinary plans
     int rank = 0, nranks = 1;
     std::vector<int> my_orders;  // orders owned by this rank (ascending)
+    void* shard = nullptr;       // ShardState (shard.cu) of a sharded plan
 
     // host-computed constants on the device
     double* d_weights = nullptr;   // 4 bw   (weights.c:32-47)
@@ -77,9 +91,9 @@ struct s2kit_cuda_plan {
     double* d_coef = nullptr;  // [chunk][2][bw*bw]   conv intermediates / staging
     double* d_coef2 = nullptr;
     double* d_filt = nullptr;  // [chunk][2][bw]
-    // staging for host-pointer calls
-    double* d_stage_grid = nullptr;  // [chunk][2][n*n]
-    double* d_stage_coef = nullptr;  // [chunk][2][bw*bw]
+    // double-buffered staging for host-pointer calls (host_pipeline, plan.cu)
+    double* d_stage = nullptr;
+    size_t stage_doubles = 0;
     size_t table_bytes = 0;
 
     // profiling
@@ -103,21 +117,22 @@ void prof_end(s2kit_cuda_plan* p, int slot);
 // ---- launchers (each checks cudaGetLastError and returns it) -----------------------------------------
 // K1 / K6: longitude FFT.  S layout [f][part][order row][latitude]
 cudaError_t launch_phi_fft_fwd(s2kit_cuda_plan* p, const double* rdata, const double* idata, long stride,
-                               double* S, int nfun, int data_format);
+                               double* S, int nfun, int data_format, const PlaneView* view = nullptr);
 cudaError_t launch_phi_fft_inv(s2kit_cuda_plan* p, const double* G, double* rdata, double* idata, long stride,
-                               int nfun, int data_format);
+                               int nfun, int data_format, const PlaneView* view = nullptr);
 // K2 / K5: DCT stages.  X layout [f][order row][part][bw]
 cudaError_t launch_dct_fwd(s2kit_cuda_plan* p, const double* S, double* X, int nfun, int row_lo, int row_hi,
-                           int data_format);
+                           int data_format, const PlaneView* view = nullptr);
 cudaError_t launch_dct_inv(s2kit_cuda_plan* p, const double* V, double* G, int nfun, int row_lo, int row_hi,
-                           int data_format);
+                           int data_format, const PlaneView* view = nullptr);
 // K3 / K4: Legendre contraction for orders [m_lo, m_hi); table_shift = tile offset subtracted from order starts
+// order_list (device, optional): the launch covers orders order_list[0 .. m_hi-m_lo) instead of [m_lo, m_hi)
 cudaError_t launch_legendre_fwd(s2kit_cuda_plan* p, const double* table, uint64_t table_shift, const double* X,
                                 double* rco, double* ico, long coef_stride, int nfun, int m_lo, int m_hi,
-                                int data_format);
+                                int data_format, const int* order_list = nullptr);
 cudaError_t launch_legendre_inv(s2kit_cuda_plan* p, const double* table, uint64_t table_shift, const double* rco,
                                 const double* ico, long coef_stride, double* V, int nfun, int m_lo, int m_hi,
-                                int data_format);
+                                int data_format, const int* order_list = nullptr);
 // K7: table generation for orders [m_lo, m_hi) into `table` (tile layout, pre-zeroed by the launcher)
 cudaError_t launch_table_gen(s2kit_cuda_plan* p, double* table, uint64_t table_shift, int m_lo, int m_hi);
 // tile layout -> reference packed layout for one order
