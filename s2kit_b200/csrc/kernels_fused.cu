@@ -113,10 +113,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_fwd(
     const int gq = lane >> 2, q4 = lane & 3;
     const double sgn_neg = (m & 1) ? -1.0 : 1.0;
     const int base_pos = coef_base(m, B), base_neg = coef_base(-m, B);
-    for (int q = warp; q < total; q += LEG_WARPS) {
-        const int p = q < mb0.nrt ? 0 : 1;
+    for (int round = 0; round * LEG_WARPS < 2 * mb0.nrt; ++round) {
+        const int q = snake_item(round, warp, LEG_WARPS);
+        const int p = q & 1;
         const BlockMeta mb = p ? mb1 : mb0;
-        const int rt = p ? (mb.nrt - 1 - (q - mb0.nrt)) : (mb.nrt - 1 - q);
+        const int rt = mb0.nrt - 1 - (q >> 1);  // mb0.nrt >= mb1.nrt
+        if (q >= 2 * mb0.nrt || rt >= mb.nrt) continue;
         const int ctn = tiles_in_row(mb, rt);
         const double* tp = tbase + (uint64_t)srt[(p ? mb0.nrt : 0) + rt] * 64;
         const double* xp = Xs + (p * NC + gq) * CS + q4;
@@ -211,7 +213,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_inv(
     for (int it = 0; it < ITEMS; ++it) {
 #pragma unroll
         for (int j = 0; j < NC / 8; ++j) acc[it][j][0] = acc[it][j][1] = 0.0;
-        const int q = warp + it * LEG_WARPS;
+        const int q = snake_item(it, warp, LEG_WARPS);
         if (q < 2 * NCT) {
             const int p = q & 1, ct = q >> 1;
             inv_col_tile<NC>(tbase, srt + (p ? mb0.nrt : 0), p ? mb1 : mb0, ct, Cs + (p * NC + gq) * CS + q4, CS, boff0,
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_inv(
     double* Vs = Cs;  // [NC][VS], natural cosine index
 #pragma unroll
     for (int it = 0; it < ITEMS; ++it) {
-        const int q = warp + it * LEG_WARPS;
+        const int q = snake_item(it, warp, LEG_WARPS);
         if (q < 2 * NCT) {
             const int p = q & 1, ct = q >> 1;
 #pragma unroll

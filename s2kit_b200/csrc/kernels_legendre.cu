@@ -12,6 +12,8 @@
 // tile, never touching shared memory; the X (or coefficient) panel of the CTA's columns sits in shared
 // memory for the whole order.  The inverse reads the SAME tiles as B fragments (4 rows x 8 columns), so
 // no transposed table is stored (the reference keeps one: cospml.c:301-362).
+#include <stdlib.h>
+
 #include "s2k_legendre.cuh"
 
 namespace s2k {
@@ -66,11 +68,15 @@ __global__ void __launch_bounds__(LEG_WARPS * 32) k_legendre_fwd(
     const double sgn_neg = (m & 1) ? -1.0 : 1.0;
     const int base_pos = coef_base(m, bw), base_neg = coef_base(-m, bw);
 
-    for (int q = blockIdx.z * LEG_WARPS + warp; q < total; q += LEG_WARPS * gridDim.z) {
-        // heavy row tiles (large rt) first
-        const int p = q < mb0.nrt ? 0 : 1;
+    // items sorted by decreasing cost: (parity 0, rt), (parity 1, rt) for rt = nrt-1 .. 0; snake over the slots
+    const int nslots = LEG_WARPS * gridDim.z, slot = blockIdx.z * LEG_WARPS + warp;
+    for (int round = 0;; ++round) {
+        const int q = snake_item(round, slot, nslots);
+        if (round * nslots >= 2 * mb0.nrt) break;
+        const int p = q & 1;
         const BlockMeta mb = p ? mb1 : mb0;
-        const int rt = p ? (mb.nrt - 1 - (q - mb0.nrt)) : (mb.nrt - 1 - q);
+        const int rt = mb0.nrt - 1 - (q >> 1);  // mb0.nrt >= mb1.nrt
+        if (q >= 2 * mb0.nrt || rt >= mb.nrt) continue;
         const int ctn = tiles_in_row(mb, rt);
         const double* tp = tbase + (uint64_t)srt[(p ? mb0.nrt : 0) + rt] * 64;
         const double* xp = Xs + (p * NC + g) * CS + q4;
@@ -163,7 +169,10 @@ __global__ void __launch_bounds__(LEG_WARPS * 32) k_legendre_inv(
     // B fragment of k-step s: element (row q4 + 4s, col g) of the 8x8 tile
     const int boff0 = tile_elem_offset(q4, g), boff1 = tile_elem_offset(q4 + 4, g);
 
-    for (int q = blockIdx.z * LEG_WARPS + warp; q < 2 * nct; q += LEG_WARPS * gridDim.z) {
+    const int nslots = LEG_WARPS * gridDim.z, slot = blockIdx.z * LEG_WARPS + warp;
+    for (int round = 0; round * nslots < 2 * nct; ++round) {
+        const int q = snake_item(round, slot, nslots);
+        if (q >= 2 * nct) continue;
         const int p = q & 1, ct = q >> 1;  // low column tiles (most rows) first
         const BlockMeta mb = p ? mb1 : mb0;
         double acc[NC / 8][2];
@@ -232,6 +241,10 @@ static int pick_nc(int bw, int nfun, int real_fmt) {
     int cols = nfun * (real_fmt ? 2 : 4);
     size_t per_col = sizeof(double) * 2 * panel_stride(bw);
     int nc = 32;
+    if (const char* e = getenv("S2KIT_CUDA_NC")) {  // tuning override: 8, 16 or 32 panel columns
+        int v = atoi(e);
+        if (v == 8 || v == 16 || v == 32) nc = v;
+    }
     // prefer panels <= 110 KB (two CTAs per SM); a single 8-column panel may take up to the whole SM
     while (nc > 8 && (nc / 2 >= cols || per_col * nc > 110 * 1024)) nc /= 2;
     return nc;

@@ -47,6 +47,14 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
+// Work items of one order are dealt to the W = (warps per CTA) x (row split) parallel slots in "snake" order:
+// round i gives slot w the item i*W + w (i even) or i*W + W-1-w (i odd).  With the items sorted by decreasing
+// cost this keeps the per-slot sums within a few percent of each other; plain round-robin left the first warp
+// of a CTA with 2.4x the work of the last one at m = 0.
+__device__ __forceinline__ int snake_item(int round, int slot, int nslots) {
+    return round * nslots + ((round & 1) ? nslots - 1 - slot : slot);
+}
+
 // number of 8-wide column tiles of row tile rt in a parity block
 __device__ __forceinline__ int tiles_in_row(const BlockMeta& mb, int rt) {
     return (mb.len0 + min(8 * rt + 7, mb.rows - 1) + 7) >> 3;
@@ -57,18 +65,18 @@ __device__ __forceinline__ int tiles_in_row(const BlockMeta& mb, int rt) {
 template <int NC>
 __device__ __forceinline__ void fwd_row_tile(const double* __restrict__ tp, const double* xp, int CS, int ctn,
                                              double (&acc)[NC / 8][2]) {
+    // Ring of LEG_PREFETCH tiles in registers.  The refill is UNCONDITIONAL (index clamped to the last tile): a
+    // predicated refill made ptxas load into a temporary and copy it into the ring slot right away, which waits
+    // for the load and serialises the whole prefetch.
     double2 abuf[LEG_PREFETCH];
 #pragma unroll
     for (int u = 0; u < LEG_PREFETCH; ++u)
-        if (u < ctn) abuf[u] = __ldg(reinterpret_cast<const double2*>(tp + u * 64));
+        abuf[u] = __ldg(reinterpret_cast<const double2*>(tp + min(u, ctn - 1) * 64));
     for (int ct0 = 0; ct0 < ctn; ct0 += LEG_PREFETCH) {
 #pragma unroll
         for (int u = 0; u < LEG_PREFETCH; ++u) {
             const int ct = ct0 + u;
             if (ct < ctn) {
-                const double2 a = abuf[u];
-                if (ct + LEG_PREFETCH < ctn)
-                    abuf[u] = __ldg(reinterpret_cast<const double2*>(tp + (ct + LEG_PREFETCH) * 64));
                 double b[NC / 8][2];
 #pragma unroll
                 for (int j = 0; j < NC / 8; ++j) {
@@ -77,9 +85,11 @@ __device__ __forceinline__ void fwd_row_tile(const double* __restrict__ tp, cons
                 }
                 // k-step outer: consecutive DMMAs go to different accumulators
 #pragma unroll
-                for (int j = 0; j < NC / 8; ++j) dmma(acc[j], a.x, b[j][0]);
+                for (int j = 0; j < NC / 8; ++j) dmma(acc[j], abuf[u].x, b[j][0]);
 #pragma unroll
-                for (int j = 0; j < NC / 8; ++j) dmma(acc[j], a.y, b[j][1]);
+                for (int j = 0; j < NC / 8; ++j) dmma(acc[j], abuf[u].y, b[j][1]);
+                // refill this slot only after its last use so the load can target the slot registers directly
+                abuf[u] = __ldg(reinterpret_cast<const double2*>(tp + min(ct + LEG_PREFETCH, ctn - 1) * 64));
             }
         }
     }
@@ -96,26 +106,20 @@ __device__ __forceinline__ void inv_col_tile(const double* __restrict__ tbase, c
     // rows below rt_min never reach ct; from the first row tile that does, all later ones do (lengths grow)
     while (rt_min < mb.nrt && ct >= tiles_in_row(mb, rt_min)) ++rt_min;
     const int cnt = mb.nrt - rt_min;
+    if (cnt <= 0) return;
     double b0buf[LEG_PREFETCH], b1buf[LEG_PREFETCH];
 #pragma unroll
-    for (int u = 0; u < LEG_PREFETCH; ++u)
-        if (u < cnt) {
-            const double* tp = tbase + ((uint64_t)srt[rt_min + u] + ct) * 64;
-            b0buf[u] = __ldg(tp + boff0);
-            b1buf[u] = __ldg(tp + boff1);
-        }
+    for (int u = 0; u < LEG_PREFETCH; ++u) {
+        const double* tp = tbase + ((uint64_t)srt[rt_min + min(u, cnt - 1)] + ct) * 64;
+        b0buf[u] = __ldg(tp + boff0);
+        b1buf[u] = __ldg(tp + boff1);
+    }
     for (int i0 = 0; i0 < cnt; i0 += LEG_PREFETCH) {
 #pragma unroll
         for (int u = 0; u < LEG_PREFETCH; ++u) {
             const int i = i0 + u;
             if (i < cnt) {
                 const int rt = rt_min + i;
-                const double b0 = b0buf[u], b1 = b1buf[u];
-                if (i + LEG_PREFETCH < cnt) {
-                    const double* tp = tbase + ((uint64_t)srt[rt + LEG_PREFETCH] + ct) * 64;
-                    b0buf[u] = __ldg(tp + boff0);
-                    b1buf[u] = __ldg(tp + boff1);
-                }
                 double a[NC / 8][2];
 #pragma unroll
                 for (int j = 0; j < NC / 8; ++j) {
@@ -123,9 +127,14 @@ __device__ __forceinline__ void inv_col_tile(const double* __restrict__ tbase, c
                     a[j][1] = cp[j * 8 * CS + 8 * rt + 4];
                 }
 #pragma unroll
-                for (int j = 0; j < NC / 8; ++j) dmma(acc[j], a[j][0], b0);
+                for (int j = 0; j < NC / 8; ++j) dmma(acc[j], a[j][0], b0buf[u]);
 #pragma unroll
-                for (int j = 0; j < NC / 8; ++j) dmma(acc[j], a[j][1], b1);
+                for (int j = 0; j < NC / 8; ++j) dmma(acc[j], a[j][1], b1buf[u]);
+                {   // unconditional refill after the last use, clamped (see fwd_row_tile)
+                    const double* tp = tbase + ((uint64_t)srt[rt_min + min(i + LEG_PREFETCH, cnt - 1)] + ct) * 64;
+                    b0buf[u] = __ldg(tp + boff0);
+                    b1buf[u] = __ldg(tp + boff1);
+                }
             }
         }
     }
