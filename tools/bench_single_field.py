@@ -44,6 +44,9 @@ def main():
     g.manual_seed(1234)  # same field on every rank; each keeps its rings
     full_r = torch.rand(n, n, generator=g, device=dev, dtype=torch.float64) * 2 - 1
     full_i = torch.rand(n, n, generator=g, device=dev, dtype=torch.float64) * 2 - 1
+    if world > 1:  # identical field on every rank regardless of per-device generator state
+        dist.broadcast(full_r, 0)
+        dist.broadcast(full_i, 0)
     my_r, my_i = full_r[rank * nr:(rank + 1) * nr].contiguous(), full_i[rank * nr:(rank + 1) * nr].contiguous()
     if not a.check:
         del full_r, full_i
@@ -114,9 +117,10 @@ def main():
             dist.all_reduce(ci)
         if rank == 0:
             Q = s2.Plan(bw, s2.MEMO, max_batch=1, device=local)
+            Q.set_stream(torch.cuda.current_stream().cuda_stream)  # same stream as the fills below
             wr, wi = torch.zeros_like(cr), torch.zeros_like(ci)
             Q.fst(full_r, full_i, wr, wi, s2.COMPLEX)
-            Q.synchronize()
+            torch.cuda.synchronize()
             ok = torch.isfinite(wr) & torch.isfinite(wi)  # bw = 2048: orders >= 2044 are unpinned (reference NaN)
             scale = float(torch.maximum(wr[ok].abs().max(), wi[ok].abs().max()))
             res["sharded_vs_single_gpu_rel_err"] = float(
