@@ -47,7 +47,7 @@ def main():
     if world > 1:  # identical field on every rank regardless of per-device generator state
         dist.broadcast(full_r, 0)
         dist.broadcast(full_i, 0)
-    my_r, my_i = full_r[rank * nr:(rank + 1) * nr].contiguous(), full_i[rank * nr:(rank + 1) * nr].contiguous()
+    my_r, my_i = full_r[rank * nr:(rank + 1) * nr].clone(), full_i[rank * nr:(rank + 1) * nr].clone()  # not views
     if not a.check:
         del full_r, full_i
     send = torch.zeros(world * blk, device=dev, dtype=torch.float64)
@@ -125,6 +125,19 @@ def main():
             scale = float(torch.maximum(wr[ok].abs().max(), wi[ok].abs().max()))
             res["sharded_vs_single_gpu_rel_err"] = float(
                 torch.maximum((cr - wr)[ok].abs().max(), (ci - wi)[ok].abs().max())) / scale
+            if res["sharded_vs_single_gpu_rel_err"] > 1e-9:  # diagnostics: which rank's orders are off
+                import numpy as np
+                err = torch.maximum((cr - wr).abs(), (ci - wi).abs()).cpu().numpy() / scale
+                for r in range(world):
+                    orders, _ = s2.shard_layout(bw, world, r)
+                    worst = []
+                    for m in orders:
+                        for sm in ((m,) if m == 0 else (m, -m)):
+                            a0 = s2.index_of_harmonic_coeff(sm, m, bw)
+                            worst.append((float(np.nanmax(err[a0:a0 + bw - m])), sm))
+                    worst.sort(reverse=True)
+                    res[f"debug_rank{r}_worst"] = worst[:4]
+                    res[f"debug_rank{r}_median"] = float(np.median([w[0] for w in worst]))
             Q.close()
     if rank == 0:
         print(json.dumps(res))
