@@ -103,3 +103,16 @@ void s2k_host_quarter(int n, double* qt) {
     qt[2 * (3 * n)] = 0.0;    /* q = 3n */
     qt[2 * (2 * n) + 1] = 0.0; /* q = 2n: sin(pi) */
 }
+
+/* The DCT kernels read their input in even/odd-reordered positions p -> j(p) = 2p (p < n/2), 2(n-1-p)+1 otherwise;
+   these copies of the weights / sines are stored in that order so the loads are contiguous.
+   wv[par*n + p] = weights[par*n + j(p)] (par = parity of the order), sv[p] = sines[j(p)], n = 2 bw. */
+void s2k_host_reordered(int bw, const double* weights, const double* sines, double* wv, double* sv) {
+    const int n = 2 * bw;
+    for (int p = 0; p < n; ++p) {
+        int j = (p < bw) ? 2 * p : 2 * (n - 1 - p) + 1;
+        wv[p] = weights[j];
+        wv[n + p] = weights[n + j];
+        sv[p] = sines[j];
+    }
+}

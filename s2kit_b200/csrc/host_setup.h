@@ -10,6 +10,7 @@ void s2k_host_sines(int bw, double* s);                            /* 2 bw */
 void s2k_host_seeds(int bw, int m_lo, int m_hi, double* seeds);    /* (m_hi-m_lo) * bw */
 void s2k_host_twiddles(int n, double* tw);                         /* 2 n */
 void s2k_host_quarter(int n, double* qt);                          /* 8 n */
+void s2k_host_reordered(int bw, const double* weights, const double* sines, double* wv, double* sv); /* 4bw, 2bw */
 #ifdef __cplusplus
 }
 #endif

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(N / 8 * FPB) k_dct_fwd(const double* __restric
     for (int e = 0; e < 8; ++e) {
         int p = t + e * T8;
         int j = (p < B) ? 2 * p : 2 * (N - 1 - p) + 1;
-        double wj = __ldg(w + j);
+        double wj = __ldg(w + p);  // weights are stored in load order (s2k_host_reordered)
         long at = (long)(j >> pv.seg_shift) * pv.seg_stride + (j & pv.seg_mask);
         xr[e] = __ldg(Sr + at) * wj;
         xi[e] = __ldg(Si + at) * wj;
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(N / 8 * FPB) k_dct_inv(const double* __restric
     for (int e = 0; e < 8; ++e) {
         int i = fft_out_index<N>(e, t);
         int j = (i < B) ? 2 * i : 2 * (N - 1 - i) + 1;
-        double s = (m & 1) ? __ldg(sinv + j) * sign : sign;
+        double s = (m & 1) ? __ldg(sinv + i) * sign : sign;  // sines stored in output order (s2k_host_reordered)
         long at = (long)(j >> pv.seg_shift) * pv.seg_stride + (j & pv.seg_mask);
         Gr[at] = xi[e] * s;  // Re z -> column a (real part)
         Gi[at] = xr[e] * s;  // Im z -> column b (imaginary part)
@@ -361,7 +361,7 @@ static cudaError_t dct_fwd_n(s2kit_cuda_plan* p, const double* S, double* X, int
     cudaError_t e = set_smem(k_dct_fwd<N, FPB>, smem);
     if (e != cudaSuccess) return e;
     k_dct_fwd<N, FPB><<<dim3((hi - lo + FPB - 1) / FPB, nfun), T8 * FPB, smem, p->stream>>>(
-        S, X, p->d_weights, lo, hi, p->d_tw_n, p->d_q_n, pv);
+        S, X, p->d_wv, lo, hi, p->d_tw_n, p->d_q_n, pv);
     return cudaGetLastError();
 }
 
@@ -375,7 +375,7 @@ static cudaError_t dct_inv_n(s2kit_cuda_plan* p, const double* V, double* G, int
     if (e != cudaSuccess) return e;
     double out_scale = 1.0 / sqrt(2.0 * M_PI);  // FST_semi_memo.c:344
     k_dct_inv<N, FPB><<<dim3((hi - lo + FPB - 1) / FPB, nfun), T8 * FPB, smem, p->stream>>>(
-        V, G, p->d_sin, lo, hi, out_scale, p->d_tw_n, p->d_q_n, pv);
+        V, G, p->d_sv, lo, hi, out_scale, p->d_tw_n, p->d_q_n, pv);
     return cudaGetLastError();
 }
 

@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_fwd(
             for (int e = 0; e < 8; ++e) {
                 int p = t + e * T8;
                 int j = (p < B) ? 2 * p : 2 * (N - 1 - p) + 1;
-                double wj = __ldg(w + j);
+                double wj = __ldg(w + p);  // load order (s2k_host_reordered)
                 xr[e] = __ldg(Sr + j) * wj;
                 xi[e] = __ldg(Si + j) * wj;
             }
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_inv(
             for (int e = 0; e < 8; ++e) {
                 int i = fft_out_index<N>(e, t);
                 int j = (i < B) ? 2 * i : 2 * (N - 1 - i) + 1;
-                double s = (m & 1) ? __ldg(sinv + j) * sign : sign;
+                double s = (m & 1) ? __ldg(sinv + i) * sign : sign;  // output order (s2k_host_reordered)
                 Gr[j] = xi[e] * s;
                 Gi[j] = xr[e] * s;
             }
@@ -305,7 +305,7 @@ static cudaError_t fused_fwd_launch(s2kit_cuda_plan* p, const double* table, uin
     int NF = NC / (real_fmt ? 2 : 4);
     dim3 grid((nfun + NF - 1) / NF, m_hi - m_lo);
     k_fused_fwd<N, NC><<<grid, FUSED_THREADS, smem, p->stream>>>(table, p->d_order_start, shift, p->d_meta,
-                                                                 p->d_rt_start, S, p->d_weights, p->d_tw_n, p->d_q_n,
+                                                                 p->d_rt_start, S, p->d_wv, p->d_tw_n, p->d_q_n,
                                                                  rco, ico, coef_stride, nfun, m_lo, real_fmt);
     return cudaGetLastError();
 }
@@ -320,7 +320,7 @@ static cudaError_t fused_inv_launch(s2kit_cuda_plan* p, const double* table, uin
     int NF = NC / (real_fmt ? 2 : 4);
     dim3 grid((nfun + NF - 1) / NF, m_hi - m_lo);
     k_fused_inv<N, NC><<<grid, FUSED_THREADS, smem, p->stream>>>(
-        table, p->d_order_start, shift, p->d_meta, p->d_rt_start, rco, ico, coef_stride, p->d_sin, p->d_tw_n, p->d_q_n, G,
+        table, p->d_order_start, shift, p->d_meta, p->d_rt_start, rco, ico, coef_stride, p->d_sv, p->d_tw_n, p->d_q_n, G,
         1.0 / sqrt(2.0 * M_PI), nfun, m_lo, real_fmt);
     return cudaGetLastError();
 }

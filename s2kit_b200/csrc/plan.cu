@@ -238,6 +238,10 @@ int s2k_plan_create_impl(s2kit_cuda_plan** out, int bw, int variant, int max_bat
         s2k_host_quarter(bw, qb.data());
         CK(upload(&p->d_weights, w.data(), w.size()));
         CK(upload(&p->d_sin, s.data(), s.size()));
+        std::vector<double> wv(4 * bw), sv(n);
+        s2k_host_reordered(bw, w.data(), s.data(), wv.data(), sv.data());
+        CK(upload(&p->d_wv, wv.data(), wv.size()));
+        CK(upload(&p->d_sv, sv.data(), sv.size()));
         CK(upload(&p->d_nodes, x.data(), x.size()));
         CK(upload(&p->d_tw_n, tw.data(), (size_t)n));
         CK(upload(&p->d_tw_b, tb.data(), (size_t)bw));
@@ -322,7 +326,7 @@ extern "C" int s2kit_cuda_plan_destroy(s2kit_cuda_plan* p) {
     cudaSetDevice(p->device);
     cudaStreamSynchronize(p->stream);
     s2k_shard_destroy(p);
-    void* ptrs[] = {p->d_weights, p->d_sin,      p->d_tw_n,       p->d_tw_b, p->d_q_n,  p->d_q_b,
+    void* ptrs[] = {p->d_wv, p->d_sv, p->d_weights, p->d_sin,      p->d_tw_n,       p->d_tw_b, p->d_q_n,  p->d_q_b,
                     p->d_nodes,   p->d_seeds,    p->d_rec,        p->d_table, p->d_meta, p->d_rt_start,
                     p->d_order_start, p->d_units, p->d_S,          p->d_X,    p->d_coef, p->d_coef2,
                     p->d_filt,    p->d_stage};

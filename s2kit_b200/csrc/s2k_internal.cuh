@@ -61,6 +61,8 @@ struct s2kit_cuda_plan {
     // host-computed constants on the device
     double* d_weights = nullptr;   // 4 bw   (weights.c:32-47)
     double* d_sin = nullptr;       // 2 bw   sin((2j+1) pi / 4bw)
+    double* d_wv = nullptr;        // 4 bw   weights in the DCT kernels' even/odd-reordered load order
+    double* d_sv = nullptr;        // 2 bw   sines in that order
     double2* d_tw_n = nullptr;     // n      (cos, -sin)(2 pi q / n)
     double2* d_tw_b = nullptr;     // bw     (cos, -sin)(2 pi q / bw)
     double2* d_q_n = nullptr;      // 4n     (cos, sin)(pi q / 2n)

@@ -5,7 +5,9 @@
 namespace s2k {
 
 constexpr int LEG_WARPS = 8;
-constexpr int LEG_PREFETCH = 4;  // table tiles kept in flight per warp
+// table tiles kept in flight per warp: few when the panel is wide (many DMMAs per tile hide the latency), many
+// when a single field streams the table from HBM with 1-2 MMA column tiles per table tile
+__host__ __device__ constexpr int leg_prefetch(int nc) { return nc >= 32 ? 4 : (nc >= 16 ? 8 : 12); }
 
 // D(8x8) += A(8x4) * B(4x8), FP64 tensor core (SASS: DMMA.8x8x4)
 __device__ __forceinline__ void dmma(double (&d)[2], double a, double b) {
@@ -32,10 +34,13 @@ __host__ __device__ inline int panel_stride(int bw) {
 // window per order, and the streaming traffic of the batch evicts it between launches: without this every tile of
 // the main loop is a first-touch DRAM miss (~1 us) that the few tiles of register prefetch cannot cover
 // (profiles/r1_ncu_summary.md).
+// One bulk-prefetch instruction per CTA (no per-line LSU traffic).  Orders larger than 1 MiB (single large-bw
+// fields) are streamed with deep register prefetch instead; pulling megabytes into L2 per CTA would only thrash.
 __device__ __forceinline__ void prefetch_order_l2(const double* base, uint64_t tiles, int tid, int nthreads) {
-    const char* p = reinterpret_cast<const char*>(base);
-    const uint64_t lines = tiles * 4;  // 512-byte tiles, 128-byte lines
-    for (uint64_t i = tid; i < lines; i += nthreads) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + i * 128));
+    (void)nthreads;
+    const uint64_t bytes = tiles * 512;
+    if (tid == 0 && bytes > 0 && bytes <= (1u << 20))
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base), "r"((unsigned)bytes) : "memory");
 }
 
 // 8-byte asynchronous global -> shared copy (LDGSTS): no register staging, all copies of a thread in flight at once
@@ -68,6 +73,7 @@ __device__ __forceinline__ void fwd_row_tile(const double* __restrict__ tp, cons
     // Ring of LEG_PREFETCH tiles in registers.  The refill is UNCONDITIONAL (index clamped to the last tile): a
     // predicated refill made ptxas load into a temporary and copy it into the ring slot right away, which waits
     // for the load and serialises the whole prefetch.
+    constexpr int LEG_PREFETCH = leg_prefetch(NC);
     double2 abuf[LEG_PREFETCH];
 #pragma unroll
     for (int u = 0; u < LEG_PREFETCH; ++u)
@@ -107,6 +113,7 @@ __device__ __forceinline__ void inv_col_tile(const double* __restrict__ tbase, c
     while (rt_min < mb.nrt && ct >= tiles_in_row(mb, rt_min)) ++rt_min;
     const int cnt = mb.nrt - rt_min;
     if (cnt <= 0) return;
+    constexpr int LEG_PREFETCH = leg_prefetch(NC) < 8 ? leg_prefetch(NC) : 8;
     double b0buf[LEG_PREFETCH], b1buf[LEG_PREFETCH];
 #pragma unroll
     for (int u = 0; u < LEG_PREFETCH; ++u) {
