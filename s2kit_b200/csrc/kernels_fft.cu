@@ -163,21 +163,28 @@ __global__ void __launch_bounds__(N / 8 * FPB) k_dct_fwd(const double* __restric
     if (!live) return;
     double* Xr = X + (((long)f * N + mp) * 2) * B;
     double* Xi = Xr + B;
-    const double s_all = rsqrt(2.0 * (double)N);  // 1/sqrt(2*size), seminaive.c:174
-    for (int k = t; k < B; k += T8) {
-        int nk = (N - k) & (N - 1);
-        double ar = sre[fft_pad(k)], ai = sim[fft_pad(k)];
-        double br = sre[fft_pad(nk)], bi = sim[fft_pad(nk)];
-        // V1 = (Z[k] + conj Z[n-k]) / 2 ; V2 = (Z[k] - conj Z[n-k]) / 2i ; REDFT10 = 2 Re(e^{-i pi k/2n} V)
-        double2 q = __ldg(qtab + k);
-        double y1 = q.x * (ar + br) + q.y * (ai - bi);
-        double y2 = q.x * (ai + bi) - q.y * (ar - br);
-        if (k == 0) {
-            y1 *= 0.70710678118654752440;  // M_SQRT1_2, seminaive.c:173
-            y2 *= 0.70710678118654752440;
+    const double s_all = 1.0 / sqrt(2.0 * (double)N);  // 1/sqrt(2*size), seminaive.c:174
+    // each thread finishes the pairs (2c, 2c+1): in the parity-split plane both land at slot c of their half, so a
+    // warp writes two fully coalesced runs
+    constexpr int HALF = B / 2;
+    for (int c = t; c < HALF; c += T8) {
+#pragma unroll
+        for (int par = 0; par < 2; ++par) {
+            int k = 2 * c + par;
+            int nk = (N - k) & (N - 1);
+            double ar = sre[fft_pad(k)], ai = sim[fft_pad(k)];
+            double br = sre[fft_pad(nk)], bi = sim[fft_pad(nk)];
+            // V1 = (Z[k] + conj Z[n-k]) / 2 ; V2 = (Z[k] - conj Z[n-k]) / 2i ; REDFT10 = 2 Re(e^{-i pi k/2n} V)
+            double2 q = __ldg(qtab + k);
+            double y1 = q.x * (ar + br) + q.y * (ai - bi);
+            double y2 = q.x * (ai + bi) - q.y * (ar - br);
+            if (k == 0) {
+                y1 *= 0.70710678118654752440;  // M_SQRT1_2, seminaive.c:173
+                y2 *= 0.70710678118654752440;
+            }
+            Xr[par * HALF + c] = y1 * s_all;
+            Xi[par * HALF + c] = y2 * s_all;
         }
-        Xr[k] = y1 * s_all;
-        Xi[k] = y2 * s_all;
     }
 }
 
@@ -199,8 +206,8 @@ __global__ void __launch_bounds__(N / 8 * FPB) k_dct_inv(const double* __restric
     const int m = mp < B ? mp : N - mp;
     const double* Va = V + (((long)f * N + mp) * 2) * B;
     const double* Vb = Va + B;
-    const double c_rest = rsqrt(2.0 * (double)N);  // 0.5/sqrt(bw), seminaive.c:72
-    const double c_zero = rsqrt((double)N);        // fcos[0] / sqrt(2 bw), seminaive.c:98
+    const double c_rest = 1.0 / sqrt(2.0 * (double)N);  // 0.5/sqrt(bw), seminaive.c:72
+    const double c_zero = 1.0 / sqrt((double)N);        // fcos[0] / sqrt(2 bw), seminaive.c:98
     double xr[8], xi[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -210,7 +217,7 @@ __global__ void __launch_bounds__(N / 8 * FPB) k_dct_inv(const double* __restric
         if (k != B) {
             int src = k < B ? k : N - k;
             double sc = (src == 0) ? c_zero : c_rest;
-            double a = __ldg(Va + src) * sc, b = __ldg(Vb + src) * sc;
+            double a = __ldg(Va + cos_slot(src, B)) * sc, b = __ldg(Vb + cos_slot(src, B)) * sc;
             double2 q = __ldg(qtab + k);
             double ur = (k < B) ? a : b, ui = (k < B) ? b : -a;  // (a + ib) or -i (a + ib)
             wr = q.x * ur - q.y * ui;
@@ -296,7 +303,7 @@ __global__ void k_direct_dct_fwd(const double* __restrict__ S, double* __restric
         for (int j = 0; j < n; ++j) acc += col[j] * w[j] * qtab[(int)(((long)(2 * j + 1) * k) % (4 * n))].x;
         acc *= 2.0;
         if (k == 0) acc *= 0.70710678118654752440;
-        X[(((long)f * n + mp) * 2 + part) * bw + k] = acc * s_all;
+        X[(((long)f * n + mp) * 2 + part) * bw + cos_slot(k, bw)] = acc * s_all;
     }
 }
 
@@ -311,7 +318,7 @@ __global__ void k_direct_dct_inv(const double* __restrict__ V, double* __restric
         int part = o / n, j = o % n;
         const double* v = V + (((long)f * n + mp) * 2 + part) * bw;
         double acc = v[0] * c_zero;
-        for (int k = 1; k < bw; ++k) acc += 2.0 * (v[k] * c_rest) * qtab[(int)(((long)(2 * j + 1) * k) % (4 * n))].x;
+        for (int k = 1; k < bw; ++k) acc += 2.0 * (v[cos_slot(k, bw)] * c_rest) * qtab[(int)(((long)(2 * j + 1) * k) % (4 * n))].x;
         double s = (m & 1) ? sinv[j] * sign : sign;
         G[(((long)f * 2 + part) * n + mp) * n + j] = acc * s;
     }

@@ -21,7 +21,7 @@ namespace s2k {
 // ------------------------------------------------------------------------------------------------ K3
 // grid: x = column tile, y = order (heavy orders first), z = row split.  NC columns per CTA.
 template <int NC>
-__global__ void __launch_bounds__(LEG_WARPS * 32) k_legendre_fwd(
+__global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_fwd(
     const double* __restrict__ table, const uint64_t* __restrict__ order_start, uint64_t table_shift,
     const BlockMeta* __restrict__ meta, const uint32_t* __restrict__ rt_start, const double* __restrict__ X,
     double* __restrict__ rco, double* __restrict__ ico, long coef_stride, int bw, int nfun, int m_lo, int real_fmt,
@@ -50,7 +50,16 @@ __global__ void __launch_bounds__(LEG_WARPS * 32) k_legendre_fwd(
         }
         int mp = sgn ? n - m : m;
         const double* src = X + (((long)f * n + mp) * 2 + part) * bw;
-        for (int k = lane; k < bw; k += 32) cp_async8(((k & 1) ? d1 : d0) + (k >> 1), src + k);
+        // the plane stores even cosine indices first, then odd ones (cos_slot): two contiguous runs per column
+        if ((bw & 3) == 0) {
+            for (int c = 2 * lane; c < half; c += 64) {
+                cp_async16(d0 + c, src + c);
+                cp_async16(d1 + c, src + half + c);
+            }
+        } else {
+            for (int c = lane; c < half; c += 32) cp_async8(d0 + c, src + c);
+            for (int c = lane; c < bw / 2; c += 32) cp_async8(d1 + c, src + half + c);
+        }
         for (int c = half + lane; c < CS; c += 32) d0[c] = d1[c] = 0.0;
         if ((bw & 1) && lane == 0) d1[half - 1] = 0.0;  // odd bw: parity 1 has one entry less
     }
@@ -123,7 +132,7 @@ __global__ void __launch_bounds__(LEG_WARPS * 32) k_legendre_fwd(
 // ------------------------------------------------------------------------------------------------ K4
 // V[col, k] = sum_l T_m[l, k] c[l, col]: D(8 cols x 8 k) += A(8 cols x 4 l) * B(4 l x 8 k)
 template <int NC>
-__global__ void __launch_bounds__(LEG_WARPS * 32) k_legendre_inv(
+__global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_inv(
     const double* __restrict__ table, const uint64_t* __restrict__ order_start, uint64_t table_shift,
     const BlockMeta* __restrict__ meta, const uint32_t* __restrict__ rt_start, const double* __restrict__ rco,
     const double* __restrict__ ico, long coef_stride, double* __restrict__ V, int bw, int nfun, int m_lo,
@@ -189,10 +198,14 @@ __global__ void __launch_bounds__(LEG_WARPS * 32) k_legendre_inv(
             if (f >= nfun || (sgn && m == 0)) continue;
             int mp = sgn ? n - m : m;
             double* dst = V + (((long)f * n + mp) * 2 + part) * bw;
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                int k = 2 * (8 * ct + 2 * q4 + e) + p;
-                if (k < bw) dst[k] = acc[j][e];
+            // slots c = 8ct + 2 q4 + {0,1} of parity p are adjacent in the parity-split plane
+            const int c0 = 8 * ct + 2 * q4, hp = p ? bw / 2 : (bw + 1) / 2;
+            double* d = dst + p * ((bw + 1) / 2) + c0;
+            if (c0 + 1 < hp && ((bw & 3) == 0)) {
+                *reinterpret_cast<double2*>(d) = make_double2(acc[j][0], acc[j][1]);
+            } else {
+                if (c0 < hp) d[0] = acc[j][0];
+                if (c0 + 1 < hp) d[1] = acc[j][1];
             }
         }
     }

@@ -213,8 +213,10 @@ int s2k_plan_create_impl(s2kit_cuda_plan** out, int bw, int variant, int max_bat
     p->nranks = nranks;
     p->fast = is_pow2(bw) && bw >= 16;
     {
-        const char* nf = getenv("S2KIT_CUDA_NO_FUSE");
-        p->fuse = !(nf && nf[0] == '1');
+        // The fused DCT+Legendre kernels save 4 of 17 MiB of HBM traffic per function and direction but are ~4%
+        // slower than the separate kernels at bw = 256 today (profiles/r1_ncu_summary.md): opt-in.
+        const char* fu = getenv("S2KIT_CUDA_FUSE");
+        p->fuse = (fu && fu[0] == '1');
         const char* np = getenv("S2KIT_CUDA_NO_L2PERSIST");
         p->l2_persist = !(np && np[0] == '1');
     }

@@ -25,6 +25,10 @@ struct BlockMeta {
 
 __host__ __device__ inline int tile_elem_offset(int i, int j) { return 2 * (4 * i + (j & 3)) + (j >> 2); }
 
+// Cosine planes X / V store the bw cosine indices of a column split by parity: even k first, then odd k.  The
+// contraction kernels keep the two parities in separate panels, so both sides move contiguous runs.
+__host__ __device__ inline int cos_slot(int k, int bw) { return (k & 1) * ((bw + 1) / 2) + (k >> 1); }
+
 // How a spectral plane is addressed.  The default describes the ordinary [part][order row][latitude] plane; the
 // sharded single-field path points the same kernels at all-to-all send / receive blocks instead
 // ([peer][part][local row][local ring], shard.cu).
@@ -48,7 +52,7 @@ struct ProfileSlot {
 struct s2kit_cuda_plan {
     int bw = 0, n = 0, variant = 0, device = 0, chunk = 1;
     bool fast = false;  // power-of-two bandwidth >= 16: radix FFT kernels; otherwise direct O(n^2) kernels
-    bool fuse = true;   // fused DCT+Legendre kernels for batched calls (S2KIT_CUDA_NO_FUSE=1 disables)
+    bool fuse = false;  // fused DCT+Legendre kernels for batched calls (S2KIT_CUDA_FUSE=1 enables)
     bool l2_persist = true;  // persisting-L2 window on a Memo table that fits (S2KIT_CUDA_NO_L2PERSIST=1 disables)
     cudaStream_t stream = nullptr;
     bool own_stream = true;
@@ -122,7 +126,7 @@ cudaError_t launch_phi_fft_fwd(s2kit_cuda_plan* p, const double* rdata, const do
                                double* S, int nfun, int data_format, const PlaneView* view = nullptr);
 cudaError_t launch_phi_fft_inv(s2kit_cuda_plan* p, const double* G, double* rdata, double* idata, long stride,
                                int nfun, int data_format, const PlaneView* view = nullptr);
-// K2 / K5: DCT stages.  X layout [f][order row][part][bw]
+// K2 / K5: DCT stages.  X layout [f][order row][part][cos_slot(k)]
 cudaError_t launch_dct_fwd(s2kit_cuda_plan* p, const double* S, double* X, int nfun, int row_lo, int row_hi,
                            int data_format, const PlaneView* view = nullptr);
 cudaError_t launch_dct_inv(s2kit_cuda_plan* p, const double* V, double* G, int nfun, int row_lo, int row_hi,
