@@ -19,31 +19,35 @@
 namespace s2k {
 
 // ------------------------------------------------------------------------------------------------ K3
-// grid: x = column tile, y = order (heavy orders first), z = row split.  NC columns per CTA.
-template <int NC>
+// grid: x = column tile, y = order (heavy orders first), z = row split.  NC = MMA columns per CTA (multiple of 8),
+// PC = columns actually stored in the panel: PC = 4 < NC = 8 is the single-field case (re/im x +-m), where the
+// other half of the 8-wide MMA tile is fed zeros from registers so the panel -- and with it the shared memory per
+// CTA -- halves and three CTAs fit an SM even at bw = 2048.
+template <int NC, int PC>
 __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_fwd(
     const double* __restrict__ table, const uint64_t* __restrict__ order_start, uint64_t table_shift,
     const BlockMeta* __restrict__ meta, const uint32_t* __restrict__ rt_start, const double* __restrict__ X,
     double* __restrict__ rco, double* __restrict__ ico, long coef_stride, int bw, int nfun, int m_lo, int real_fmt,
-    const int* __restrict__ order_list) {
+    const int* __restrict__ order_list, unsigned l2pf_cap) {
     extern __shared__ double smem[];
     const int n = 2 * bw, CS = panel_stride(bw);
     const int m = order_list ? order_list[blockIdx.y] : m_lo + blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cols_per_fn = real_fmt ? 2 : 4;
-    const int NF = NC / cols_per_fn;
+    const int NF = PC / cols_per_fn;
     const int f0 = blockIdx.x * NF;
-    double* Xs = smem;  // [2][NC][CS]
+    double* Xs = smem;  // [2][PC][CS]
 
-    prefetch_order_l2(table + (order_start[m] - table_shift) * 64, order_start[m + 1] - order_start[m], tid, blockDim.x);
+    prefetch_order_l2(table + (order_start[m] - table_shift) * 64, order_start[m + 1] - order_start[m], tid, blockDim.x,
+                      l2pf_cap);
     // ---- stage the X panel, de-interleaved by cosine-index parity; dead columns and the pad slots are zero
     const int half = (bw + 1) / 2;
-    for (int col = warp; col < NC; col += LEG_WARPS) {
+    for (int col = warp; col < PC; col += LEG_WARPS) {
         int fl = col / cols_per_fn, sub = col % cols_per_fn;
         int sgn = real_fmt ? 0 : (sub >> 1), part = sub & 1;
         int f = f0 + fl;
         double* d0 = Xs + col * CS;
-        double* d1 = Xs + (NC + col) * CS;
+        double* d1 = Xs + (PC + col) * CS;
         if (f >= nfun || (sgn && m == 0)) {
             for (int c = lane; c < CS; c += 32) d0[c] = d1[c] = 0.0;
             continue;
@@ -68,7 +72,7 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_fwd(
 
     const BlockMeta mb0 = meta[2 * m], mb1 = meta[2 * m + 1];
     const int total = mb0.nrt + mb1.nrt;
-    uint32_t* srt = reinterpret_cast<uint32_t*>(Xs + 2 * NC * CS);  // row-tile starts of both parity blocks
+    uint32_t* srt = reinterpret_cast<uint32_t*>(Xs + 2 * PC * CS);  // row-tile starts of both parity blocks
     for (int i = tid; i < total; i += blockDim.x)
         srt[i] = rt_start[(i < mb0.nrt ? mb0.rt_base : mb1.rt_base - mb0.nrt) + i];
     __syncthreads();
@@ -88,12 +92,12 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_fwd(
         if (q >= 2 * mb0.nrt || rt >= mb.nrt) continue;
         const int ctn = tiles_in_row(mb, rt);
         const double* tp = tbase + (uint64_t)srt[(p ? mb0.nrt : 0) + rt] * 64;
-        const double* xp = Xs + (p * NC + g) * CS + q4;
+        const double* xp = Xs + (p * PC + (PC < NC ? (g & (PC - 1)) : g)) * CS + q4;
 
         double acc[NC / 8][2];
 #pragma unroll
         for (int j = 0; j < NC / 8; ++j) acc[j][0] = acc[j][1] = 0.0;
-        fwd_row_tile<NC>(tp, xp, CS, ctn, acc);
+        fwd_row_tile<NC>(tp, xp, CS, ctn, acc, PC < NC && g >= PC);
 
         // ---- epilogue: lane holds rows r = 8rt + g, columns 8j + 2 q4 + {0,1}
         const int r = 8 * rt + g;
@@ -106,7 +110,7 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_fwd(
                     int col = 8 * j + 2 * q4 + e;
                     int fl = col / cols_per_fn, sub = col % cols_per_fn;
                     int f = f0 + fl;
-                    if (f >= nfun) continue;
+                    if (f >= nfun || col >= PC) continue;
                     double v = acc[j][e];
                     if (real_fmt) {
                         int part = sub & 1;
@@ -131,29 +135,30 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_fwd(
 
 // ------------------------------------------------------------------------------------------------ K4
 // V[col, k] = sum_l T_m[l, k] c[l, col]: D(8 cols x 8 k) += A(8 cols x 4 l) * B(4 l x 8 k)
-template <int NC>
+template <int NC, int PC>
 __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_inv(
     const double* __restrict__ table, const uint64_t* __restrict__ order_start, uint64_t table_shift,
     const BlockMeta* __restrict__ meta, const uint32_t* __restrict__ rt_start, const double* __restrict__ rco,
     const double* __restrict__ ico, long coef_stride, double* __restrict__ V, int bw, int nfun, int m_lo,
-    int real_fmt, const int* __restrict__ order_list) {
+    int real_fmt, const int* __restrict__ order_list, unsigned l2pf_cap) {
     extern __shared__ double smem[];
     const int n = 2 * bw, CS = panel_stride(bw);
     const int m = order_list ? order_list[blockIdx.y] : m_lo + blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int cols_per_fn = real_fmt ? 2 : 4;
-    const int NF = NC / cols_per_fn;
+    const int NF = PC / cols_per_fn;
     const int f0 = blockIdx.x * NF;
-    double* Cs = smem;  // [2][NC][CS], row index r = (l-m)>>1
+    double* Cs = smem;  // [2][PC][CS], row index r = (l-m)>>1
 
-    prefetch_order_l2(table + (order_start[m] - table_shift) * 64, order_start[m + 1] - order_start[m], tid, blockDim.x);
+    prefetch_order_l2(table + (order_start[m] - table_shift) * 64, order_start[m + 1] - order_start[m], tid, blockDim.x,
+                      l2pf_cap);
     const int base_pos = coef_base(m, bw), base_neg = coef_base(-m, bw);
-    for (int col = warp; col < NC; col += LEG_WARPS) {
+    for (int col = warp; col < PC; col += LEG_WARPS) {
         int fl = col / cols_per_fn, sub = col % cols_per_fn;
         int sgn = real_fmt ? 0 : (sub >> 1), part = sub & 1;
         int f = f0 + fl;
         double* d0 = Cs + col * CS;
-        double* d1 = Cs + (NC + col) * CS;
+        double* d1 = Cs + (PC + col) * CS;
         if (f >= nfun || (sgn && m == 0)) {
             for (int c = lane; c < CS; c += 32) d0[c] = d1[c] = 0.0;
             continue;
@@ -169,7 +174,7 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_inv(
 
     const BlockMeta mb0 = meta[2 * m], mb1 = meta[2 * m + 1];
     const int nct = (((bw + 1) / 2) + 7) >> 3;  // column tiles needed to cover every k < bw of one parity
-    uint32_t* srt = reinterpret_cast<uint32_t*>(Cs + 2 * NC * CS);
+    uint32_t* srt = reinterpret_cast<uint32_t*>(Cs + 2 * PC * CS);
     for (int i = tid; i < mb0.nrt + mb1.nrt; i += blockDim.x)
         srt[i] = rt_start[(i < mb0.nrt ? mb0.rt_base : mb1.rt_base - mb0.nrt) + i];
     __syncthreads();
@@ -187,7 +192,9 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_inv(
         double acc[NC / 8][2];
 #pragma unroll
         for (int j = 0; j < NC / 8; ++j) acc[j][0] = acc[j][1] = 0.0;
-        inv_col_tile<NC>(tbase, srt + (p ? mb0.nrt : 0), mb, ct, Cs + (p * NC + g) * CS + q4, CS, boff0, boff1, acc);
+        inv_col_tile<NC>(tbase, srt + (p ? mb0.nrt : 0), mb, ct,
+                         Cs + (p * PC + (PC < NC ? (g & (PC - 1)) : g)) * CS + q4, CS, boff0, boff1, acc,
+                         PC < NC && g >= PC);
         // ---- epilogue: lane holds column 8j + g, cosine slots c = 8ct + 2 q4 + {0,1}
 #pragma unroll
         for (int j = 0; j < NC / 8; ++j) {
@@ -195,7 +202,7 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_inv(
             int fl = col / cols_per_fn, sub = col % cols_per_fn;
             int sgn = real_fmt ? 0 : (sub >> 1), part = sub & 1;
             int f = f0 + fl;
-            if (f >= nfun || (sgn && m == 0)) continue;
+            if (f >= nfun || col >= PC || (sgn && m == 0)) continue;
             int mp = sgn ? n - m : m;
             double* dst = V + (((long)f * n + mp) * 2 + part) * bw;
             // slots c = 8ct + 2 q4 + {0,1} of parity p are adjacent in the parity-split plane
@@ -211,40 +218,54 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_inv(
     }
 }
 
+// Orders up to this many bytes are pulled into L2 by one bulk prefetch at CTA start.  Larger orders (single large-bw
+// fields) are streamed by the register ring alone: with hundreds of CTAs in flight a whole-order prefetch of
+// megabytes each overruns L2 and the data is fetched twice.
+static unsigned l2_prefetch_cap(int panel_cols) {
+    static long cap = [] {
+        const char* e = getenv("S2KIT_CUDA_L2PF_MAX");
+        return e ? (long)strtoul(e, nullptr, 10) : -1L;
+    }();
+    if (cap >= 0) return (unsigned)cap;
+    // measured (profiles/r1_ncu_summary.md): the prefetch pays when 32-column CTAs of a batch share an order; a
+    // single field streams every tile exactly once and is faster without it (bw 512: 68 vs 84 us, bw 2048: 3.2 vs 4.0 ms)
+    return panel_cols >= 16 ? (1u << 20) : 0u;
+}
+
 // ------------------------------------------------------------------------------------------------ launchers
-template <int NC>
+template <int NC, int PC = NC>
 static cudaError_t leg_fwd_nc(s2kit_cuda_plan* p, const double* table, uint64_t shift, const double* X, double* rco,
                               double* ico, long coef_stride, int nfun, int m_lo, int m_hi, int real_fmt, int rowsplit,
                               const int* order_list) {
     int cols_per_fn = real_fmt ? 2 : 4;
-    int NF = NC / cols_per_fn;
-    size_t smem = sizeof(double) * 2 * NC * panel_stride(p->bw) + sizeof(uint32_t) * (p->bw / 8 + 8);
+    int NF = PC / cols_per_fn;
+    size_t smem = sizeof(double) * 2 * PC * panel_stride(p->bw) + sizeof(uint32_t) * (p->bw / 8 + 8);
     if (smem > 48 * 1024) {
-        cudaError_t e = ensure_smem(reinterpret_cast<const void*>(k_legendre_fwd<NC>), smem);
+        cudaError_t e = ensure_smem(reinterpret_cast<const void*>(k_legendre_fwd<NC, PC>), smem);
         if (e != cudaSuccess) return e;
     }
     dim3 grid((nfun + NF - 1) / NF, m_hi - m_lo, rowsplit);
-    k_legendre_fwd<NC><<<grid, LEG_WARPS * 32, smem, p->stream>>>(table, p->d_order_start, shift, p->d_meta,
+    k_legendre_fwd<NC, PC><<<grid, LEG_WARPS * 32, smem, p->stream>>>(table, p->d_order_start, shift, p->d_meta,
                                                                   p->d_rt_start, X, rco, ico, coef_stride, p->bw, nfun,
-                                                                  m_lo, real_fmt, order_list);
+                                                                  m_lo, real_fmt, order_list, l2_prefetch_cap(PC));
     return cudaGetLastError();
 }
 
-template <int NC>
+template <int NC, int PC = NC>
 static cudaError_t leg_inv_nc(s2kit_cuda_plan* p, const double* table, uint64_t shift, const double* rco,
                               const double* ico, long coef_stride, double* V, int nfun, int m_lo, int m_hi,
                               int real_fmt, int rowsplit, const int* order_list) {
     int cols_per_fn = real_fmt ? 2 : 4;
-    int NF = NC / cols_per_fn;
-    size_t smem = sizeof(double) * 2 * NC * panel_stride(p->bw) + sizeof(uint32_t) * (p->bw / 8 + 8);
+    int NF = PC / cols_per_fn;
+    size_t smem = sizeof(double) * 2 * PC * panel_stride(p->bw) + sizeof(uint32_t) * (p->bw / 8 + 8);
     if (smem > 48 * 1024) {
-        cudaError_t e = ensure_smem(reinterpret_cast<const void*>(k_legendre_inv<NC>), smem);
+        cudaError_t e = ensure_smem(reinterpret_cast<const void*>(k_legendre_inv<NC, PC>), smem);
         if (e != cudaSuccess) return e;
     }
     dim3 grid((nfun + NF - 1) / NF, m_hi - m_lo, rowsplit);
-    k_legendre_inv<NC><<<grid, LEG_WARPS * 32, smem, p->stream>>>(table, p->d_order_start, shift, p->d_meta,
+    k_legendre_inv<NC, PC><<<grid, LEG_WARPS * 32, smem, p->stream>>>(table, p->d_order_start, shift, p->d_meta,
                                                                   p->d_rt_start, rco, ico, coef_stride, V, p->bw, nfun,
-                                                                  m_lo, real_fmt, order_list);
+                                                                  m_lo, real_fmt, order_list, l2_prefetch_cap(PC));
     return cudaGetLastError();
 }
 
@@ -280,11 +301,13 @@ cudaError_t launch_legendre_fwd(s2kit_cuda_plan* p, const double* table, uint64_
     if (m_hi <= m_lo || nfun <= 0) return cudaSuccess;
     int real_fmt = data_format == S2KIT_REAL;
     int nc = pick_nc(p->bw, nfun, real_fmt);
+    if (nc == 8 && nfun * (real_fmt ? 2 : 4) <= 4) nc = 4;  // single field: half-width panel
     int NF = nc / (real_fmt ? 2 : 4);
     int rs = pick_rowsplit(p->bw, (nfun + NF - 1) / NF, m_hi - m_lo);
     int slot = prof_begin(p, S2KIT_K_LEGENDRE_FWD);
     cudaError_t e;
     switch (nc) {
+        case 4: e = leg_fwd_nc<8, 4>(p, table, shift, X, rco, ico, coef_stride, nfun, m_lo, m_hi, real_fmt, rs, order_list); break;
         case 8: e = leg_fwd_nc<8>(p, table, shift, X, rco, ico, coef_stride, nfun, m_lo, m_hi, real_fmt, rs, order_list); break;
         case 16: e = leg_fwd_nc<16>(p, table, shift, X, rco, ico, coef_stride, nfun, m_lo, m_hi, real_fmt, rs, order_list); break;
         default: e = leg_fwd_nc<32>(p, table, shift, X, rco, ico, coef_stride, nfun, m_lo, m_hi, real_fmt, rs, order_list); break;
@@ -299,11 +322,13 @@ cudaError_t launch_legendre_inv(s2kit_cuda_plan* p, const double* table, uint64_
     if (m_hi <= m_lo || nfun <= 0) return cudaSuccess;
     int real_fmt = data_format == S2KIT_REAL;
     int nc = pick_nc(p->bw, nfun, real_fmt);
+    if (nc == 8 && nfun * (real_fmt ? 2 : 4) <= 4) nc = 4;  // single field: half-width panel
     int NF = nc / (real_fmt ? 2 : 4);
     int rs = pick_rowsplit(p->bw, (nfun + NF - 1) / NF, m_hi - m_lo);
     int slot = prof_begin(p, S2KIT_K_LEGENDRE_INV);
     cudaError_t e;
     switch (nc) {
+        case 4: e = leg_inv_nc<8, 4>(p, table, shift, rco, ico, coef_stride, V, nfun, m_lo, m_hi, real_fmt, rs, order_list); break;
         case 8: e = leg_inv_nc<8>(p, table, shift, rco, ico, coef_stride, V, nfun, m_lo, m_hi, real_fmt, rs, order_list); break;
         case 16: e = leg_inv_nc<16>(p, table, shift, rco, ico, coef_stride, V, nfun, m_lo, m_hi, real_fmt, rs, order_list); break;
         default: e = leg_inv_nc<32>(p, table, shift, rco, ico, coef_stride, V, nfun, m_lo, m_hi, real_fmt, rs, order_list); break;

@@ -38,9 +38,11 @@ __host__ __device__ inline int panel_stride(int bw) {
 // one warp): no per-line LSU traffic, and for single large-bw fields it is what keeps HBM busy -- the memory system
 // works through the queued prefetch while the main loop consumes tiles behind it (measured at bw = 2048: 2.5 TB/s
 // with the whole-order prefetch vs 1.3-1.5 TB/s with register prefetch alone or a per-warp look-ahead).
-__device__ __forceinline__ void prefetch_order_l2(const double* base, uint64_t tiles, int tid, int nthreads) {
+__device__ __forceinline__ void prefetch_order_l2(const double* base, uint64_t tiles, int tid, int nthreads,
+                                                  unsigned cap_bytes = 0xffffffffu) {
     (void)nthreads;
     const uint64_t bytes = tiles * 512;
+    if (bytes > cap_bytes) return;
     const uint64_t piece = 256u << 10;
     if (tid < 32)
         for (uint64_t off = (uint64_t)tid * piece; off < bytes; off += 32 * piece) {
@@ -81,7 +83,7 @@ __device__ __forceinline__ int tiles_in_row(const BlockMeta& mb, int rt) {
 // tp: first tile of the row tile (+ 2*lane); xp: panel base of this lane (parity, column g, slot q4).
 template <int NC>
 __device__ __forceinline__ void fwd_row_tile(const double* __restrict__ tp, const double* xp, int CS, int ctn,
-                                             double (&acc)[NC / 8][2]) {
+                                             double (&acc)[NC / 8][2], bool dead_lane = false) {
     // Ring of LEG_PREFETCH tiles in registers.  The refill is UNCONDITIONAL (index clamped to the last tile): a
     // predicated refill made ptxas load into a temporary and copy it into the ring slot right away, which waits
     // for the load and serialises the whole prefetch.
@@ -100,6 +102,7 @@ __device__ __forceinline__ void fwd_row_tile(const double* __restrict__ tp, cons
                 for (int j = 0; j < NC / 8; ++j) {
                     b[j][0] = xp[j * 8 * CS + 8 * ct];
                     b[j][1] = xp[j * 8 * CS + 8 * ct + 4];
+                    if (dead_lane) b[j][0] = b[j][1] = 0.0;  // MMA columns beyond a half-width panel
                 }
                 // k-step outer: consecutive DMMAs go to different accumulators
 #pragma unroll
@@ -118,7 +121,7 @@ __device__ __forceinline__ void fwd_row_tile(const double* __restrict__ tp, cons
 template <int NC>
 __device__ __forceinline__ void inv_col_tile(const double* __restrict__ tbase, const uint32_t* srt, const BlockMeta& mb,
                                              int ct, const double* cp, int CS, int boff0, int boff1,
-                                             double (&acc)[NC / 8][2]) {
+                                             double (&acc)[NC / 8][2], bool dead_lane = false) {
     int rt_min = 0;
     if (8 * ct >= mb.len0 + 7) rt_min = (8 * ct - mb.len0 - 7) / 8 + 1;
     // rows below rt_min never reach ct; from the first row tile that does, all later ones do (lengths grow)
@@ -144,6 +147,7 @@ __device__ __forceinline__ void inv_col_tile(const double* __restrict__ tbase, c
                 for (int j = 0; j < NC / 8; ++j) {
                     a[j][0] = cp[j * 8 * CS + 8 * rt];
                     a[j][1] = cp[j * 8 * CS + 8 * rt + 4];
+                    if (dead_lane) a[j][0] = a[j][1] = 0.0;
                 }
 #pragma unroll
                 for (int j = 0; j < NC / 8; ++j) dmma(acc[j], a[j][0], b0buf[u]);
