@@ -16,6 +16,10 @@
 
 namespace s2k {
 
+// K1 / K6 keep LT transforms in shared memory and read / write them transposed (lanes run over the LT rows first):
+// a double2 row stride == 8/LT (mod 8) makes those 128-bit accesses conflict-free.
+__host__ __device__ constexpr int phi_row_stride(int n, int lt) { return ((fft_padded_len(n) + 7) / 8) * 8 + (8 / lt); }
+
 // ------------------------------------------------------------------------------------------------ K1
 // One CTA transforms LT latitude rows of one function and writes them transposed.
 template <int N, int LT>
@@ -24,10 +28,9 @@ __global__ void __launch_bounds__(N / 8 * LT) k_phi_fft_fwd(const double* __rest
                                                             double* __restrict__ S, double scale, int rows_kept,
                                                             const double2* __restrict__ tw, PlaneView pv) {
     constexpr int T8 = N / 8, NT = T8 * LT;
-    constexpr int RS = ((fft_padded_len(N) + 15) / 16) * 16 + (16 / LT);  // row stride: conflict-free transposed reads
-    extern __shared__ double smem[];
-    double* sre = smem;
-    double* sim = smem + LT * RS;
+    constexpr int RS = phi_row_stride(N, LT);  // double2 row stride: conflict-free transposed reads
+    extern __shared__ double2 smem2[];
+    double2* sx = smem2;
     const int tid = threadIdx.x, jj = tid / T8, t = tid % T8;
     const int j0 = blockIdx.x * LT, f = blockIdx.y;
     const double* rrow = rdata + (long)f * stride + (long)(j0 + jj) * N;
@@ -38,14 +41,11 @@ __global__ void __launch_bounds__(N / 8 * LT) k_phi_fft_fwd(const double* __rest
         xr[e] = __ldg(rrow + t + e * T8);
         xi[e] = __ldg(irow + t + e * T8);
     }
-    fft_block<N>(xr, xi, sre + jj * RS, sim + jj * RS, t, tw);
-    __syncthreads();
+    fft_block<N>(xr, xi, sx + jj * RS, t, jj, tw);
+    fft_sync<N>(jj);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        int p = fft_pad(fft_out_index<N>(e, t));
-        sre[jj * RS + p] = xr[e] * scale;
-        sim[jj * RS + p] = xi[e] * scale;
-    }
+    for (int e = 0; e < 8; ++e)
+        sx[jj * RS + fft_pad(fft_out_index<N>(e, t))] = make_double2(xr[e] * scale, xi[e] * scale);
     __syncthreads();
     double* Sr = S + (long)f * 2 * N * N + j0;
     double* Si = Sr + pv.part_stride;
@@ -54,10 +54,10 @@ __global__ void __launch_bounds__(N / 8 * LT) k_phi_fft_fwd(const double* __rest
         int j2 = flat % LT, mp = flat / LT;
         // REAL format never reads rows >= bw; COMPLEX skips only row bw (rows_kept encodes which)
         if (rows_kept == N ? (mp != N / 2) : (mp < rows_kept)) {
-            int p = fft_pad(mp);
             long at = (pv.rowbase ? pv.rowbase[mp] : (long)mp * N) + j2;
-            Sr[at] = sre[j2 * RS + p];
-            Si[at] = sim[j2 * RS + p];
+            double2 v = sx[j2 * RS + fft_pad(mp)];
+            Sr[at] = v.x;
+            Si[at] = v.y;
         }
     }
 }
@@ -68,10 +68,9 @@ __global__ void __launch_bounds__(N / 8 * LT) k_phi_fft_inv(const double* __rest
                                                             double* __restrict__ idata, long stride, int real_fmt,
                                                             const double2* __restrict__ tw, PlaneView pv) {
     constexpr int T8 = N / 8, NT = T8 * LT;
-    constexpr int RS = ((fft_padded_len(N) + 15) / 16) * 16 + (16 / LT);
-    extern __shared__ double smem[];
-    double* sre = smem;
-    double* sim = smem + LT * RS;
+    constexpr int RS = phi_row_stride(N, LT);
+    extern __shared__ double2 smem2[];
+    double2* sx = smem2;
     const int tid = threadIdx.x, jj = tid / T8, t = tid % T8;
     const int j0 = blockIdx.x * LT, f = blockIdx.y;
     const double* Gr = G + (long)f * 2 * N * N + j0;
@@ -95,20 +94,18 @@ __global__ void __launch_bounds__(N / 8 * LT) k_phi_fft_inv(const double* __rest
         for (int it = 0; it < 8; ++it) {
             int flat = tid + it * NT;
             int j2 = flat % LT, mp = flat / LT;
-            int p = fft_pad(mp);
-            sre[j2 * RS + p] = vi[it];
-            sim[j2 * RS + p] = vr[it];
+            sx[j2 * RS + fft_pad(mp)] = make_double2(vi[it], vr[it]);  // swapped
         }
     }
     __syncthreads();
     double xr[8], xi[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        int p = fft_pad(fft_in_index<N>(e, t));
-        xr[e] = sre[jj * RS + p];
-        xi[e] = sim[jj * RS + p];
+        double2 v = sx[jj * RS + fft_pad(fft_in_index<N>(e, t))];
+        xr[e] = v.x;
+        xi[e] = v.y;
     }
-    fft_block<N>(xr, xi, sre + jj * RS, sim + jj * RS, t, tw);
+    fft_block<N>(xr, xi, sx + jj * RS, t, jj, tw);
     double* rrow = rdata + (long)f * stride + (long)(j0 + jj) * N;
     double* irow = idata + (long)f * stride + (long)(j0 + jj) * N;
 #pragma unroll
@@ -129,10 +126,9 @@ __global__ void __launch_bounds__(N / 8 * FPB) k_dct_fwd(const double* __restric
                                                          const double2* __restrict__ tw,
                                                          const double2* __restrict__ qtab, PlaneView pv) {
     constexpr int T8 = N / 8, B = N / 2, NP = fft_padded_len(N);
-    extern __shared__ double smem[];
+    extern __shared__ double2 smem2[];
     const int tid = threadIdx.x, g = tid / T8, t = tid % T8;
-    double* sre = smem + g * 2 * NP;
-    double* sim = sre + NP;
+    double2* sx = smem2 + g * NP;
     const int ridx = ridx_lo + blockIdx.x * FPB + g, f = blockIdx.y;
     const bool live = ridx < ridx_hi;
     const int rsel = live ? ridx : ridx_lo;
@@ -151,15 +147,11 @@ __global__ void __launch_bounds__(N / 8 * FPB) k_dct_fwd(const double* __restric
         xr[e] = __ldg(Sr + at) * wj;
         xi[e] = __ldg(Si + at) * wj;
     }
-    fft_block<N>(xr, xi, sre, sim, t, tw);
-    __syncthreads();
+    fft_block<N>(xr, xi, sx, t, g, tw);
+    fft_sync<N>(g);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        int p = fft_pad(fft_out_index<N>(e, t));
-        sre[p] = xr[e];
-        sim[p] = xi[e];
-    }
-    __syncthreads();
+    for (int e = 0; e < 8; ++e) sx[fft_pad(fft_out_index<N>(e, t))] = make_double2(xr[e], xi[e]);
+    fft_sync<N>(g);
     if (!live) return;
     double* Xr = X + (((long)f * N + mp) * 2) * B;
     double* Xi = Xr + B;
@@ -172,8 +164,8 @@ __global__ void __launch_bounds__(N / 8 * FPB) k_dct_fwd(const double* __restric
         for (int par = 0; par < 2; ++par) {
             int k = 2 * c + par;
             int nk = (N - k) & (N - 1);
-            double ar = sre[fft_pad(k)], ai = sim[fft_pad(k)];
-            double br = sre[fft_pad(nk)], bi = sim[fft_pad(nk)];
+            const double2 za = sx[fft_pad(k)], zb = sx[fft_pad(nk)];
+            const double ar = za.x, ai = za.y, br = zb.x, bi = zb.y;
             // V1 = (Z[k] + conj Z[n-k]) / 2 ; V2 = (Z[k] - conj Z[n-k]) / 2i ; REDFT10 = 2 Re(e^{-i pi k/2n} V)
             double2 q = __ldg(qtab + k);
             double y1 = q.x * (ar + br) + q.y * (ai - bi);
@@ -195,10 +187,9 @@ __global__ void __launch_bounds__(N / 8 * FPB) k_dct_inv(const double* __restric
                                                          double out_scale, const double2* __restrict__ tw,
                                                          const double2* __restrict__ qtab, PlaneView pv) {
     constexpr int T8 = N / 8, B = N / 2, NP = fft_padded_len(N);
-    extern __shared__ double smem[];
+    extern __shared__ double2 smem2[];
     const int tid = threadIdx.x, g = tid / T8, t = tid % T8;
-    double* sre = smem + g * 2 * NP;
-    double* sim = sre + NP;
+    double2* sx = smem2 + g * NP;
     const int ridx = ridx_lo + blockIdx.x * FPB + g, f = blockIdx.y;
     const bool live = ridx < ridx_hi;
     const int rsel = live ? ridx : ridx_lo;
@@ -226,7 +217,7 @@ __global__ void __launch_bounds__(N / 8 * FPB) k_dct_inv(const double* __restric
         xr[e] = wi;  // swapped: inverse DFT through the forward transform
         xi[e] = wr;
     }
-    fft_block<N>(xr, xi, sre, sim, t, tw);
+    fft_block<N>(xr, xi, sx, t, g, tw);
     if (!live) return;
     double sign = ((mp > B) && (m & 1)) ? -out_scale : out_scale;  // (-1)^m for negative orders
     double* Gr = G + (long)f * 2 * N * N + (long)(pv.rowlist ? rsel : mp) * pv.lrow_stride;
@@ -334,8 +325,8 @@ template <int N>
 static cudaError_t phi_fwd_n(s2kit_cuda_plan* p, const double* rdata, const double* idata, long stride, double* S,
                              int nfun, int rows_kept, const PlaneView& pv, int nrings) {
     constexpr int LT = (4096 / N) < 8 ? (4096 / N) : 8;
-    constexpr int RS = ((fft_padded_len(N) + 15) / 16) * 16 + (16 / LT);
-    size_t smem = sizeof(double) * 2 * LT * RS;
+    constexpr int RS = phi_row_stride(N, LT);
+    size_t smem = sizeof(double2) * LT * RS;
     cudaError_t e = set_smem(k_phi_fft_fwd<N, LT>, smem);
     if (e != cudaSuccess) return e;
     double scale = sqrt(2.0 * M_PI) / (double)N;  // FST_semi_memo.c:86
@@ -349,8 +340,8 @@ template <int N>
 static cudaError_t phi_inv_n(s2kit_cuda_plan* p, const double* G, double* rdata, double* idata, long stride, int nfun,
                              int real_fmt, const PlaneView& pv, int nrings) {
     constexpr int LT = (4096 / N) < 8 ? (4096 / N) : 8;
-    constexpr int RS = ((fft_padded_len(N) + 15) / 16) * 16 + (16 / LT);
-    size_t smem = sizeof(double) * 2 * LT * RS;
+    constexpr int RS = phi_row_stride(N, LT);
+    size_t smem = sizeof(double2) * LT * RS;
     cudaError_t e = set_smem(k_phi_fft_inv<N, LT>, smem);
     if (e != cudaSuccess) return e;
     if (nrings % LT) return cudaErrorInvalidValue;
@@ -364,7 +355,7 @@ static cudaError_t dct_fwd_n(s2kit_cuda_plan* p, const double* S, double* X, int
                              const PlaneView& pv) {
     constexpr int T8 = N / 8;
     constexpr int FPB = (256 / T8) < 1 ? 1 : ((256 / T8) > 8 ? 8 : (256 / T8));
-    size_t smem = sizeof(double) * 2 * FPB * fft_padded_len(N);
+    size_t smem = sizeof(double2) * FPB * fft_padded_len(N);
     cudaError_t e = set_smem(k_dct_fwd<N, FPB>, smem);
     if (e != cudaSuccess) return e;
     k_dct_fwd<N, FPB><<<dim3((hi - lo + FPB - 1) / FPB, nfun), T8 * FPB, smem, p->stream>>>(
@@ -377,7 +368,7 @@ static cudaError_t dct_inv_n(s2kit_cuda_plan* p, const double* V, double* G, int
                              const PlaneView& pv) {
     constexpr int T8 = N / 8;
     constexpr int FPB = (256 / T8) < 1 ? 1 : ((256 / T8) > 8 ? 8 : (256 / T8));
-    size_t smem = sizeof(double) * 2 * FPB * fft_padded_len(N);
+    size_t smem = sizeof(double2) * FPB * fft_padded_len(N);
     cudaError_t e = set_smem(k_dct_inv<N, FPB>, smem);
     if (e != cudaSuccess) return e;
     double out_scale = 1.0 / sqrt(2.0 * M_PI);  // FST_semi_memo.c:344

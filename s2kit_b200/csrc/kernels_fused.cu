@@ -35,8 +35,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_fwd(
     const int NF = NC / cols_per_fn;
     const int f0 = blockIdx.x * NF;
     double* Xs = smem;                                   // [2][NC][CS]  MMA B-operand panel
-    double* ex = smem + 2 * NC * CS;                     // [G][2][NP]   FFT exchange rows
-    uint32_t* srt = reinterpret_cast<uint32_t*>(ex + G * 2 * NP);
+    double2* ex = reinterpret_cast<double2*>(smem + 2 * NC * CS);  // [G][NP] FFT exchange rows
+    uint32_t* srt = reinterpret_cast<uint32_t*>(ex + G * NP);
 
     prefetch_order_l2(table + (order_start[m] - table_shift) * 64, order_start[m + 1] - order_start[m], tid, FUSED_THREADS);
     const BlockMeta mb0 = meta[2 * m], mb1 = meta[2 * m + 1];
@@ -52,8 +52,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_fwd(
 
     // ---- DCT rounds: G transforms at a time
     const int g = tid / T8, t = tid % T8;
-    double* sre = ex + g * 2 * NP;
-    double* sim = sre + NP;
+    double2* sx = ex + g * NP;
     const double* w = weights + ((m & 1) ? N : 0);
     const double s_all = 1.0 / sqrt(2.0 * (double)N);  // seminaive.c:174
 #pragma unroll 1
@@ -79,20 +78,16 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_fwd(
 #pragma unroll
             for (int e = 0; e < 8; ++e) xr[e] = xi[e] = 0.0;
         }
-        fft_block<N>(xr, xi, sre, sim, t, tw);
-        __syncthreads();
+        fft_block<N>(xr, xi, sx, t, g, tw);
+        fft_sync<N>(g);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            int p = fft_pad(fft_out_index<N>(e, t));
-            sre[p] = xr[e];
-            sim[p] = xi[e];
-        }
-        __syncthreads();
+        for (int e = 0; e < 8; ++e) sx[fft_pad(fft_out_index<N>(e, t))] = make_double2(xr[e], xi[e]);
+        fft_sync<N>(g);
         double* x_re = Xs + (2 * q) * CS;  // parity 0 block; parity 1 block is NC*CS further
         for (int k = t; k < B; k += T8) {
             int nk = (N - k) & (N - 1);
-            double ar = sre[fft_pad(k)], ai = sim[fft_pad(k)];
-            double br = sre[fft_pad(nk)], bi = sim[fft_pad(nk)];
+            const double2 za = sx[fft_pad(k)], zb = sx[fft_pad(nk)];
+            const double ar = za.x, ai = za.y, br = zb.x, bi = zb.y;
             double2 qq = __ldg(qtab + k);
             double y1 = qq.x * (ar + br) + qq.y * (ai - bi);
             double y2 = qq.x * (ai + bi) - qq.y * (ar - br);
@@ -104,7 +99,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_fwd(
             dst[0] = y1 * s_all;
             dst[CS] = y2 * s_all;
         }
-        // the next round's fft_block synchronises before it overwrites the exchange rows
+        // the next round's fft_block synchronises (per transform) before it overwrites the exchange row
     }
     __syncthreads();
 
@@ -177,8 +172,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_inv(
     const int NF = NC / cols_per_fn;
     const int f0 = blockIdx.x * NF;
     double* Cs = smem;                 // [2][NC][CS] coefficient panel, later [NC][VS] cosine-domain panel
-    double* ex = smem + 2 * NC * CS;   // [G][2][NP]
-    uint32_t* srt = reinterpret_cast<uint32_t*>(ex + G * 2 * NP);
+    double2* ex = reinterpret_cast<double2*>(smem + 2 * NC * CS);  // [G][NP]
+    uint32_t* srt = reinterpret_cast<uint32_t*>(ex + G * NP);
     static_assert(NC * VS <= 2 * NC * (B / 2 + 4), "result panel must fit in the coefficient panel");
 
     prefetch_order_l2(table + (order_start[m] - table_shift) * 64, order_start[m + 1] - order_start[m], tid, FUSED_THREADS);
@@ -241,8 +236,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_inv(
 
     // ---- DCT-III rounds (same arithmetic as k_dct_inv)
     const int g = tid / T8, t = tid % T8;
-    double* sre = ex + g * 2 * NP;
-    double* sim = sre + NP;
+    double2* sx = ex + g * NP;
     const double c_rest = 1.0 / sqrt(2.0 * (double)N);  // 0.5/sqrt(bw), seminaive.c:72
     const double c_zero = 1.0 / sqrt((double)N);        // seminaive.c:98
 #pragma unroll 1
@@ -271,7 +265,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_inv(
             xr[e] = wi;
             xi[e] = wr;
         }
-        fft_block<N>(xr, xi, sre, sim, t, tw);
+        fft_block<N>(xr, xi, sx, t, g, tw);
         if (live) {
             double sign = (sgn && (m & 1)) ? -out_scale : out_scale;  // (-1)^m for negative orders
             double* Gr = Gout + ((long)f * 2 * N + mp) * N;

@@ -18,6 +18,13 @@
 
 namespace s2k {
 
+// destination of one panel column in the epilogues
+struct ColOut {
+    double* dst;     // element (l = m) of the column's output run, nullptr = dead column
+    double* mirror;  // K3, REAL format: the (-m) copy
+    double scale, mscale;
+};
+
 // ------------------------------------------------------------------------------------------------ K3
 // grid: x = column tile, y = order (heavy orders first), z = row split.  NC = MMA columns per CTA (multiple of 8),
 // PC = columns actually stored in the panel: PC = 4 < NC = 8 is the single-field case (re/im x +-m), where the
@@ -28,7 +35,7 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_fwd(
     const double* __restrict__ table, const uint64_t* __restrict__ order_start, uint64_t table_shift,
     const BlockMeta* __restrict__ meta, const uint32_t* __restrict__ rt_start, const double* __restrict__ X,
     double* __restrict__ rco, double* __restrict__ ico, long coef_stride, int bw, int nfun, int m_lo, int real_fmt,
-    const int* __restrict__ order_list, unsigned l2pf_cap) {
+    const int* __restrict__ order_list, unsigned l2pf_cap, int experiment) {
     extern __shared__ double smem[];
     const int n = 2 * bw, CS = panel_stride(bw);
     const int m = order_list ? order_list[blockIdx.y] : m_lo + blockIdx.y;
@@ -54,6 +61,7 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_fwd(
         }
         int mp = sgn ? n - m : m;
         const double* src = X + (((long)f * n + mp) * 2 + part) * bw;
+        if (experiment == 3) continue;  // TIMING EXPERIMENT ONLY: no panel staging
         // the plane stores even cosine indices first, then odd ones (cos_slot): two contiguous runs per column
         if ((bw & 3) == 0) {
             for (int c = 2 * lane; c < half; c += 64) {
@@ -73,14 +81,33 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_fwd(
     const BlockMeta mb0 = meta[2 * m], mb1 = meta[2 * m + 1];
     const int total = mb0.nrt + mb1.nrt;
     uint32_t* srt = reinterpret_cast<uint32_t*>(Xs + 2 * PC * CS);  // row-tile starts of both parity blocks
+    ColOut* cinfo = reinterpret_cast<ColOut*>(srt + ((bw / 8 + 8 + 3) & ~3));
+    if (tid < NC) {
+        // where column `tid` of the panel lands: f^(+-m, l) of function f, re or im array, with its sign
+        ColOut co = {nullptr, nullptr, 1.0, 1.0};
+        const int fl = tid / cols_per_fn, sub = tid % cols_per_fn, f = f0 + fl;
+        if (tid < PC && f < nfun) {
+            const int part = sub & 1, sgn = real_fmt ? 0 : (sub >> 1);
+            double* arr = (part ? ico : rco) + (long)f * coef_stride;
+            const double sneg = (m & 1) ? -1.0 : 1.0;
+            if (!sgn) {
+                co.dst = arr + coef_base(m, bw);
+                if (real_fmt && m > 0) {  // f^(-m,l) = (-1)^m conj f^(m,l)   (FST_semi_memo.c:131-145)
+                    co.mirror = arr + coef_base(-m, bw);
+                    co.mscale = part ? -sneg : sneg;
+                }
+            } else if (m > 0) {  // (-1)^m' on the negative orders  (FST_semi_memo.c:181-186)
+                co.dst = arr + coef_base(-m, bw);
+                co.scale = sneg;
+            }
+        }
+        cinfo[tid] = co;
+    }
     for (int i = tid; i < total; i += blockDim.x)
         srt[i] = rt_start[(i < mb0.nrt ? mb0.rt_base : mb1.rt_base - mb0.nrt) + i];
     __syncthreads();
     const double* tbase = table + (order_start[m] - table_shift) * 64 + lane * 2;
     const int g = lane >> 2, q4 = lane & 3;
-    const double sgn_neg = (m & 1) ? -1.0 : 1.0;
-    const int base_pos = coef_base(m, bw), base_neg = coef_base(-m, bw);
-
     // items sorted by decreasing cost: (parity 0, rt), (parity 1, rt) for rt = nrt-1 .. 0; snake over the slots
     const int nslots = LEG_WARPS * gridDim.z, slot = blockIdx.z * LEG_WARPS + warp;
     for (int round = 0;; ++round) {
@@ -97,9 +124,14 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_fwd(
         double acc[NC / 8][2];
 #pragma unroll
         for (int j = 0; j < NC / 8; ++j) acc[j][0] = acc[j][1] = 0.0;
-        fwd_row_tile<NC>(tp, xp, CS, ctn, acc, PC < NC && g >= PC);
+        fwd_row_tile<NC>(tp, xp, CS, ctn, acc, PC < NC && g >= PC, experiment == 1);
+        if (experiment == 2) {  // TIMING EXPERIMENT ONLY: no epilogue stores
+            if (acc[0][0] == 1.2345e300) rco[0] = 1.0;
+            continue;
+        }
 
-        // ---- epilogue: lane holds rows r = 8rt + g, columns 8j + 2 q4 + {0,1}
+        // ---- epilogue: lane holds rows r = 8rt + g, columns 8j + 2 q4 + {0,1}; destinations come from the
+        // per-column table built once per CTA (the index arithmetic used to cost as many instructions as the main loop)
         const int r = 8 * rt + g;
         if (r < mb.rows) {
             const int off = p + 2 * r;  // l - m
@@ -107,26 +139,10 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_fwd(
             for (int j = 0; j < NC / 8; ++j) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    int col = 8 * j + 2 * q4 + e;
-                    int fl = col / cols_per_fn, sub = col % cols_per_fn;
-                    int f = f0 + fl;
-                    if (f >= nfun || col >= PC) continue;
-                    double v = acc[j][e];
-                    if (real_fmt) {
-                        int part = sub & 1;
-                        double* dst = (part ? ico : rco) + (long)f * coef_stride;
-                        dst[base_pos + off] = v;
-                        // f^(-m,l) = (-1)^m conj f^(m,l)   (FST_semi_memo.c:131-145)
-                        if (m > 0) dst[base_neg + off] = part ? -sgn_neg * v : sgn_neg * v;
-                    } else {
-                        int sgn = sub >> 1, part = sub & 1;
-                        if (sgn && m == 0) continue;
-                        double* dst = (part ? ico : rco) + (long)f * coef_stride;
-                        if (sgn)
-                            dst[base_neg + off] = sgn_neg * v;  // (-1)^m'  (FST_semi_memo.c:181-186)
-                        else
-                            dst[base_pos + off] = v;
-                    }
+                    const ColOut co = cinfo[8 * j + 2 * q4 + e];
+                    const double v = acc[j][e];
+                    if (co.dst) co.dst[off] = v * co.scale;
+                    if (co.mirror) co.mirror[off] = v * co.mscale;
                 }
             }
         }
@@ -175,6 +191,15 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_inv(
     const BlockMeta mb0 = meta[2 * m], mb1 = meta[2 * m + 1];
     const int nct = (((bw + 1) / 2) + 7) >> 3;  // column tiles needed to cover every k < bw of one parity
     uint32_t* srt = reinterpret_cast<uint32_t*>(Cs + 2 * PC * CS);
+    ColOut* cinfo = reinterpret_cast<ColOut*>(srt + ((bw / 8 + 8 + 3) & ~3));
+    if (tid < NC) {
+        ColOut co = {nullptr, nullptr, 1.0, 1.0};
+        const int fl = tid / cols_per_fn, sub = tid % cols_per_fn, f = f0 + fl;
+        const int sgn = real_fmt ? 0 : (sub >> 1), part = sub & 1;
+        if (tid < PC && f < nfun && !(sgn && m == 0))
+            co.dst = V + (((long)f * n + (sgn ? n - m : m)) * 2 + part) * bw;  // row of the cosine plane
+        cinfo[tid] = co;
+    }
     for (int i = tid; i < mb0.nrt + mb1.nrt; i += blockDim.x)
         srt[i] = rt_start[(i < mb0.nrt ? mb0.rt_base : mb1.rt_base - mb0.nrt) + i];
     __syncthreads();
@@ -196,17 +221,12 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_inv(
                          Cs + (p * PC + (PC < NC ? (g & (PC - 1)) : g)) * CS + q4, CS, boff0, boff1, acc,
                          PC < NC && g >= PC);
         // ---- epilogue: lane holds column 8j + g, cosine slots c = 8ct + 2 q4 + {0,1}
+        // slots c0, c0+1 of parity p are adjacent in the parity-split plane
+        const int c0 = 8 * ct + 2 * q4, hp = p ? bw / 2 : (bw + 1) / 2;
 #pragma unroll
         for (int j = 0; j < NC / 8; ++j) {
-            int col = 8 * j + g;
-            int fl = col / cols_per_fn, sub = col % cols_per_fn;
-            int sgn = real_fmt ? 0 : (sub >> 1), part = sub & 1;
-            int f = f0 + fl;
-            if (f >= nfun || col >= PC || (sgn && m == 0)) continue;
-            int mp = sgn ? n - m : m;
-            double* dst = V + (((long)f * n + mp) * 2 + part) * bw;
-            // slots c = 8ct + 2 q4 + {0,1} of parity p are adjacent in the parity-split plane
-            const int c0 = 8 * ct + 2 * q4, hp = p ? bw / 2 : (bw + 1) / 2;
+            double* dst = cinfo[8 * j + g].dst;
+            if (!dst) continue;
             double* d = dst + p * ((bw + 1) / 2) + c0;
             if (c0 + 1 < hp && ((bw & 3) == 0)) {
                 *reinterpret_cast<double2*>(d) = make_double2(acc[j][0], acc[j][1]);
@@ -239,7 +259,8 @@ static cudaError_t leg_fwd_nc(s2kit_cuda_plan* p, const double* table, uint64_t 
                               const int* order_list) {
     int cols_per_fn = real_fmt ? 2 : 4;
     int NF = PC / cols_per_fn;
-    size_t smem = sizeof(double) * 2 * PC * panel_stride(p->bw) + sizeof(uint32_t) * (p->bw / 8 + 8);
+    size_t smem = sizeof(double) * 2 * PC * panel_stride(p->bw) + sizeof(uint32_t) * ((p->bw / 8 + 8 + 3) & ~3) +
+                  sizeof(ColOut) * NC;
     if (smem > 48 * 1024) {
         cudaError_t e = ensure_smem(reinterpret_cast<const void*>(k_legendre_fwd<NC, PC>), smem);
         if (e != cudaSuccess) return e;
@@ -247,7 +268,7 @@ static cudaError_t leg_fwd_nc(s2kit_cuda_plan* p, const double* table, uint64_t 
     dim3 grid((nfun + NF - 1) / NF, m_hi - m_lo, rowsplit);
     k_legendre_fwd<NC, PC><<<grid, LEG_WARPS * 32, smem, p->stream>>>(table, p->d_order_start, shift, p->d_meta,
                                                                   p->d_rt_start, X, rco, ico, coef_stride, p->bw, nfun,
-                                                                  m_lo, real_fmt, order_list, l2_prefetch_cap(PC));
+                                                                  m_lo, real_fmt, order_list, l2_prefetch_cap(PC), getenv("S2K_EXPERIMENT") ? atoi(getenv("S2K_EXPERIMENT")) : 0);
     return cudaGetLastError();
 }
 
@@ -257,7 +278,8 @@ static cudaError_t leg_inv_nc(s2kit_cuda_plan* p, const double* table, uint64_t 
                               int real_fmt, int rowsplit, const int* order_list) {
     int cols_per_fn = real_fmt ? 2 : 4;
     int NF = PC / cols_per_fn;
-    size_t smem = sizeof(double) * 2 * PC * panel_stride(p->bw) + sizeof(uint32_t) * (p->bw / 8 + 8);
+    size_t smem = sizeof(double) * 2 * PC * panel_stride(p->bw) + sizeof(uint32_t) * ((p->bw / 8 + 8 + 3) & ~3) +
+                  sizeof(ColOut) * NC;
     if (smem > 48 * 1024) {
         cudaError_t e = ensure_smem(reinterpret_cast<const void*>(k_legendre_inv<NC, PC>), smem);
         if (e != cudaSuccess) return e;

@@ -47,10 +47,9 @@ __global__ void __launch_bounds__(NB / 8 * G) k_table_gen(double* __restrict__ t
                                                           const double2* __restrict__ tw,
                                                           const double2* __restrict__ qtab) {
     constexpr int T8 = NB / 8, NP = fft_padded_len(NB);
-    extern __shared__ double smem[];
+    extern __shared__ double2 smem2[];
     const int tid = threadIdx.x, g = tid / T8, t = tid % T8;
-    double* sre = smem + g * 2 * NP;
-    double* sim = sre + NP;
+    double2* sx = smem2 + g * NP;
     int u = unit_lo + blockIdx.x * G + g;
     const bool live = u < unit_hi;
     if (!live) u = unit_lo;
@@ -81,15 +80,11 @@ __global__ void __launch_bounds__(NB / 8 * G) k_table_gen(double* __restrict__ t
         for (int e = 0; e < 8; ++e) xi[e] = (l + 1 < NB) ? cur[e] : 0.0;
         if (l + 2 < NB) rec_step(x, prev, cur, __ldg(rc + l + 1));
 
-        fft_block<NB>(xr, xi, sre, sim, t, tw);
-        __syncthreads();
+        fft_block<NB>(xr, xi, sx, t, g, tw);
+        fft_sync<NB>(g);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            int p = fft_pad(fft_out_index<NB>(e, t));
-            sre[p] = xr[e];
-            sim[p] = xi[e];
-        }
-        __syncthreads();
+        for (int e = 0; e < 8; ++e) sx[fft_pad(fft_out_index<NB>(e, t))] = make_double2(xr[e], xi[e]);
+        fft_sync<NB>(g);
         if (live && l < NB) {
             // degree l keeps cosine indices of parity 0 (l0 - m is even), degree l+1 those of parity 1
             const int ra = (l - m) >> 1;  // row inside either parity block
@@ -99,8 +94,8 @@ __global__ void __launch_bounds__(NB / 8 * G) k_table_gen(double* __restrict__ t
                 const BlockMeta& mb = pk ? mb1 : mb0;
                 if (c >= mb.len0 + ra) continue;
                 int nk = (NB - k) & (NB - 1);
-                double ar = sre[fft_pad(k)], ai = sim[fft_pad(k)];
-                double br = sre[fft_pad(nk)], bi = sim[fft_pad(nk)];
+                const double2 za = sx[fft_pad(k)], zb = sx[fft_pad(nk)];
+                const double ar = za.x, ai = za.y, br = zb.x, bi = zb.y;
                 double2 q = __ldg(qtab + k);
                 double y = pk ? (q.x * (ai + bi) - q.y * (ar - br)) : (q.x * (ar + br) + q.y * (ai - bi));
                 if (k == 0) y *= 0.70710678118654752440;  // cospml.c:205
@@ -201,7 +196,7 @@ template <int NB>
 static cudaError_t table_gen_nb(s2kit_cuda_plan* p, double* table, uint64_t shift, int unit_lo, int unit_hi, int lch) {
     constexpr int T8 = NB / 8;
     constexpr int G = (256 / T8) < 1 ? 1 : ((256 / T8) > 8 ? 8 : (256 / T8));
-    size_t smem = sizeof(double) * 2 * G * fft_padded_len(NB);
+    size_t smem = sizeof(double2) * G * fft_padded_len(NB);
     if (smem > 48 * 1024) {
         cudaError_t e =
             ensure_smem(reinterpret_cast<const void*>(k_table_gen<NB, G>), smem);

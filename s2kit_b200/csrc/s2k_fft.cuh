@@ -8,16 +8,30 @@
 // final radix-2/4 pass when log2 N is not a multiple of 3), so the result comes out in natural order and
 // the first pass reads / the last pass leaves the SAME eight slots {t + s*N/8}: the first pass can be fed
 // straight from global memory and the last pass can be consumed straight from registers.  Between
-// passes the points are exchanged through shared memory (split re/im arrays, index padded by i>>4, which
-// keeps the 64-bit accesses of all passes within 1.25x of conflict-free).  The base twiddle of each butterfly
+// passes the points are exchanged through shared memory as interleaved double2 (128-bit accesses: half the LSU
+// instructions of split re/im arrays), index padded by i>>3, which keeps every pass within 1.08x of conflict-free.
+// The threads of one transform synchronise on their own named barrier when they are whole warps.  The base twiddle of each butterfly
 // comes from a host-computed exact table W[q] = (cos 2 pi q/N, -sin 2 pi q/N).
 #pragma once
 #include <cuda_runtime.h>
 
 namespace s2k {
 
-__host__ __device__ constexpr int fft_pad(int i) { return i + (i >> 4); }
-__host__ __device__ constexpr int fft_padded_len(int n) { return n + (n >> 4) + 1; }
+// shared-memory exchange rows hold double2 elements; index padding for 128-bit accesses (8 lanes per wavefront)
+__host__ __device__ constexpr int fft_pad(int i) { return i + (i >> 3); }
+__host__ __device__ constexpr int fft_padded_len(int n) { return n + (n >> 3) + 1; }
+
+// barrier among the N/8 threads of transform `group` of the CTA (named barrier 1 + group when they are whole
+// warps, the CTA-wide barrier otherwise -- then every thread of the CTA must take part)
+template <int N>
+__device__ __forceinline__ void fft_sync(int group) {
+    if constexpr (N / 8 >= 32) {
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "n"(N / 8) : "memory");
+    } else {
+        (void)group;
+        __syncthreads();
+    }
+}
 
 __host__ __device__ constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n >> 1); }
 // last-pass radix: 8 if log2 N % 3 == 0, else 2 or 4
@@ -125,8 +139,7 @@ __device__ __forceinline__ void fft_pass_compute(double (&xr)[8], double (&xi)[8
 }
 
 template <int N, int NS, int R>
-__device__ __forceinline__ void fft_pass_write(const double (&xr)[8], const double (&xi)[8], double* sre,
-                                               double* sim, int t) {
+__device__ __forceinline__ void fft_pass_write(const double (&xr)[8], const double (&xi)[8], double2* sx, int t) {
     constexpr int T8 = N / 8, NB = 8 / R;
 #pragma unroll
     for (int q = 0; q < NB; ++q) {
@@ -135,57 +148,55 @@ __device__ __forceinline__ void fft_pass_write(const double (&xr)[8], const doub
         int base = (j - k) * R + k;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            int p = fft_pad(base + r * NS);
-            sre[p] = xr[q * R + r];
-            sim[p] = xi[q * R + r];
+            sx[fft_pad(base + r * NS)] = make_double2(xr[q * R + r], xi[q * R + r]);
         }
     }
 }
 
 template <int N, int R>
-__device__ __forceinline__ void fft_pass_read(double (&xr)[8], double (&xi)[8], const double* sre,
-                                              const double* sim, int t) {
+__device__ __forceinline__ void fft_pass_read(double (&xr)[8], double (&xi)[8], const double2* sx, int t) {
     constexpr int T8 = N / 8;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        int p = fft_pad(t + fft_slot<R>(e) * T8);
-        xr[e] = sre[p];
-        xi[e] = sim[p];
+        double2 v = sx[fft_pad(t + fft_slot<R>(e) * T8)];
+        xr[e] = v.x;
+        xi[e] = v.y;
     }
 }
 
 template <int N, int NS, int LEFT>
 struct FftRest {
     // LEFT = number of radix-8 passes still to run after the first one
-    __device__ static __forceinline__ void run(double (&xr)[8], double (&xi)[8], double* sre, double* sim, int t,
+    __device__ static __forceinline__ void run(double (&xr)[8], double (&xi)[8], double2* sx, int t, int group,
                                                const double2* __restrict__ tw) {
         if constexpr (LEFT > 0) {
-            __syncthreads();
-            fft_pass_write<N, NS / 8, 8>(xr, xi, sre, sim, t);
-            __syncthreads();
-            fft_pass_read<N, 8>(xr, xi, sre, sim, t);
+            fft_sync<N>(group);
+            fft_pass_write<N, NS / 8, 8>(xr, xi, sx, t);
+            fft_sync<N>(group);
+            fft_pass_read<N, 8>(xr, xi, sx, t);
             fft_pass_compute<N, NS, 8>(xr, xi, t, tw);
-            FftRest<N, NS * 8, LEFT - 1>::run(xr, xi, sre, sim, t, tw);
+            FftRest<N, NS * 8, LEFT - 1>::run(xr, xi, sx, t, group, tw);
         } else if constexpr (NS < N) {
             constexpr int R = N / NS;  // 2 or 4
-            __syncthreads();
-            fft_pass_write<N, NS / 8, 8>(xr, xi, sre, sim, t);
-            __syncthreads();
-            fft_pass_read<N, R>(xr, xi, sre, sim, t);
+            fft_sync<N>(group);
+            fft_pass_write<N, NS / 8, 8>(xr, xi, sx, t);
+            fft_sync<N>(group);
+            fft_pass_read<N, R>(xr, xi, sx, t);
             fft_pass_compute<N, NS, R>(xr, xi, t, tw);
         }
     }
 };
 
 // Forward DFT of N points spread over N/8 threads.  On entry register e holds x[t + e*N/8]; on exit it
-// holds X[fft_out_index<N>(e, t)].  sre/sim: this transform's padded exchange rows (fft_padded_len(N)
-// doubles each).  Calls __syncthreads(): every thread of the CTA must call it the same number of times.
+// holds X[fft_out_index<N>(e, t)].  sx: this transform's padded exchange row (fft_padded_len(N) double2).
+// Synchronises with fft_sync<N>(group): all N/8 threads of the transform must call it (for N < 256 every thread
+// of the CTA, the same number of times).
 template <int N>
-__device__ __forceinline__ void fft_block(double (&xr)[8], double (&xi)[8], double* sre, double* sim, int t,
+__device__ __forceinline__ void fft_block(double (&xr)[8], double (&xi)[8], double2* sx, int t, int group,
                                           const double2* __restrict__ tw) {
     static_assert(N >= 8 && (N & (N - 1)) == 0, "power of two >= 8");
     fft_pass_compute<N, 1, 8>(xr, xi, t, tw);
-    FftRest<N, 8, fft_num_r8(N) - 1>::run(xr, xi, sre, sim, t, tw);
+    FftRest<N, 8, fft_num_r8(N) - 1>::run(xr, xi, sx, t, group, tw);
 }
 
 }  // namespace s2k
