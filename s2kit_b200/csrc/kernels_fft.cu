@@ -20,6 +20,11 @@ namespace s2k {
 // a double2 row stride == 8/LT (mod 8) makes those 128-bit accesses conflict-free.
 __host__ __device__ constexpr int phi_row_stride(int n, int lt) { return ((fft_padded_len(n) + 7) / 8) * 8 + (8 / lt); }
 
+__device__ __forceinline__ void cp_async8_g2s(double* smem_dst, const double* gsrc) {
+    unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(a), "l"(gsrc));
+}
+
 // ------------------------------------------------------------------------------------------------ K1
 // One CTA transforms LT latitude rows of one function and writes them transposed.
 template <int N, int LT>
@@ -76,33 +81,30 @@ __global__ void __launch_bounds__(N / 8 * LT) k_phi_fft_inv(const double* __rest
     const double* Gr = G + (long)f * 2 * N * N + j0;
     const double* Gi = Gr + pv.part_stride;
     // inverse DFT through the forward one: feed (im, re), read back (im, re)   (FST_semi_memo.c:350)
-    // N*LT elements per part and NT = N/8*LT threads: exactly 8 per thread, all loads issued before any use
-    {
-        double vr[8], vi[8];
+    // The transposed gather (runs of LT doubles per order row) goes straight into shared memory with 8-byte
+    // cp.async: all N*LT*2 copies of the CTA are in flight at once and no registers wait on them.
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            int flat = tid + it * NT;
-            int j2 = flat % LT, mp = flat / LT;
+    for (int it = 0; it < 8; ++it) {
+        int flat = tid + it * NT;
+        int j2 = flat % LT, mp = flat / LT;
+        double2* dst = sx + j2 * RS + fft_pad(mp);
+        if (mp == N / 2) {
+            *dst = make_double2(0.0, 0.0);  // row bw is zero by definition (FST_semi_memo.c:283-284)
+        } else {
             int row = (real_fmt && mp > N / 2) ? N - mp : mp;  // conjugate mirror of row n - m' (FST_semi_memo.c:333-341)
-            bool dead = (mp == N / 2);
             long at = (pv.rowbase ? pv.rowbase[row] : (long)row * N) + j2;
-            vr[it] = dead ? 0.0 : __ldg(Gr + at);
-            vi[it] = dead ? 0.0 : __ldg(Gi + at);
-            if (real_fmt && mp > N / 2) vi[it] = -vi[it];
-        }
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            int flat = tid + it * NT;
-            int j2 = flat % LT, mp = flat / LT;
-            sx[j2 * RS + fft_pad(mp)] = make_double2(vi[it], vr[it]);  // swapped
+            cp_async8_g2s(&dst->y, Gr + at);  // real part -> imaginary slot (swap)
+            cp_async8_g2s(&dst->x, Gi + at);  // imaginary part -> real slot; the mirror's sign flip happens on read
         }
     }
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     double xr[8], xi[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        double2 v = sx[jj * RS + fft_pad(fft_in_index<N>(e, t))];
-        xr[e] = v.x;
+        int idx = fft_in_index<N>(e, t);
+        double2 v = sx[jj * RS + fft_pad(idx)];
+        xr[e] = (real_fmt && idx > N / 2) ? -v.x : v.x;
         xi[e] = v.y;
     }
     fft_block<N>(xr, xi, sx + jj * RS, t, jj, tw);

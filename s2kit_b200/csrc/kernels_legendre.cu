@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_fwd(
     const double* __restrict__ table, const uint64_t* __restrict__ order_start, uint64_t table_shift,
     const BlockMeta* __restrict__ meta, const uint32_t* __restrict__ rt_start, const double* __restrict__ X,
     double* __restrict__ rco, double* __restrict__ ico, long coef_stride, int bw, int nfun, int m_lo, int real_fmt,
-    const int* __restrict__ order_list, unsigned l2pf_cap, int experiment) {
+    const int* __restrict__ order_list, unsigned l2pf_cap) {
     extern __shared__ double smem[];
     const int n = 2 * bw, CS = panel_stride(bw);
     const int m = order_list ? order_list[blockIdx.y] : m_lo + blockIdx.y;
@@ -61,7 +61,6 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_fwd(
         }
         int mp = sgn ? n - m : m;
         const double* src = X + (((long)f * n + mp) * 2 + part) * bw;
-        if (experiment == 3) continue;  // TIMING EXPERIMENT ONLY: no panel staging
         // the plane stores even cosine indices first, then odd ones (cos_slot): two contiguous runs per column
         if ((bw & 3) == 0) {
             for (int c = 2 * lane; c < half; c += 64) {
@@ -124,11 +123,7 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_fwd(
         double acc[NC / 8][2];
 #pragma unroll
         for (int j = 0; j < NC / 8; ++j) acc[j][0] = acc[j][1] = 0.0;
-        fwd_row_tile<NC>(tp, xp, CS, ctn, acc, PC < NC && g >= PC, experiment == 1);
-        if (experiment == 2) {  // TIMING EXPERIMENT ONLY: no epilogue stores
-            if (acc[0][0] == 1.2345e300) rco[0] = 1.0;
-            continue;
-        }
+        fwd_row_tile<NC>(tp, xp, CS, ctn, acc, PC < NC && g >= PC);
 
         // ---- epilogue: lane holds rows r = 8rt + g, columns 8j + 2 q4 + {0,1}; destinations come from the
         // per-column table built once per CTA (the index arithmetic used to cost as many instructions as the main loop)
@@ -268,7 +263,7 @@ static cudaError_t leg_fwd_nc(s2kit_cuda_plan* p, const double* table, uint64_t 
     dim3 grid((nfun + NF - 1) / NF, m_hi - m_lo, rowsplit);
     k_legendre_fwd<NC, PC><<<grid, LEG_WARPS * 32, smem, p->stream>>>(table, p->d_order_start, shift, p->d_meta,
                                                                   p->d_rt_start, X, rco, ico, coef_stride, p->bw, nfun,
-                                                                  m_lo, real_fmt, order_list, l2_prefetch_cap(PC), getenv("S2K_EXPERIMENT") ? atoi(getenv("S2K_EXPERIMENT")) : 0);
+                                                                  m_lo, real_fmt, order_list, l2_prefetch_cap(PC));
     return cudaGetLastError();
 }
 

@@ -83,8 +83,7 @@ __device__ __forceinline__ int tiles_in_row(const BlockMeta& mb, int rt) {
 // tp: first tile of the row tile (+ 2*lane); xp: panel base of this lane (parity, column g, slot q4).
 template <int NC>
 __device__ __forceinline__ void fwd_row_tile(const double* __restrict__ tp, const double* xp, int CS, int ctn,
-                                             double (&acc)[NC / 8][2], bool dead_lane = false,
-                                             bool exp_no_lds = false) {
+                                             double (&acc)[NC / 8][2], bool dead_lane = false) {
     // Ring of LEG_PREFETCH tiles in registers.  The refill is UNCONDITIONAL (index clamped to the last tile): a
     // predicated refill made ptxas load into a temporary and copy it into the ring slot right away, which waits
     // for the load and serialises the whole prefetch.
@@ -99,16 +98,11 @@ __device__ __forceinline__ void fwd_row_tile(const double* __restrict__ tp, cons
             const int ct = ct0 + u;
             if (ct < ctn) {
                 double b[NC / 8][2];
-                if (!exp_no_lds) {
 #pragma unroll
-                    for (int j = 0; j < NC / 8; ++j) {
-                        b[j][0] = xp[j * 8 * CS + 8 * ct];
-                        b[j][1] = xp[j * 8 * CS + 8 * ct + 4];
-                        if (dead_lane) b[j][0] = b[j][1] = 0.0;  // MMA columns beyond a half-width panel
-                    }
-                } else {  // TIMING EXPERIMENT ONLY (S2K_EXPERIMENT=1): no shared-memory fragment loads
-#pragma unroll
-                    for (int j = 0; j < NC / 8; ++j) b[j][0] = b[j][1] = 1.0 + ct;
+                for (int j = 0; j < NC / 8; ++j) {
+                    b[j][0] = xp[j * 8 * CS + 8 * ct];
+                    b[j][1] = xp[j * 8 * CS + 8 * ct + 4];
+                    if (dead_lane) b[j][0] = b[j][1] = 0.0;  // MMA columns beyond a half-width panel
                 }
                 // k-step outer: consecutive DMMAs go to different accumulators
 #pragma unroll
