@@ -56,6 +56,10 @@ void DLTSemi(double* data, const int bw, const int m, double* result, double* wo
 void InvDLTSemi(double* coeffs, const int bw, const int m, double* result, double* trans_cos_pml_table,
                 double* sin_values, double* workspace, fftw_plan* plan);
 
+/* include/s2kit/chebyshev_nodes.h:4-6 */
+void AcosOfChebyshevNodes(const int n, double* eval_points);
+void ChebyshevNodes(const int n, double* eval_points);
+
 /* include/s2kit/weights.h:4 */
 void GenerateWeightsForDLT(const int bw, double* weights);
 

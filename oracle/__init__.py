@@ -38,6 +38,10 @@ def build(ref=True, port=True):
         targets.append("ref")
     if targets:
         subprocess.run(["make", "-s", "-C", _HERE] + targets, check=True)
+    # the reference's test mains relinked against the product library (needs the product .so to exist)
+    if ref and os.path.isdir("/root/reference/test") and os.path.exists(
+            os.path.join(_HERE, "..", "s2kit_b200", "libs2kit_cuda.so")):
+        subprocess.run(["make", "-s", "-C", _HERE, "relink"], check=True)
 
 
 def have_ref():

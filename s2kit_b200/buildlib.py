@@ -68,6 +68,10 @@ def build(force=False, verbose=False):
     if jobs or not os.path.exists(LIB):
         _run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs +
              ["-lpthread", "-lm"], os.path.join(OBJ, "link.log"))
+    # descriptor-only FFTW plan stubs for callers without FFTW (include/s2kit_fftw_shim/fftw3.h)
+    shim_src, shim_lib = os.path.join(CSRC, "fftw_shim.c"), os.path.join(HERE, "libs2kit_fftw_shim.so")
+    if force or _newer([shim_src] + hdrs, shim_lib):
+        _run(["gcc"] + GCC_FLAGS + ["-shared", "-o", shim_lib, shim_src], os.path.join(OBJ, "shim.log"))
     return LIB
 
 

@@ -149,6 +149,17 @@ int IndexOfHarmonicCoeff(const int m, const int l, const int bw) {
 
 /* ------------------------------------------------------------------------------------ setup */
 
+/* chebyshev_nodes.c:16-34 (host helpers some callers use directly, e.g. test/test_DLT_semi.c:54) */
+void AcosOfChebyshevNodes(const int n, double* eval_points) {
+    const double den = 2. * n;
+    for (int i = 0; i < n; ++i) eval_points[i] = (2. * i + 1.) * M_PI / den;
+}
+
+void ChebyshevNodes(const int n, double* eval_points) {
+    const double den = 2. * n;
+    for (int i = 0; i < n; ++i) eval_points[i] = cos((2. * i + 1.) * M_PI / den);
+}
+
 void GenerateWeightsForDLT(const int bw, double* weights) { s2k_host_weights(bw, weights); }
 
 /* cospml.c:161-242: generated on the device, exported in the reference's packed layout */
