@@ -149,6 +149,16 @@ class ClockSampler:
                 "samples_in_timed_region": len(inside)}
 
 
+# DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) per function and kernel from the committed
+# `ncu --set full` capture of this command at bw = 256, COMPLEX, 256 functions per launch
+# (profiles/r1_ncu_full_metrics_final.csv); scaled to the launch size for `roofline.traffic`.
+NCU_DRAM_BYTES_PER_FUNCTION_BW256_COMPLEX = {
+    "phi_fft_fwd": (1.074085e9 + 1.027033e9) / 256, "phi_fft_inv": (1.07166e9 + 1.028037e9) / 256,
+    "dct_fwd": (1.071721e9 + 0.508014e9) / 256, "dct_inv": (0.545191e9 + 1.017913e9) / 256,
+    "legendre_fwd": (0.570337e9 + 0.271074e9) / 256, "legendre_inv": (0.294773e9 + 0.484361e9) / 256,
+}
+
+
 def table_doubles(bw):
     tot = 0
     for m in range(bw):
@@ -348,8 +358,12 @@ def run_ours(a):
     roofline = None
     if dom:
         d = stages[dom]
+        traffic = None
+        if bw == 256 and fmt == s2.COMPLEX and dom in NCU_DRAM_BYTES_PER_FUNCTION_BW256_COMPLEX:
+            traffic = NCU_DRAM_BYTES_PER_FUNCTION_BW256_COMPLEX[dom] * d["functions_per_launch"]
         roofline = {"kernel": dom, "bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"], "unit": d["unit"],
-                    "frac": d["frac"], "traffic": None,
+                    "frac": d["frac"], "traffic": traffic,
+                    "alg_bytes_per_launch": d["alg_bytes_per_launch"], "alg_flops_per_launch": d["alg_flops_per_launch"],
                     "peak_source": (hbm_src if d["bound"] == "hbm" else
                                     "FP64 tensor (DMMA mma.sync.m8n8k4.f64) micro-benchmark measured in this run; "
                                     "MEASURED_PEAKS.json has no FP64 figure"),
