@@ -129,38 +129,78 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_fwd(
     __syncthreads();
     const double* tbase = table + (order_start[m] - table_shift) * 64 + lane * 2;
     const int g = lane >> 2, q4 = lane & 3;
-    // One work item = row tile rt of BOTH parity blocks (16 consecutive degrees l), heaviest first, snake over the
-    // slots.  Keeping the two parities in one warp lets the epilogue store 16-byte pairs (l, l+1): the scattered
-    // 8-byte stores of one parity at a time touched every 32-byte sector twice and cost 20 % of the kernel.
-    const int nslots = LEG_WARPS * gridDim.z, slot = blockIdx.z * LEG_WARPS + warp;
-    for (int round = 0; round * nslots < mb0.nrt; ++round) {
-        const int q = snake_item(round, slot, nslots);
-        if (q >= mb0.nrt) continue;
-        const int rt = mb0.nrt - 1 - q;  // mb0.nrt >= mb1.nrt
-        const int gsel = PC < NC ? (g & (PC - 1)) : g;
-        double acc0[NC / 8][2], acc1[NC / 8][2];
-#pragma unroll
-        for (int j = 0; j < NC / 8; ++j) acc0[j][0] = acc0[j][1] = acc1[j][0] = acc1[j][1] = 0.0;
-        fwd_row_tile<NC>(tbase + (uint64_t)srt[rt] * 64, Xs + gsel * CS + q4, CS, tiles_in_row(mb0, rt), acc0,
-                         PC < NC && g >= PC);
-        if (rt < mb1.nrt)
-            fwd_row_tile<NC>(tbase + (uint64_t)srt[mb0.nrt + rt] * 64, Xs + (PC + gsel) * CS + q4, CS,
-                             tiles_in_row(mb1, rt), acc1, PC < NC && g >= PC);
+    if constexpr (NC >= 32) {
+        // Batched panels: one item per (parity, row tile) -- finer-grained balance over the eight warps measured ~4 %
+        // faster here than the paired items below.
+        // items sorted by decreasing cost: (parity 0, rt), (parity 1, rt) for rt = nrt-1 .. 0; snake over the slots
+        const int nslots = LEG_WARPS * gridDim.z, slot = blockIdx.z * LEG_WARPS + warp;
+        for (int round = 0;; ++round) {
+            const int q = snake_item(round, slot, nslots);
+            if (round * nslots >= 2 * mb0.nrt) break;
+            const int p = q & 1;
+            const BlockMeta mb = p ? mb1 : mb0;
+            const int rt = mb0.nrt - 1 - (q >> 1);  // mb0.nrt >= mb1.nrt
+            if (q >= 2 * mb0.nrt || rt >= mb.nrt) continue;
+            const int ctn = tiles_in_row(mb, rt);
+            const double* tp = tbase + (uint64_t)srt[(p ? mb0.nrt : 0) + rt] * 64;
+            const double* xp = Xs + (p * PC + (PC < NC ? (g & (PC - 1)) : g)) * CS + q4;
 
-        // ---- epilogue: lane holds row r = 8rt + g of both parities = degrees l - m = 2r, 2r+1, columns 8j + 2 q4 + {0,1}
-        const int r = 8 * rt + g;
-        const bool v0ok = r < mb0.rows, v1ok = r < mb1.rows;
-#pragma unroll
-        for (int j = 0; j < NC / 8; ++j) {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const ColOut co = cinfo[8 * j + 2 * q4 + e];
-                const double v0 = acc0[j][e], v1 = acc1[j][e];
-                // parity-0 value of the next row (lane + 4): partner of v1 when the run starts at an odd element
-                const double n0 = __shfl_down_sync(0xffffffffu, v0, 4);
-                const bool n0ok = g < 7 && r + 1 < mb0.rows;
-                store_pair(co.dst, co.scale, r, g, v0, v1, n0, v0ok, v1ok, n0ok);
-                store_pair(co.mirror, co.mscale, r, g, v0, v1, n0, v0ok, v1ok, n0ok);
+            double acc[NC / 8][2];
+    #pragma unroll
+            for (int j = 0; j < NC / 8; ++j) acc[j][0] = acc[j][1] = 0.0;
+            fwd_row_tile<NC>(tp, xp, CS, ctn, acc, PC < NC && g >= PC);
+
+            // ---- epilogue: lane holds rows r = 8rt + g, columns 8j + 2 q4 + {0,1}; destinations come from the
+            // per-column table built once per CTA (the index arithmetic used to cost as many instructions as the main loop)
+            const int r = 8 * rt + g;
+            if (r < mb.rows) {
+                const int off = p + 2 * r;  // l - m
+    #pragma unroll
+                for (int j = 0; j < NC / 8; ++j) {
+    #pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const ColOut co = cinfo[8 * j + 2 * q4 + e];
+                        const double v = acc[j][e];
+                        if (co.dst) co.dst[off] = v * co.scale;
+                        if (co.mirror) co.mirror[off] = v * co.mscale;
+                    }
+                }
+            }
+        }
+    } else {
+        // One work item = row tile rt of BOTH parity blocks (16 consecutive degrees l), heaviest first, snake over the
+        // slots.  Keeping the two parities in one warp lets the epilogue store 16-byte pairs (l, l+1): the scattered
+        // 8-byte stores of one parity at a time touched every 32-byte sector twice and cost 20 % of the kernel.
+        const int nslots = LEG_WARPS * gridDim.z, slot = blockIdx.z * LEG_WARPS + warp;
+        for (int round = 0; round * nslots < mb0.nrt; ++round) {
+            const int q = snake_item(round, slot, nslots);
+            if (q >= mb0.nrt) continue;
+            const int rt = mb0.nrt - 1 - q;  // mb0.nrt >= mb1.nrt
+            const int gsel = PC < NC ? (g & (PC - 1)) : g;
+            double acc0[NC / 8][2], acc1[NC / 8][2];
+    #pragma unroll
+            for (int j = 0; j < NC / 8; ++j) acc0[j][0] = acc0[j][1] = acc1[j][0] = acc1[j][1] = 0.0;
+            fwd_row_tile<NC>(tbase + (uint64_t)srt[rt] * 64, Xs + gsel * CS + q4, CS, tiles_in_row(mb0, rt), acc0,
+                             PC < NC && g >= PC);
+            if (rt < mb1.nrt)
+                fwd_row_tile<NC>(tbase + (uint64_t)srt[mb0.nrt + rt] * 64, Xs + (PC + gsel) * CS + q4, CS,
+                                 tiles_in_row(mb1, rt), acc1, PC < NC && g >= PC);
+
+            // ---- epilogue: lane holds row r = 8rt + g of both parities = degrees l - m = 2r, 2r+1, columns 8j + 2 q4 + {0,1}
+            const int r = 8 * rt + g;
+            const bool v0ok = r < mb0.rows, v1ok = r < mb1.rows;
+    #pragma unroll
+            for (int j = 0; j < NC / 8; ++j) {
+    #pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const ColOut co = cinfo[8 * j + 2 * q4 + e];
+                    const double v0 = acc0[j][e], v1 = acc1[j][e];
+                    // parity-0 value of the next row (lane + 4): partner of v1 when the run starts at an odd element
+                    const double n0 = __shfl_down_sync(0xffffffffu, v0, 4);
+                    const bool n0ok = g < 7 && r + 1 < mb0.rows;
+                    store_pair(co.dst, co.scale, r, g, v0, v1, n0, v0ok, v1ok, n0ok);
+                    store_pair(co.mirror, co.mscale, r, g, v0, v1, n0, v0ok, v1ok, n0ok);
+                }
             }
         }
     }
