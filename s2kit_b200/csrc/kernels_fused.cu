@@ -200,9 +200,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_inv(
     cp_async_wait_all();
     __syncthreads();
 
-    const double* tbase = table + (order_start[m] - table_shift) * 64;
+    const double* tbase = table + (order_start[m] - table_shift) * 64 + lane * 2;  // B-fragment-ordered tiles
     const int gq = lane >> 2, q4 = lane & 3;
-    const int boff0 = tile_elem_offset(q4, gq), boff1 = tile_elem_offset(q4 + 4, gq);
     double acc[ITEMS][NC / 8][2];
 #pragma unroll
     for (int it = 0; it < ITEMS; ++it) {
@@ -211,8 +210,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) k_fused_inv(
         const int q = snake_item(it, warp, LEG_WARPS);
         if (q < 2 * NCT) {
             const int p = q & 1, ct = q >> 1;
-            inv_col_tile<NC>(tbase, srt + (p ? mb0.nrt : 0), p ? mb1 : mb0, ct, Cs + (p * NC + gq) * CS + q4, CS, boff0,
-                             boff1, acc[it]);
+            inv_col_tile<NC>(tbase, srt + (p ? mb0.nrt : 0), p ? mb1 : mb0, ct, Cs + (p * NC + gq) * CS + q4, CS,
+                             acc[it]);
         }
     }
     __syncthreads();  // every warp is done with the coefficient panel

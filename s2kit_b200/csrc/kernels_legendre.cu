@@ -260,10 +260,8 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_inv(
     for (int i = tid; i < mb0.nrt + mb1.nrt; i += blockDim.x)
         srt[i] = rt_start[(i < mb0.nrt ? mb0.rt_base : mb1.rt_base - mb0.nrt) + i];
     __syncthreads();
-    const double* tbase = table + (order_start[m] - table_shift) * 64;
+    const double* tbase = table + (order_start[m] - table_shift) * 64 + lane * 2;  // B-fragment-ordered tiles
     const int g = lane >> 2, q4 = lane & 3;
-    // B fragment of k-step s: element (row q4 + 4s, col g) of the 8x8 tile
-    const int boff0 = tile_elem_offset(q4, g), boff1 = tile_elem_offset(q4 + 4, g);
 
     const int nslots = LEG_WARPS * gridDim.z, slot = blockIdx.z * LEG_WARPS + warp;
     for (int round = 0; round * nslots < 2 * nct; ++round) {
@@ -275,7 +273,7 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_inv(
 #pragma unroll
         for (int j = 0; j < NC / 8; ++j) acc[j][0] = acc[j][1] = 0.0;
         inv_col_tile<NC>(tbase, srt + (p ? mb0.nrt : 0), mb, ct,
-                         Cs + (p * PC + (PC < NC ? (g & (PC - 1)) : g)) * CS + q4, CS, boff0, boff1, acc,
+                         Cs + (p * PC + (PC < NC ? (g & (PC - 1)) : g)) * CS + q4, CS, acc,
                          PC < NC && g >= PC);
         // ---- epilogue: lane holds column 8j + g, cosine slots c = 8ct + 2 q4 + {0,1}
         // slots c0, c0+1 of parity p are adjacent in the parity-split plane

@@ -29,10 +29,13 @@ __device__ __forceinline__ void rec_step(const double (&x)[8], double (&prev)[8]
     }
 }
 
+// transposed = 0: A-fragment order (forward contraction); 1: the same tile with rows and columns swapped inside the
+// tile = B-fragment order, so the inverse contraction also reads one coalesced 128-bit value pair per lane
 __device__ __forceinline__ void tile_store(double* __restrict__ table, uint64_t order_tile0, const BlockMeta& mb,
-                                           const uint32_t* __restrict__ rt_start, int r, int c, double v) {
+                                           const uint32_t* __restrict__ rt_start, int r, int c, double v,
+                                           int transposed) {
     uint64_t tile = order_tile0 + rt_start[mb.rt_base + (r >> 3)] + (uint64_t)(c >> 3);
-    table[tile * 64 + tile_elem_offset(r & 7, c & 7)] = v;
+    table[tile * 64 + (transposed ? tile_elem_offset(c & 7, r & 7) : tile_elem_offset(r & 7, c & 7))] = v;
 }
 
 template <int NB, int G>
@@ -41,7 +44,7 @@ __global__ void __launch_bounds__(NB / 8 * G) k_table_gen(double* __restrict__ t
                                                           const BlockMeta* __restrict__ meta,
                                                           const uint32_t* __restrict__ rt_start,
                                                           const int* __restrict__ units, int unit_lo, int unit_hi,
-                                                          int lch, const double* __restrict__ nodes,
+                                                          int lch, int transposed, const double* __restrict__ nodes,
                                                           const double* __restrict__ seeds,
                                                           const double2* __restrict__ rec,
                                                           const double2* __restrict__ tw,
@@ -99,7 +102,7 @@ __global__ void __launch_bounds__(NB / 8 * G) k_table_gen(double* __restrict__ t
                 double2 q = __ldg(qtab + k);
                 double y = pk ? (q.x * (ai + bi) - q.y * (ar - br)) : (q.x * (ar + br) + q.y * (ai - bi));
                 if (k == 0) y *= 0.70710678118654752440;  // cospml.c:205
-                tile_store(table, tile0, mb, rt_start, ra, c, y * fudge);
+                tile_store(table, tile0, mb, rt_start, ra, c, y * fudge, transposed);
             }
         }
     }
@@ -108,7 +111,7 @@ __global__ void __launch_bounds__(NB / 8 * G) k_table_gen(double* __restrict__ t
 // Any bandwidth <= 1024: one CTA per order, thread i owns node i, DCT by the O(bw^2) definition.
 __global__ void k_table_gen_direct(double* __restrict__ table, const uint64_t* __restrict__ order_start, uint64_t shift,
                                    const BlockMeta* __restrict__ meta, const uint32_t* __restrict__ rt_start, int m_lo,
-                                   int bw, const double* __restrict__ nodes, const double* __restrict__ seeds,
+                                   int bw, int transposed, const double* __restrict__ nodes, const double* __restrict__ seeds,
                                    const double2* __restrict__ rec, const double2* __restrict__ qtab) {
     extern __shared__ double sm[];
     const int m = m_lo + blockIdx.x, i = threadIdx.x;
@@ -130,7 +133,7 @@ __global__ void k_table_gen_direct(double* __restrict__ table, const uint64_t* _
             for (int s = 0; s < bw; ++s) acc += sm[s] * qtab[(int)(((long)(2 * s + 1) * k) % (4 * bw))].x;
             acc *= 2.0;
             if (k == 0) acc *= 0.70710678118654752440;
-            tile_store(table, tile0, mb, rt_start, r, k >> 1, acc * fudge);
+            tile_store(table, tile0, mb, rt_start, r, k >> 1, acc * fudge, transposed);
         }
         __syncthreads();
         if (i < bw && l + 1 < bw) {
@@ -193,7 +196,8 @@ __global__ void k_table_unpack(const double* __restrict__ table, const uint64_t*
 
 // ------------------------------------------------------------------------------------------------ launchers
 template <int NB>
-static cudaError_t table_gen_nb(s2kit_cuda_plan* p, double* table, uint64_t shift, int unit_lo, int unit_hi, int lch) {
+static cudaError_t table_gen_nb(s2kit_cuda_plan* p, double* table, uint64_t shift, int unit_lo, int unit_hi, int lch,
+                                int transposed) {
     constexpr int T8 = NB / 8;
     constexpr int G = (256 / T8) < 1 ? 1 : ((256 / T8) > 8 ? 8 : (256 / T8));
     size_t smem = sizeof(double2) * G * fft_padded_len(NB);
@@ -204,14 +208,14 @@ static cudaError_t table_gen_nb(s2kit_cuda_plan* p, double* table, uint64_t shif
     }
     int nunits = unit_hi - unit_lo;
     k_table_gen<NB, G><<<(nunits + G - 1) / G, T8 * G, smem, p->stream>>>(
-        table, p->d_order_start, shift, p->d_meta, p->d_rt_start, p->d_units, unit_lo, unit_hi, lch, p->d_nodes,
+        table, p->d_order_start, shift, p->d_meta, p->d_rt_start, p->d_units, unit_lo, unit_hi, lch, transposed, p->d_nodes,
         p->d_seeds, p->d_rec, p->d_tw_b, p->d_q_b);
     return cudaGetLastError();
 }
 
 int table_unit_rows(int bw) { return bw <= 512 ? 32 : 64; }
 
-cudaError_t launch_table_gen(s2kit_cuda_plan* p, double* table, uint64_t shift, int m_lo, int m_hi) {
+cudaError_t launch_table_gen(s2kit_cuda_plan* p, double* table, uint64_t shift, int m_lo, int m_hi, int transposed) {
     if (m_hi <= m_lo) return cudaSuccess;
     uint64_t t0 = p->h_order_start[m_lo], t1 = p->h_order_start[m_hi];
     cudaError_t e = cudaMemsetAsync(table + (t0 - shift) * 64, 0, (t1 - t0) * 64 * sizeof(double), p->stream);
@@ -220,20 +224,20 @@ cudaError_t launch_table_gen(s2kit_cuda_plan* p, double* table, uint64_t shift, 
     if (p->fast) {
         int ulo = p->h_unit_first[m_lo], uhi = p->h_unit_first[m_hi], lch = table_unit_rows(p->bw);
         switch (p->bw) {
-            case 16: e = table_gen_nb<16>(p, table, shift, ulo, uhi, lch); break;
-            case 32: e = table_gen_nb<32>(p, table, shift, ulo, uhi, lch); break;
-            case 64: e = table_gen_nb<64>(p, table, shift, ulo, uhi, lch); break;
-            case 128: e = table_gen_nb<128>(p, table, shift, ulo, uhi, lch); break;
-            case 256: e = table_gen_nb<256>(p, table, shift, ulo, uhi, lch); break;
-            case 512: e = table_gen_nb<512>(p, table, shift, ulo, uhi, lch); break;
-            case 1024: e = table_gen_nb<1024>(p, table, shift, ulo, uhi, lch); break;
-            case 2048: e = table_gen_nb<2048>(p, table, shift, ulo, uhi, lch); break;
+            case 16: e = table_gen_nb<16>(p, table, shift, ulo, uhi, lch, transposed); break;
+            case 32: e = table_gen_nb<32>(p, table, shift, ulo, uhi, lch, transposed); break;
+            case 64: e = table_gen_nb<64>(p, table, shift, ulo, uhi, lch, transposed); break;
+            case 128: e = table_gen_nb<128>(p, table, shift, ulo, uhi, lch, transposed); break;
+            case 256: e = table_gen_nb<256>(p, table, shift, ulo, uhi, lch, transposed); break;
+            case 512: e = table_gen_nb<512>(p, table, shift, ulo, uhi, lch, transposed); break;
+            case 1024: e = table_gen_nb<1024>(p, table, shift, ulo, uhi, lch, transposed); break;
+            case 2048: e = table_gen_nb<2048>(p, table, shift, ulo, uhi, lch, transposed); break;
             default: e = cudaErrorInvalidValue;
         }
     } else {
         int nt = ((p->bw + 31) / 32) * 32;
         k_table_gen_direct<<<m_hi - m_lo, nt, sizeof(double) * p->bw, p->stream>>>(
-            table, p->d_order_start, shift, p->d_meta, p->d_rt_start, m_lo, p->bw, p->d_nodes, p->d_seeds, p->d_rec,
+            table, p->d_order_start, shift, p->d_meta, p->d_rt_start, m_lo, p->bw, transposed, p->d_nodes, p->d_seeds, p->d_rec,
             p->d_q_b);
         e = cudaGetLastError();
     }

@@ -162,9 +162,10 @@ static void apply_table_l2_policy(s2kit_cuda_plan* p) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, p->device) != cudaSuccess) return;
     size_t want = p->table_bytes;
-    if (prop.persistingL2CacheMaxSize <= 0 || want > (size_t)prop.persistingL2CacheMaxSize) return;
-    if (want > (size_t)prop.accessPolicyMaxWindowSize) return;
-    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) {
+    if (prop.persistingL2CacheMaxSize <= 0 || want > (size_t)prop.accessPolicyMaxWindowSize) return;
+    size_t carve = std::min(want, (size_t)prop.persistingL2CacheMaxSize);
+    if (carve * 4 < want) return;  // far larger than the carve-out: streamed anyway
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) != cudaSuccess) {
         cudaGetLastError();
         return;
     }
@@ -172,7 +173,7 @@ static void apply_table_l2_policy(s2kit_cuda_plan* p) {
     memset(&attr, 0, sizeof(attr));
     attr.accessPolicyWindow.base_ptr = p->d_table;
     attr.accessPolicyWindow.num_bytes = want;
-    attr.accessPolicyWindow.hitRatio = 1.0f;
+    attr.accessPolicyWindow.hitRatio = (float)((double)carve / (double)want);
     attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
     attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
     if (cudaStreamSetAttribute(p->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
@@ -217,8 +218,10 @@ int s2k_plan_create_impl(s2kit_cuda_plan** out, int bw, int variant, int max_bat
         // slower than the separate kernels at bw = 256 today (profiles/r1_ncu_summary.md): opt-in.
         const char* fu = getenv("S2KIT_CUDA_FUSE");
         p->fuse = (fu && fu[0] == '1');
-        const char* np = getenv("S2KIT_CUDA_NO_L2PERSIST");
-        p->l2_persist = !(np && np[0] == '1');
+        // persisting-L2 carve-out for the tables: measured neutral with one table copy and harmful with two (it takes
+        // L2 away from the streaming kernels), the per-CTA bulk prefetch already does the job -- opt-in
+        const char* np = getenv("S2KIT_CUDA_L2PERSIST");
+        p->l2_persist = (np && np[0] == '1');
     }
     if (!p->fast && bw > 512) {
         delete p;
@@ -278,9 +281,12 @@ int s2k_plan_create_impl(s2kit_cuda_plan** out, int bw, int variant, int max_bat
     // ---- tables
     const uint64_t total_tiles = p->h_order_start[bw];
     if (variant == S2KIT_CUDA_MEMO) {
+        // two copies of the tiles in one allocation: A-fragment order for the forward contraction, B-fragment
+        // (tile-transposed) order for the inverse
         p->table_tiles = total_tiles;
-        p->table_bytes = total_tiles * 64 * sizeof(double);
+        p->table_bytes = 2 * total_tiles * 64 * sizeof(double);
         CK(cudaMalloc((void**)&p->d_table, p->table_bytes));
+        p->d_table_t = p->d_table + total_tiles * 64;
         // generate every run of consecutive owned orders
         int m = 0;
         while (m < bw) {
@@ -290,7 +296,8 @@ int s2k_plan_create_impl(s2kit_cuda_plan** out, int bw, int variant, int max_bat
             }
             int hi = m;
             while (hi < bw && owned[hi]) ++hi;
-            CK(s2k::launch_table_gen(p, p->d_table, 0, m, hi));
+            CK(s2k::launch_table_gen(p, p->d_table, 0, m, hi, 0));
+            CK(s2k::launch_table_gen(p, p->d_table_t, 0, m, hi, 1));
             m = hi;
         }
     } else {
@@ -428,11 +435,12 @@ static int inv_fst_device(s2kit_cuda_plan* p, const double* rco, const double* i
         double* id = idata + (long)c0 * data_stride;
         const bool fused = s2k::fused_supported(p, nf, fmt);
         for (const OrderGroup& g : order_groups(p, 0, bw)) {
-            if (p->variant == S2KIT_CUDA_FLY) CK(s2k::launch_table_gen(p, p->d_table, g.shift, g.lo, g.hi));
+            const double* tt = p->variant == S2KIT_CUDA_FLY ? p->d_table : p->d_table_t;
+            if (p->variant == S2KIT_CUDA_FLY) CK(s2k::launch_table_gen(p, p->d_table, g.shift, g.lo, g.hi, 1));
             if (fused)
-                CK(s2k::launch_fused_inv(p, p->d_table, g.shift, rc, ic, coef_stride, p->d_S, nf, g.lo, g.hi, fmt));
+                CK(s2k::launch_fused_inv(p, tt, g.shift, rc, ic, coef_stride, p->d_S, nf, g.lo, g.hi, fmt));
             else
-                CK(s2k::launch_legendre_inv(p, p->d_table, g.shift, rc, ic, coef_stride, p->d_X, nf, g.lo, g.hi, fmt));
+                CK(s2k::launch_legendre_inv(p, tt, g.shift, rc, ic, coef_stride, p->d_X, nf, g.lo, g.hi, fmt));
         }
         if (!fused) CK(s2k::launch_dct_inv(p, p->d_X, p->d_S, nf, 0, nrows, fmt));
         CK(s2k::launch_phi_fft_inv(p, p->d_S, rd, id, data_stride, nf, fmt));
@@ -758,9 +766,9 @@ extern "C" int s2kit_cuda_inv_dlt_semi(s2kit_cuda_plan* p, const double* coeffs,
                                 where == S2KIT_CUDA_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                                 p->stream);
         for (const OrderGroup& g : order_groups(p, m, m + 1)) {
-            if (e == cudaSuccess && p->variant == S2KIT_CUDA_FLY) e = s2k::launch_table_gen(p, p->d_table, g.shift, g.lo, g.hi);
+            if (e == cudaSuccess && p->variant == S2KIT_CUDA_FLY) e = s2k::launch_table_gen(p, p->d_table, g.shift, g.lo, g.hi, 1);
             if (e == cudaSuccess)
-                e = s2k::launch_legendre_inv(p, p->d_table, g.shift, dcoef, dcoef + cs, cs, p->d_X, 1, m, m + 1,
+                e = s2k::launch_legendre_inv(p, p->variant == S2KIT_CUDA_FLY ? p->d_table : p->d_table_t, g.shift, dcoef, dcoef + cs, cs, p->d_X, 1, m, m + 1,
                                              S2KIT_REAL);
         }
         if (e == cudaSuccess) e = s2k::launch_dct_inv(p, p->d_X, p->d_S, 1, m, m + 1, S2KIT_COMPLEX);

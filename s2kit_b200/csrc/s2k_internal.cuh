@@ -53,7 +53,7 @@ struct s2kit_cuda_plan {
     int bw = 0, n = 0, variant = 0, device = 0, chunk = 1;
     bool fast = false;  // power-of-two bandwidth >= 16: radix FFT kernels; otherwise direct O(n^2) kernels
     bool fuse = false;  // fused DCT+Legendre kernels for batched calls (S2KIT_CUDA_FUSE=1 enables)
-    bool l2_persist = true;  // persisting-L2 window on a Memo table that fits (S2KIT_CUDA_NO_L2PERSIST=1 disables)
+    bool l2_persist = false;  // persisting-L2 window on Memo tables that fit (S2KIT_CUDA_L2PERSIST=1 enables)
     cudaStream_t stream = nullptr;
     bool own_stream = true;
 
@@ -76,7 +76,8 @@ struct s2kit_cuda_plan {
     double2* d_rec = nullptr;      // bw*bw  rec[m*bw + l] = (a_l^m, c_l^m)  (l2_norms.c:16-38)
 
     // table (private tiled layout)
-    double* d_table = nullptr;
+    double* d_table = nullptr;    // tiles in A-fragment order (forward); Fly: the scratch ring, either order
+    double* d_table_t = nullptr;  // Memo: the same tiles in B-fragment order (inverse), second half of one allocation
     size_t table_tiles = 0;             // tiles resident in d_table
     std::vector<uint64_t> h_order_start;  // [bw+1] tile offset of each order in a full table
     std::vector<s2k::BlockMeta> h_meta;   // [2*bw]
@@ -140,7 +141,8 @@ cudaError_t launch_legendre_inv(s2kit_cuda_plan* p, const double* table, uint64_
                                 const double* ico, long coef_stride, double* V, int nfun, int m_lo, int m_hi,
                                 int data_format, const int* order_list = nullptr);
 // K7: table generation for orders [m_lo, m_hi) into `table` (tile layout, pre-zeroed by the launcher)
-cudaError_t launch_table_gen(s2kit_cuda_plan* p, double* table, uint64_t table_shift, int m_lo, int m_hi);
+cudaError_t launch_table_gen(s2kit_cuda_plan* p, double* table, uint64_t table_shift, int m_lo, int m_hi,
+                             int transposed = 0);
 // tile layout -> reference packed layout for one order
 cudaError_t launch_table_unpack(s2kit_cuda_plan* p, const double* table, uint64_t table_shift, int m, double* out);
 // recurrence coefficients (a_l^m, c_l^m) for all (m, l)

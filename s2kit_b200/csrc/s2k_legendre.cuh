@@ -117,25 +117,23 @@ __device__ __forceinline__ void fwd_row_tile(const double* __restrict__ tp, cons
 }
 
 // Inverse main loop for one (parity, column tile ct): acc[j] += C_panel * T_tile over the row tiles that reach ct.
+// tbase: the table in B-fragment (tile-transposed) order + 2*lane, so one 128-bit load yields both k-steps' fragments.
 // srt: this parity block's row-tile starts (shared memory); cp: panel base of this lane.
 template <int NC>
 __device__ __forceinline__ void inv_col_tile(const double* __restrict__ tbase, const uint32_t* srt, const BlockMeta& mb,
-                                             int ct, const double* cp, int CS, int boff0, int boff1,
-                                             double (&acc)[NC / 8][2], bool dead_lane = false) {
+                                             int ct, const double* cp, int CS, double (&acc)[NC / 8][2],
+                                             bool dead_lane = false) {
     int rt_min = 0;
     if (8 * ct >= mb.len0 + 7) rt_min = (8 * ct - mb.len0 - 7) / 8 + 1;
     // rows below rt_min never reach ct; from the first row tile that does, all later ones do (lengths grow)
     while (rt_min < mb.nrt && ct >= tiles_in_row(mb, rt_min)) ++rt_min;
     const int cnt = mb.nrt - rt_min;
     if (cnt <= 0) return;
-    constexpr int LEG_PREFETCH = leg_prefetch(NC) < 8 ? leg_prefetch(NC) : 8;
-    double b0buf[LEG_PREFETCH], b1buf[LEG_PREFETCH];
+    constexpr int LEG_PREFETCH = leg_prefetch(NC);
+    double2 bbuf[LEG_PREFETCH];
 #pragma unroll
-    for (int u = 0; u < LEG_PREFETCH; ++u) {
-        const double* tp = tbase + ((uint64_t)srt[rt_min + min(u, cnt - 1)] + ct) * 64;
-        b0buf[u] = __ldg(tp + boff0);
-        b1buf[u] = __ldg(tp + boff1);
-    }
+    for (int u = 0; u < LEG_PREFETCH; ++u)
+        bbuf[u] = __ldg(reinterpret_cast<const double2*>(tbase + ((uint64_t)srt[rt_min + min(u, cnt - 1)] + ct) * 64));
     for (int i0 = 0; i0 < cnt; i0 += LEG_PREFETCH) {
 #pragma unroll
         for (int u = 0; u < LEG_PREFETCH; ++u) {
@@ -150,14 +148,12 @@ __device__ __forceinline__ void inv_col_tile(const double* __restrict__ tbase, c
                     if (dead_lane) a[j][0] = a[j][1] = 0.0;
                 }
 #pragma unroll
-                for (int j = 0; j < NC / 8; ++j) dmma(acc[j], a[j][0], b0buf[u]);
+                for (int j = 0; j < NC / 8; ++j) dmma(acc[j], a[j][0], bbuf[u].x);
 #pragma unroll
-                for (int j = 0; j < NC / 8; ++j) dmma(acc[j], a[j][1], b1buf[u]);
-                {   // unconditional refill after the last use, clamped (see fwd_row_tile)
-                    const double* tp = tbase + ((uint64_t)srt[rt_min + min(i + LEG_PREFETCH, cnt - 1)] + ct) * 64;
-                    b0buf[u] = __ldg(tp + boff0);
-                    b1buf[u] = __ldg(tp + boff1);
-                }
+                for (int j = 0; j < NC / 8; ++j) dmma(acc[j], a[j][1], bbuf[u].y);
+                // unconditional refill after the last use, clamped (see fwd_row_tile)
+                bbuf[u] = __ldg(reinterpret_cast<const double2*>(
+                    tbase + ((uint64_t)srt[rt_min + min(i + LEG_PREFETCH, cnt - 1)] + ct) * 64));
             }
         }
     }

@@ -189,7 +189,7 @@ extern "C" int s2kit_cuda_inv_fst_orders(s2kit_cuda_plan* p, const double* rcoef
     if (!p || !shard_of(p)) return s2k_fail_msg("not a sharded plan");
     CKS(cudaSetDevice(p->device));
     ShardState* st = shard_of(p);
-    CKS(s2k::launch_legendre_inv(p, p->d_table, 0, rcoeffs, icoeffs, (long)p->bw * p->bw, p->d_X, 1, 0, st->norders,
+    CKS(s2k::launch_legendre_inv(p, p->d_table_t, 0, rcoeffs, icoeffs, (long)p->bw * p->bw, p->d_X, 1, 0, st->norders,
                                  S2KIT_COMPLEX, st->d_orders));
     CKS(s2k::launch_dct_inv(p, p->d_X, sendbuf, 1, 0, st->nrows_real, S2KIT_COMPLEX, &st->order_view));
     return 0;
