@@ -11,6 +11,8 @@
 // A DCT pair (real and imaginary column of one order) rides on ONE complex FFT of length 2bw: even/odd
 // reordering v[i] = x[2i], v[n-1-i] = x[2i+1] packed as v_re + i v_im, then the two spectra are separated
 // by conjugate symmetry.  Non-power-of-two bandwidths use the direct O(n^2) kernels at the end.
+#include <algorithm>
+
 #include "s2k_fft.cuh"
 #include "s2k_internal.cuh"
 
@@ -64,6 +66,63 @@ __global__ void __launch_bounds__(N / 8 * LT) k_phi_fft_fwd(const double* __rest
             Sr[at] = v.x;
             Si[at] = v.y;
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K1, TMA store
+// Same transform as k_phi_fft_fwd, but the transposed write goes through the TMA: each thread drops its eight outputs
+// into a [order row][LT latitudes] staging tile laid out in CU_TENSOR_MAP_SWIZZLE_64B order (which also keeps those
+// stores to 2-way bank conflicts), and one elected thread issues cp.async.bulk.tensor stores of 256-row boxes.  This
+// takes the transposed shared-memory read and all global store instructions (half-used 64-byte runs, one request per
+// 4 rows) off the LSU pipe that bounds the kernel (profiles/r1_ncu_summary.md).
+__device__ __forceinline__ unsigned swz64(unsigned byte_off) { return byte_off ^ (((byte_off >> 7) & 3u) << 4); }
+
+template <int N>
+__global__ void __launch_bounds__(N) k_phi_fft_fwd_tma(const double* __restrict__ rdata, const double* __restrict__ idata,
+                                                        long stride, double scale, int rows_kept,
+                                                        const double2* __restrict__ tw,
+                                                        const __grid_constant__ CUtensorMap tmap) {
+    constexpr int LT = 8, T8 = N / 8;
+    constexpr int RS = phi_row_stride(N, LT);
+    constexpr int ROWS = N < 256 ? N : 256;             // order rows per TMA box
+    constexpr int BOX_BYTES = ROWS * LT * 8;            // one box = ROWS x 64 bytes
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    double2* sx = reinterpret_cast<double2*>(smem_raw);  // exchange rows during the FFT, staging tiles afterwards
+    const int tid = threadIdx.x, jj = tid / T8, t = tid % T8;
+    const int j0 = blockIdx.x * LT, f = blockIdx.y;
+    const double* rrow = rdata + (long)f * stride + (long)(j0 + jj) * N;
+    const double* irow = idata + (long)f * stride + (long)(j0 + jj) * N;
+    double xr[8], xi[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        xr[e] = __ldg(rrow + t + e * T8);
+        xi[e] = __ldg(irow + t + e * T8);
+    }
+    fft_block<N>(xr, xi, sx + jj * RS, t, jj, tw);
+    __syncthreads();  // every transform is done with the exchange rows: reuse them as staging
+    // staging: part p (0 = re, 1 = im), box h: rows [h*ROWS, (h+1)*ROWS); element (row r, latitude jj) at swz64(r*64 + jj*8)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int mp = fft_out_index<N>(e, t);
+        const int h = mp / ROWS, r = mp % ROWS;
+        const unsigned off = swz64((unsigned)(r * 64 + jj * 8));
+        *reinterpret_cast<double*>(smem_raw + (0 * (N / ROWS) + h) * BOX_BYTES + off) = xr[e] * scale;
+        *reinterpret_cast<double*>(smem_raw + (1 * (N / ROWS) + h) * BOX_BYTES + off) = xi[e] * scale;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // make the generic-proxy writes visible to the TMA
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned sbase = static_cast<unsigned>(__cvta_generic_to_shared(smem_raw));
+        const int nbox = (rows_kept == N) ? N / ROWS : (rows_kept + ROWS - 1) / ROWS;  // REAL format: rows < bw only
+        for (int part = 0; part < 2; ++part)
+            for (int h = 0; h < nbox; ++h)
+                asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(
+                                 reinterpret_cast<uint64_t>(&tmap)),
+                             "r"(j0), "r"(h * ROWS), "r"(f * 2 + part),
+                             "r"(sbase + (unsigned)((part * (N / ROWS) + h) * BOX_BYTES))
+                             : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // staging must outlive the reads
     }
 }
 
@@ -327,6 +386,19 @@ template <int N>
 static cudaError_t phi_fwd_n(s2kit_cuda_plan* p, const double* rdata, const double* idata, long stride, double* S,
                              int nfun, int rows_kept, const PlaneView& pv, int nrings) {
     constexpr int LT = (4096 / N) < 8 ? (4096 / N) : 8;
+    if constexpr (N <= 512) {
+        // ordinary plane in the plan's own workspace: transposed write through the TMA
+        if (p->tma_S_ok && S == p->d_S && !pv.rowbase && nrings == N && nfun <= p->chunk) {
+            constexpr int RSX = phi_row_stride(N, 8);
+            size_t smem = std::max(sizeof(double2) * 8 * RSX, (size_t)2 * N * 8 * 8);
+            cudaError_t e = set_smem(k_phi_fft_fwd_tma<N>, smem);
+            if (e != cudaSuccess) return e;
+            double scale = sqrt(2.0 * M_PI) / (double)N;
+            k_phi_fft_fwd_tma<N><<<dim3(N / 8, nfun), N, smem, p->stream>>>(rdata, idata, stride, scale, rows_kept,
+                                                                              p->d_tw_n, p->tma_S);
+            return cudaGetLastError();
+        }
+    }
     constexpr int RS = phi_row_stride(N, LT);
     size_t smem = sizeof(double2) * LT * RS;
     cudaError_t e = set_smem(k_phi_fft_fwd<N, LT>, smem);

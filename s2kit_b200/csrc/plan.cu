@@ -179,6 +179,34 @@ static void apply_table_l2_policy(s2kit_cuda_plan* p) {
     if (cudaStreamSetAttribute(p->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
 }
 
+// Tensor map of the spectral-plane workspace for the TMA stores of K1 (kernels_fft.cu).  The driver entry point is
+// looked up at run time so the library does not link libcuda; on failure K1 simply keeps its LSU store path.
+static void make_plane_tensor_map(s2kit_cuda_plan* p) {
+    p->tma_S_ok = false;
+    const char* off = getenv("S2KIT_CUDA_NO_TMA");
+    if (off && off[0] == '1') return;
+    if (!p->fast || p->n > 512 || p->n < 64) return;
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    const cuuint64_t n = (cuuint64_t)p->n;
+    cuuint64_t gdim[3] = {n, n, (cuuint64_t)p->chunk * 2};
+    cuuint64_t gstride[2] = {n * sizeof(double), n * n * sizeof(double)};
+    cuuint32_t box[3] = {8, (cuuint32_t)(p->n < 256 ? p->n : 256), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = reinterpret_cast<encode_fn>(fn)(&p->tma_S, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, p->d_S, gdim, gstride, box,
+                                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                                 CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    p->tma_S_ok = (r == CUDA_SUCCESS);
+}
+
 template <typename T>
 static cudaError_t upload(T** dptr, const void* host, size_t count) {
     cudaError_t e = cudaMalloc((void**)dptr, count * sizeof(T));
@@ -320,6 +348,7 @@ int s2k_plan_create_impl(s2kit_cuda_plan** out, int bw, int variant, int max_bat
     p->chunk = chunk;
     CK(cudaMalloc((void**)&p->d_S, sizeof(double) * (size_t)chunk * 2 * n * n));
     CK(cudaMalloc((void**)&p->d_X, sizeof(double) * (size_t)chunk * n * 2 * bw));
+    make_plane_tensor_map(p);
     CK(cudaStreamSynchronize(p->stream));
     apply_table_l2_policy(p);
     *out = p;

@@ -1,5 +1,6 @@
 // s2k_internal.cuh -- plan object and kernel launch prototypes shared by the .cu files.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -94,6 +95,8 @@ struct s2kit_cuda_plan {
 
     // workspace for `chunk` functions
     double* d_S = nullptr;  // spectral planes  [chunk][2][n][n]
+    CUtensorMap tma_S;      // d_S as a 3-D tensor (latitude, order row, plane) with 8 x 256 x 1 boxes, 64-byte swizzle
+    bool tma_S_ok = false;
     double* d_X = nullptr;  // cosine planes    [chunk][n][2][bw]
     double* d_coef = nullptr;  // [chunk][2][bw*bw]   conv intermediates / staging
     double* d_coef2 = nullptr;
