@@ -177,6 +177,86 @@ __global__ void __launch_bounds__(N / 8 * LT) k_phi_fft_inv(const double* __rest
     }
 }
 
+// ------------------------------------------------------------------------------------------------ K6, TMA load
+// Mirror image of k_phi_fft_fwd_tma: the transposed gather of the LT = 8 latitude columns of every order row is done
+// by cp.async.bulk.tensor loads of 256-row boxes into 64B-swizzled staging tiles (completion on an mbarrier), the
+// transforms read their inputs from the staging tiles and then reuse the same shared memory for the FFT exchange.
+__device__ __forceinline__ void mbar_wait(unsigned mbar_addr, unsigned phase) {
+    unsigned done = 0;
+    unsigned long long spins = 0;
+    while (!done) {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(mbar_addr), "r"(phase)
+            : "memory");
+        if (++spins > (1ull << 28)) __trap();  // a lost TMA completion must not hang the device
+    }
+}
+
+template <int N>
+__global__ void __launch_bounds__(N) k_phi_fft_inv_tma(double* __restrict__ rdata, double* __restrict__ idata, long stride,
+                                                        int real_fmt, const double2* __restrict__ tw,
+                                                        const __grid_constant__ CUtensorMap tmap) {
+    constexpr int LT = 8, T8 = N / 8;
+    constexpr int RS = phi_row_stride(N, LT);
+    constexpr int ROWS = N < 256 ? N : 256;
+    constexpr int NBOX = N / ROWS;
+    constexpr int BOX_BYTES = ROWS * LT * 8;
+    constexpr int WORK_BYTES = (int)(sizeof(double2) * LT * RS) > 2 * NBOX * BOX_BYTES ? (int)(sizeof(double2) * LT * RS)
+                                                                                       : 2 * NBOX * BOX_BYTES;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    double2* sx = reinterpret_cast<double2*>(smem_raw);
+    const unsigned sbase = static_cast<unsigned>(__cvta_generic_to_shared(smem_raw));
+    const unsigned mbar = sbase + WORK_BYTES;  // 8-byte mbarrier behind the work area
+    const int tid = threadIdx.x, jj = tid / T8, t = tid % T8;
+    const int j0 = blockIdx.x * LT, f = blockIdx.y;
+    // REAL format only needs rows < bw (the rest are conjugate mirrors): one box when N = 512
+    const int nbox = (real_fmt && NBOX > 1) ? NBOX / 2 : NBOX;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(2 * nbox * BOX_BYTES)
+                     : "memory");
+        for (int part = 0; part < 2; ++part)
+            for (int h = 0; h < nbox; ++h)
+                asm volatile(
+                    "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::
+                        "r"(sbase + (unsigned)((part * NBOX + h) * BOX_BYTES)),
+                    "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(j0), "r"(h * ROWS), "r"(f * 2 + part), "r"(mbar)
+                    : "memory");
+    }
+    mbar_wait(mbar, 0);
+    // inverse DFT through the forward one: feed (im, re), read back (im, re)   (FST_semi_memo.c:350)
+    double xr[8], xi[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int idx = fft_in_index<N>(e, t);
+        const bool mirror = real_fmt && idx > N / 2;  // conjugate mirror of row n - m' (FST_semi_memo.c:333-341)
+        const int row = mirror ? N - idx : idx;
+        const int h = row / ROWS, r = row % ROWS;
+        const unsigned off = swz64((unsigned)(r * 64 + jj * 8));
+        double vr = *reinterpret_cast<const double*>(smem_raw + (0 * NBOX + h) * BOX_BYTES + off);
+        double vi = *reinterpret_cast<const double*>(smem_raw + (1 * NBOX + h) * BOX_BYTES + off);
+        if (idx == N / 2) vr = vi = 0.0;  // row bw is zero by definition (FST_semi_memo.c:283-284)
+        xr[e] = mirror ? -vi : vi;
+        xi[e] = vr;
+    }
+    __syncthreads();  // every transform has its inputs: the staging tiles become the exchange rows
+    fft_block<N>(xr, xi, sx + jj * RS, t, jj, tw);
+    double* rrow = rdata + (long)f * stride + (long)(j0 + jj) * N;
+    double* irow = idata + (long)f * stride + (long)(j0 + jj) * N;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        int k = fft_out_index<N>(e, t);
+        irow[k] = xr[e];
+        rrow[k] = xi[e];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ K2
 __device__ __forceinline__ int ridx_to_row(int ridx, int bw) { return ridx < bw ? ridx : ridx + 1; }
 
@@ -414,6 +494,17 @@ template <int N>
 static cudaError_t phi_inv_n(s2kit_cuda_plan* p, const double* G, double* rdata, double* idata, long stride, int nfun,
                              int real_fmt, const PlaneView& pv, int nrings) {
     constexpr int LT = (4096 / N) < 8 ? (4096 / N) : 8;
+    if constexpr (N <= 512) {
+        if (p->tma_S_ok && G == p->d_S && !pv.rowbase && nrings == N && nfun <= p->chunk) {
+            constexpr int RSX = phi_row_stride(N, 8);
+            size_t smem = std::max(sizeof(double2) * 8 * RSX, (size_t)2 * N * 8 * 8) + 16;
+            cudaError_t e = set_smem(k_phi_fft_inv_tma<N>, smem);
+            if (e != cudaSuccess) return e;
+            k_phi_fft_inv_tma<N><<<dim3(N / 8, nfun), N, smem, p->stream>>>(rdata, idata, stride, real_fmt, p->d_tw_n,
+                                                                              p->tma_S);
+            return cudaGetLastError();
+        }
+    }
     constexpr int RS = phi_row_stride(N, LT);
     size_t smem = sizeof(double2) * LT * RS;
     cudaError_t e = set_smem(k_phi_fft_inv<N, LT>, smem);
