@@ -77,9 +77,14 @@ __global__ void __launch_bounds__(N / 8 * LT) k_phi_fft_fwd(const double* __rest
 // 4 rows) off the LSU pipe that bounds the kernel (profiles/r1_ncu_summary.md).
 __device__ __forceinline__ unsigned swz64(unsigned byte_off) { return byte_off ^ (((byte_off >> 7) & 3u) << 4); }
 
+// PlaneView::lat_perm: latitude held at slot `pos` of a spectral-plane row
+__device__ __forceinline__ int lat_row(int pos, int n, int lat_perm) {
+    return !lat_perm ? pos : (pos < n / 2 ? 2 * pos : 2 * (n - 1 - pos) + 1);
+}
+
 template <int N>
 __global__ void __launch_bounds__(N) k_phi_fft_fwd_tma(const double* __restrict__ rdata, const double* __restrict__ idata,
-                                                        long stride, double scale, int rows_kept,
+                                                        long stride, double scale, int rows_kept, int lat_perm,
                                                         const double2* __restrict__ tw,
                                                         const __grid_constant__ CUtensorMap tmap) {
     constexpr int LT = 8, T8 = N / 8;
@@ -90,8 +95,9 @@ __global__ void __launch_bounds__(N) k_phi_fft_fwd_tma(const double* __restrict_
     double2* sx = reinterpret_cast<double2*>(smem_raw);  // exchange rows during the FFT, staging tiles afterwards
     const int tid = threadIdx.x, jj = tid / T8, t = tid % T8;
     const int j0 = blockIdx.x * LT, f = blockIdx.y;
-    const double* rrow = rdata + (long)f * stride + (long)(j0 + jj) * N;
-    const double* irow = idata + (long)f * stride + (long)(j0 + jj) * N;
+    const int jrow = lat_row(j0 + jj, N, lat_perm);  // grid row whose transform lands at latitude slot j0 + jj
+    const double* rrow = rdata + (long)f * stride + (long)jrow * N;
+    const double* irow = idata + (long)f * stride + (long)jrow * N;
     double xr[8], xi[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -196,7 +202,7 @@ __device__ __forceinline__ void mbar_wait(unsigned mbar_addr, unsigned phase) {
 
 template <int N>
 __global__ void __launch_bounds__(N) k_phi_fft_inv_tma(double* __restrict__ rdata, double* __restrict__ idata, long stride,
-                                                        int real_fmt, const double2* __restrict__ tw,
+                                                        int real_fmt, int lat_perm, const double2* __restrict__ tw,
                                                         const __grid_constant__ CUtensorMap tmap) {
     constexpr int LT = 8, T8 = N / 8;
     constexpr int RS = phi_row_stride(N, LT);
@@ -247,8 +253,9 @@ __global__ void __launch_bounds__(N) k_phi_fft_inv_tma(double* __restrict__ rdat
     }
     __syncthreads();  // every transform has its inputs: the staging tiles become the exchange rows
     fft_block<N>(xr, xi, sx + jj * RS, t, jj, tw);
-    double* rrow = rdata + (long)f * stride + (long)(j0 + jj) * N;
-    double* irow = idata + (long)f * stride + (long)(j0 + jj) * N;
+    const int jrow = lat_row(j0 + jj, N, lat_perm);
+    double* rrow = rdata + (long)f * stride + (long)jrow * N;
+    double* irow = idata + (long)f * stride + (long)jrow * N;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         int k = fft_out_index<N>(e, t);
@@ -282,42 +289,54 @@ __global__ void __launch_bounds__(N / 8 * FPB) k_dct_fwd(const double* __restric
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         int p = t + e * T8;
-        int j = (p < B) ? 2 * p : 2 * (N - 1 - p) + 1;
         double wj = __ldg(w + p);  // weights are stored in load order (s2k_host_reordered)
-        long at = (long)(j >> pv.seg_shift) * pv.seg_stride + (j & pv.seg_mask);
+        long at = p;               // lat_perm: the row already is in load order
+        if (!pv.lat_perm) {
+            int j = (p < B) ? 2 * p : 2 * (N - 1 - p) + 1;
+            at = (long)(j >> pv.seg_shift) * pv.seg_stride + (j & pv.seg_mask);
+        }
         xr[e] = __ldg(Sr + at) * wj;
         xi[e] = __ldg(Si + at) * wj;
     }
     fft_block<N>(xr, xi, sx, t, g, tw);
+    // Separation of the two real spectra needs Z[k] and Z[n-k], k < bw: Z[k] is still in this thread's registers, so
+    // only the upper half of the spectrum (indices > bw) goes through shared memory -- half a write and half a read
+    // per point instead of a full write and two reads.
+    constexpr int R = fft_last_radix(N);
     fft_sync<N>(g);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) sx[fft_pad(fft_out_index<N>(e, t))] = make_double2(xr[e], xi[e]);
+    for (int e = 0; e < 8; ++e)
+        if (fft_slot<R>(e) >= 4) sx[fft_pad(fft_out_index<N>(e, t) - B)] = make_double2(xr[e], xi[e]);
     fft_sync<N>(g);
     if (!live) return;
     double* Xr = X + (((long)f * N + mp) * 2) * B;
     double* Xi = Xr + B;
     const double s_all = 1.0 / sqrt(2.0 * (double)N);  // 1/sqrt(2*size), seminaive.c:174
-    // each thread finishes the pairs (2c, 2c+1): in the parity-split plane both land at slot c of their half, so a
-    // warp writes two fully coalesced runs
+    // consecutive lanes hold consecutive k: even and odd k go to slot k/2 of their half of the parity-split plane, so
+    // a warp writes two contiguous 128-byte runs per store
     constexpr int HALF = B / 2;
-    for (int c = t; c < HALF; c += T8) {
 #pragma unroll
-        for (int par = 0; par < 2; ++par) {
-            int k = 2 * c + par;
-            int nk = (N - k) & (N - 1);
-            const double2 za = sx[fft_pad(k)], zb = sx[fft_pad(nk)];
-            const double ar = za.x, ai = za.y, br = zb.x, bi = zb.y;
-            // V1 = (Z[k] + conj Z[n-k]) / 2 ; V2 = (Z[k] - conj Z[n-k]) / 2i ; REDFT10 = 2 Re(e^{-i pi k/2n} V)
-            double2 q = __ldg(qtab + k);
-            double y1 = q.x * (ar + br) + q.y * (ai - bi);
-            double y2 = q.x * (ai + bi) - q.y * (ar - br);
-            if (k == 0) {
-                y1 *= 0.70710678118654752440;  // M_SQRT1_2, seminaive.c:173
-                y2 *= 0.70710678118654752440;
-            }
-            Xr[par * HALF + c] = y1 * s_all;
-            Xi[par * HALF + c] = y2 * s_all;
+    for (int e = 0; e < 8; ++e) {
+        if (fft_slot<R>(e) >= 4) continue;
+        const int k = fft_out_index<N>(e, t);
+        const double ar = xr[e], ai = xi[e];
+        double br = ar, bi = ai;  // k = 0: Z[n] = Z[0]
+        if (k != 0) {
+            const double2 zb = sx[fft_pad(B - k)];  // Z[n - k] sits at (n - k) - bw
+            br = zb.x;
+            bi = zb.y;
         }
+        // V1 = (Z[k] + conj Z[n-k]) / 2 ; V2 = (Z[k] - conj Z[n-k]) / 2i ; REDFT10 = 2 Re(e^{-i pi k/2n} V)
+        const double2 q = __ldg(qtab + k);
+        double y1 = q.x * (ar + br) + q.y * (ai - bi);
+        double y2 = q.x * (ai + bi) - q.y * (ar - br);
+        if (k == 0) {
+            y1 *= 0.70710678118654752440;  // M_SQRT1_2, seminaive.c:173
+            y2 *= 0.70710678118654752440;
+        }
+        const int slot = (k & 1) * HALF + (k >> 1);
+        Xr[slot] = y1 * s_all;
+        Xi[slot] = y2 * s_all;
     }
 }
 
@@ -366,9 +385,12 @@ __global__ void __launch_bounds__(N / 8 * FPB) k_dct_inv(const double* __restric
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         int i = fft_out_index<N>(e, t);
-        int j = (i < B) ? 2 * i : 2 * (N - 1 - i) + 1;
         double s = (m & 1) ? __ldg(sinv + i) * sign : sign;  // sines stored in output order (s2k_host_reordered)
-        long at = (long)(j >> pv.seg_shift) * pv.seg_stride + (j & pv.seg_mask);
+        long at = i;  // lat_perm: the row is kept in output order
+        if (!pv.lat_perm) {
+            int j = (i < B) ? 2 * i : 2 * (N - 1 - i) + 1;
+            at = (long)(j >> pv.seg_shift) * pv.seg_stride + (j & pv.seg_mask);
+        }
         Gr[at] = xi[e] * s;  // Re z -> column a (real part)
         Gi[at] = xr[e] * s;  // Im z -> column b (imaginary part)
     }
@@ -468,17 +490,18 @@ static cudaError_t phi_fwd_n(s2kit_cuda_plan* p, const double* rdata, const doub
     constexpr int LT = (4096 / N) < 8 ? (4096 / N) : 8;
     if constexpr (N <= 512) {
         // ordinary plane in the plan's own workspace: transposed write through the TMA
-        if (p->tma_S_ok && S == p->d_S && !pv.rowbase && nrings == N && nfun <= p->chunk) {
+        if (tma_planes_ok(p, nfun) && S == p->d_S && !pv.rowbase && nrings == N) {
             constexpr int RSX = phi_row_stride(N, 8);
             size_t smem = std::max(sizeof(double2) * 8 * RSX, (size_t)2 * N * 8 * 8);
             cudaError_t e = set_smem(k_phi_fft_fwd_tma<N>, smem);
             if (e != cudaSuccess) return e;
             double scale = sqrt(2.0 * M_PI) / (double)N;
             k_phi_fft_fwd_tma<N><<<dim3(N / 8, nfun), N, smem, p->stream>>>(rdata, idata, stride, scale, rows_kept,
-                                                                              p->d_tw_n, p->tma_S);
+                                                                              pv.lat_perm, p->d_tw_n, p->tma_S);
             return cudaGetLastError();
         }
     }
+    if (pv.lat_perm) return cudaErrorInvalidValue;  // only the TMA variant writes the reordered latitude layout
     constexpr int RS = phi_row_stride(N, LT);
     size_t smem = sizeof(double2) * LT * RS;
     cudaError_t e = set_smem(k_phi_fft_fwd<N, LT>, smem);
@@ -495,16 +518,17 @@ static cudaError_t phi_inv_n(s2kit_cuda_plan* p, const double* G, double* rdata,
                              int real_fmt, const PlaneView& pv, int nrings) {
     constexpr int LT = (4096 / N) < 8 ? (4096 / N) : 8;
     if constexpr (N <= 512) {
-        if (p->tma_S_ok && G == p->d_S && !pv.rowbase && nrings == N && nfun <= p->chunk) {
+        if (tma_planes_ok(p, nfun) && G == p->d_S && !pv.rowbase && nrings == N) {
             constexpr int RSX = phi_row_stride(N, 8);
             size_t smem = std::max(sizeof(double2) * 8 * RSX, (size_t)2 * N * 8 * 8) + 16;
             cudaError_t e = set_smem(k_phi_fft_inv_tma<N>, smem);
             if (e != cudaSuccess) return e;
-            k_phi_fft_inv_tma<N><<<dim3(N / 8, nfun), N, smem, p->stream>>>(rdata, idata, stride, real_fmt, p->d_tw_n,
-                                                                              p->tma_S);
+            k_phi_fft_inv_tma<N><<<dim3(N / 8, nfun), N, smem, p->stream>>>(rdata, idata, stride, real_fmt, pv.lat_perm,
+                                                                              p->d_tw_n, p->tma_S);
             return cudaGetLastError();
         }
     }
+    if (pv.lat_perm) return cudaErrorInvalidValue;
     constexpr int RS = phi_row_stride(N, LT);
     size_t smem = sizeof(double2) * LT * RS;
     cudaError_t e = set_smem(k_phi_fft_inv<N, LT>, smem);
@@ -555,7 +579,11 @@ static cudaError_t dct_inv_n(s2kit_cuda_plan* p, const double* V, double* G, int
         default: return cudaErrorInvalidValue;   \
     }
 
-static PlaneView default_view(int n) {
+bool tma_planes_ok(const s2kit_cuda_plan* p, int nfun) {
+    return p->tma_S_ok && p->fast && p->n >= 64 && p->n <= 512 && nfun <= p->chunk;
+}
+
+PlaneView default_view(int n) {
     PlaneView v;
     v.rowbase = nullptr;
     v.rowlist = nullptr;
@@ -565,6 +593,7 @@ static PlaneView default_view(int n) {
     v.seg_shift = 30;  // j >> 30 == 0: a row is one segment
     v.seg_mask = 0x3fffffff;
     v.nrings = n;
+    v.lat_perm = 0;
     return v;
 }
 

@@ -438,9 +438,12 @@ static int fst_device(s2kit_cuda_plan* p, const double* rdata, const double* ida
         const double* id = idata + (long)c0 * data_stride;
         double* rc = rco + (long)c0 * coef_stride;
         double* ic = ico + (long)c0 * coef_stride;
-        CK(s2k::launch_phi_fft_fwd(p, rd, id, data_stride, p->d_S, nf, fmt));
         const bool fused = s2k::fused_supported(p, nf, fmt);
-        if (!fused) CK(s2k::launch_dct_fwd(p, p->d_S, p->d_X, nf, 0, nrows, fmt));
+        // TMA variant of K1 available: keep the planes' latitudes in the DCT's own load order (PlaneView::lat_perm)
+        s2k::PlaneView pv = s2k::default_view(p->n);
+        pv.lat_perm = !fused && s2k::tma_planes_ok(p, nf);
+        CK(s2k::launch_phi_fft_fwd(p, rd, id, data_stride, p->d_S, nf, fmt, &pv));
+        if (!fused) CK(s2k::launch_dct_fwd(p, p->d_S, p->d_X, nf, 0, nrows, fmt, &pv));
         for (const OrderGroup& g : order_groups(p, 0, bw)) {
             if (p->variant == S2KIT_CUDA_FLY) CK(s2k::launch_table_gen(p, p->d_table, g.shift, g.lo, g.hi));
             if (fused)
@@ -463,6 +466,8 @@ static int inv_fst_device(s2kit_cuda_plan* p, const double* rco, const double* i
         double* rd = rdata + (long)c0 * data_stride;
         double* id = idata + (long)c0 * data_stride;
         const bool fused = s2k::fused_supported(p, nf, fmt);
+        s2k::PlaneView pv = s2k::default_view(p->n);
+        pv.lat_perm = !fused && s2k::tma_planes_ok(p, nf);
         for (const OrderGroup& g : order_groups(p, 0, bw)) {
             const double* tt = p->variant == S2KIT_CUDA_FLY ? p->d_table : p->d_table_t;
             if (p->variant == S2KIT_CUDA_FLY) CK(s2k::launch_table_gen(p, p->d_table, g.shift, g.lo, g.hi, 1));
@@ -471,8 +476,8 @@ static int inv_fst_device(s2kit_cuda_plan* p, const double* rco, const double* i
             else
                 CK(s2k::launch_legendre_inv(p, tt, g.shift, rc, ic, coef_stride, p->d_X, nf, g.lo, g.hi, fmt));
         }
-        if (!fused) CK(s2k::launch_dct_inv(p, p->d_X, p->d_S, nf, 0, nrows, fmt));
-        CK(s2k::launch_phi_fft_inv(p, p->d_S, rd, id, data_stride, nf, fmt));
+        if (!fused) CK(s2k::launch_dct_inv(p, p->d_X, p->d_S, nf, 0, nrows, fmt, &pv));
+        CK(s2k::launch_phi_fft_inv(p, p->d_S, rd, id, data_stride, nf, fmt, &pv));
     }
     return 0;
 }

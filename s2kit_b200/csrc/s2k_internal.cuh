@@ -41,6 +41,11 @@ struct PlaneView {
     long seg_stride;      // K2/K5: a row of 2bw latitudes is cut into segments of (seg_mask+1) entries, this far apart
     int seg_shift, seg_mask;
     int nrings;           // K1/K6: latitude rows handled by this launch
+    // Latitude order inside a row.  0: natural (j).  1: the DCT kernels' even/odd-reordered order -- position i holds
+    // latitude 2i (i < bw) or 2(2bw-1-i)+1 (i >= bw), i.e. exactly the sequence K2 feeds its FFT and K5's FFT emits, so
+    // K2 loads / K5 stores contiguous runs.  Only the TMA variants of K1 / K6 write / read it (a tile of 8 positions is
+    // 8 even or 8 odd grid rows); it is private to one fst / inv_fst call.
+    int lat_perm = 0;
 };
 
 struct ProfileSlot {
@@ -123,6 +128,11 @@ cudaError_t ensure_smem(const void* kernel, size_t bytes);
 // RAII-less profiling bracket: begin returns a slot index (or -1)
 int prof_begin(s2kit_cuda_plan* p, int kind);
 void prof_end(s2kit_cuda_plan* p, int slot);
+
+// the ordinary [part][order row][latitude] plane of bandwidth n/2
+PlaneView default_view(int n);
+// true when K1 / K6 can use their TMA variants on the plan's own spectral workspace (then lat_perm = 1 is allowed)
+bool tma_planes_ok(const s2kit_cuda_plan* p, int nfun);
 
 // ---- launchers (each checks cudaGetLastError and returns it) -----------------------------------------
 // K1 / K6: longitude FFT.  S layout [f][part][order row][latitude]
