@@ -130,37 +130,42 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_fwd(
     const double* tbase = table + (order_start[m] - table_shift) * 64 + lane * 2;
     const int g = lane >> 2, q4 = lane & 3;
     if constexpr (NC >= 32) {
-        // Batched panels: one item per (parity, row tile) -- finer-grained balance over the eight warps measured ~4 %
-        // faster here than the paired items below.
-        // items sorted by decreasing cost: (parity 0, rt), (parity 1, rt) for rt = nrt-1 .. 0; snake over the slots
+        // Batched panels: one item = two adjacent row tiles (rt, rt - 1) of one parity block, which share every panel
+        // fragment (fwd_row_tile2); an odd block's lightest tile rides alone.  Items sorted by decreasing cost --
+        // (parity 0, pair i), (parity 1, pair i) from the longest rows down -- and dealt in snake order.
         const int nslots = LEG_WARPS * gridDim.z, slot = blockIdx.z * LEG_WARPS + warp;
-        for (int round = 0;; ++round) {
+        const int npair0 = (mb0.nrt + 1) / 2;  // mb0.nrt >= mb1.nrt
+        for (int round = 0; round * nslots < 2 * npair0; ++round) {
             const int q = snake_item(round, slot, nslots);
-            if (round * nslots >= 2 * mb0.nrt) break;
+            if (q >= 2 * npair0) continue;
             const int p = q & 1;
             const BlockMeta mb = p ? mb1 : mb0;
-            const int rt = mb0.nrt - 1 - (q >> 1);  // mb0.nrt >= mb1.nrt
-            if (q >= 2 * mb0.nrt || rt >= mb.nrt) continue;
-            const int ctn = tiles_in_row(mb, rt);
-            const double* tp = tbase + (uint64_t)srt[(p ? mb0.nrt : 0) + rt] * 64;
-            const double* xp = Xs + (p * PC + (PC < NC ? (g & (PC - 1)) : g)) * CS + q4;
-
-            double acc[NC / 8][2];
+            const int rt1 = mb.nrt - 1 - 2 * (q >> 1), rt0 = rt1 - 1;  // rt0 = -1: single tile
+            if (rt1 < 0) continue;
+            const uint32_t* sr = srt + (p ? mb0.nrt : 0);
+            const double* xp = Xs + (p * PC + g) * CS + q4;
+            double acc0[NC / 8][2], acc1[NC / 8][2];
     #pragma unroll
-            for (int j = 0; j < NC / 8; ++j) acc[j][0] = acc[j][1] = 0.0;
-            fwd_row_tile<NC>(tp, xp, CS, ctn, acc, PC < NC && g >= PC);
+            for (int j = 0; j < NC / 8; ++j) acc0[j][0] = acc0[j][1] = acc1[j][0] = acc1[j][1] = 0.0;
+            if (rt0 >= 0)
+                fwd_row_tile2<NC>(tbase + (uint64_t)sr[rt0] * 64, tiles_in_row(mb, rt0), tbase + (uint64_t)sr[rt1] * 64,
+                                  tiles_in_row(mb, rt1), xp, CS, acc0, acc1);
+            else
+                fwd_row_tile<NC>(tbase + (uint64_t)sr[rt1] * 64, xp, CS, tiles_in_row(mb, rt1), acc1);
 
-            // ---- epilogue: lane holds rows r = 8rt + g, columns 8j + 2 q4 + {0,1}; destinations come from the
-            // per-column table built once per CTA (the index arithmetic used to cost as many instructions as the main loop)
-            const int r = 8 * rt + g;
-            if (r < mb.rows) {
+            // ---- epilogue: lane holds rows 8 rt + g of both tiles, columns 8j + 2 q4 + {0,1}; destinations come from
+            // the per-column table built once per CTA
+    #pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = 8 * (h ? rt1 : rt0) + g;
+                if ((h == 0 && rt0 < 0) || r >= mb.rows) continue;
                 const int off = p + 2 * r;  // l - m
     #pragma unroll
                 for (int j = 0; j < NC / 8; ++j) {
     #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const ColOut co = cinfo[8 * j + 2 * q4 + e];
-                        const double v = acc[j][e];
+                        const double v = h ? acc1[j][e] : acc0[j][e];
                         if (co.dst) co.dst[off] = v * co.scale;
                         if (co.mirror) co.mirror[off] = v * co.mscale;
                     }
@@ -264,6 +269,42 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_inv(
     const int g = lane >> 2, q4 = lane & 3;
 
     const int nslots = LEG_WARPS * gridDim.z, slot = blockIdx.z * LEG_WARPS + warp;
+    if constexpr (NC >= 32) {
+        // Batched panels: one item = column tiles (2i, 2i + 1) of one parity block, which share every coefficient
+        // fragment (inv_col_tile2); low column tiles (most rows) first.
+        const int npair = (nct + 1) / 2;
+        for (int round = 0; round * nslots < 2 * npair; ++round) {
+            const int q = snake_item(round, slot, nslots);
+            if (q >= 2 * npair) continue;
+            const int p = q & 1, ct = 2 * (q >> 1);
+            const BlockMeta mb = p ? mb1 : mb0;
+            double acc0[NC / 8][2], acc1[NC / 8][2];
+#pragma unroll
+            for (int j = 0; j < NC / 8; ++j) acc0[j][0] = acc0[j][1] = acc1[j][0] = acc1[j][1] = 0.0;
+            inv_col_tile2<NC>(tbase, srt + (p ? mb0.nrt : 0), mb, ct, Cs + (p * PC + g) * CS + q4, CS, acc0, acc1);
+            // ---- epilogue: lane holds column 8j + g, cosine slots c = 8 (ct + h) + 2 q4 + {0,1} of parity p, adjacent in
+            // the parity-split plane
+            const int hp = p ? bw / 2 : (bw + 1) / 2;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c0 = 8 * (ct + h) + 2 * q4;
+#pragma unroll
+                for (int j = 0; j < NC / 8; ++j) {
+                    double* dst = cinfo[8 * j + g].dst;
+                    if (!dst) continue;
+                    double* d = dst + p * ((bw + 1) / 2) + c0;
+                    const double v0 = h ? acc1[j][0] : acc0[j][0], v1 = h ? acc1[j][1] : acc0[j][1];
+                    if (c0 + 1 < hp && ((bw & 3) == 0)) {
+                        *reinterpret_cast<double2*>(d) = make_double2(v0, v1);
+                    } else {
+                        if (c0 < hp) d[0] = v0;
+                        if (c0 + 1 < hp) d[1] = v1;
+                    }
+                }
+            }
+        }
+        return;
+    }
     for (int round = 0; round * nslots < 2 * nct; ++round) {
         const int q = snake_item(round, slot, nslots);
         if (q >= 2 * nct) continue;
