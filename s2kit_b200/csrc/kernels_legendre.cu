@@ -53,7 +53,7 @@ __device__ __forceinline__ void store_pair(double* run, double scale, int r, int
 // other half of the 8-wide MMA tile is fed zeros from registers so the panel -- and with it the shared memory per
 // CTA -- halves and three CTAs fit an SM even at bw = 2048.
 template <int NC, int PC>
-__global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_fwd(
+__global__ void __launch_bounds__(LEG_WARPS * 32, NC >= 32 ? 2 : 3) k_legendre_fwd(
     const double* __restrict__ table, const uint64_t* __restrict__ order_start, uint64_t table_shift,
     const BlockMeta* __restrict__ meta, const uint32_t* __restrict__ rt_start, const double* __restrict__ X,
     double* __restrict__ rco, double* __restrict__ ico, long coef_stride, int bw, int nfun, int m_lo, int real_fmt,
@@ -69,6 +69,8 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_fwd(
 
     prefetch_order_l2(table + (order_start[m] - table_shift) * 64, order_start[m + 1] - order_start[m], tid, blockDim.x,
                       l2pf_cap);
+    // block metadata first: the loads fly while the panel is staged
+    const BlockMeta mb0 = meta[2 * m], mb1 = meta[2 * m + 1];
     // ---- stage the X panel, de-interleaved by cosine-index parity; dead columns and the pad slots are zero
     const int half = (bw + 1) / 2;
     for (int col = warp; col < PC; col += LEG_WARPS) {
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_fwd(
         double* d0 = Xs + col * CS;
         double* d1 = Xs + (PC + col) * CS;
         if (f >= nfun || (sgn && m == 0)) {
-            for (int c = lane; c < CS; c += 32) d0[c] = d1[c] = 0.0;
+            for (int c = lane; c < half; c += 32) d0[c] = d1[c] = 0.0;
             continue;
         }
         int mp = sgn ? n - m : m;
@@ -93,17 +95,17 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_fwd(
             for (int c = lane; c < half; c += 32) cp_async8(d0 + c, src + c);
             for (int c = lane; c < bw / 2; c += 32) cp_async8(d1 + c, src + half + c);
         }
-        for (int c = half + lane; c < CS; c += 32) d0[c] = d1[c] = 0.0;
         if ((bw & 1) && lane == 0) d1[half - 1] = 0.0;  // odd bw: parity 1 has one entry less
     }
-    cp_async_wait_all();
-    __syncthreads();
-
-    const BlockMeta mb0 = meta[2 * m], mb1 = meta[2 * m + 1];
+    {
+        // pad slots [half, CS) of every panel column
+        const int padw = CS - half;
+        for (int i = tid; i < 2 * PC * padw; i += blockDim.x) Xs[(i / padw) * CS + half + i % padw] = 0.0;
+    }
     const int total = mb0.nrt + mb1.nrt;
     uint32_t* srt = reinterpret_cast<uint32_t*>(Xs + 2 * PC * CS);  // row-tile starts of both parity blocks
     ColOut* cinfo = reinterpret_cast<ColOut*>(srt + ((bw / 8 + 8 + 3) & ~3));
-    if (tid < NC) {
+    if (NC < 32 && tid < NC) {
         // where column `tid` of the panel lands: f^(+-m, l) of function f, re or im array, with its sign
         ColOut co = {nullptr, nullptr, 1.0, 1.0};
         const int fl = tid / cols_per_fn, sub = tid % cols_per_fn, f = f0 + fl;
@@ -126,6 +128,7 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_fwd(
     }
     for (int i = tid; i < total; i += blockDim.x)
         srt[i] = rt_start[(i < mb0.nrt ? mb0.rt_base : mb1.rt_base - mb0.nrt) + i];
+    cp_async_wait_all();
     __syncthreads();
     const double* tbase = table + (order_start[m] - table_shift) * 64 + lane * 2;
     const int g = lane >> 2, q4 = lane & 3;
@@ -148,26 +151,42 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_fwd(
     #pragma unroll
             for (int j = 0; j < NC / 8; ++j) acc0[j][0] = acc0[j][1] = acc1[j][0] = acc1[j][1] = 0.0;
             if (rt0 >= 0)
-                fwd_row_tile2<NC>(tbase + (uint64_t)sr[rt0] * 64, tiles_in_row(mb, rt0), tbase + (uint64_t)sr[rt1] * 64,
+                fwd_row_tile2<NC, LEG_PF2_FWD>(tbase + (uint64_t)sr[rt0] * 64, tiles_in_row(mb, rt0), tbase + (uint64_t)sr[rt1] * 64,
                                   tiles_in_row(mb, rt1), xp, CS, acc0, acc1);
             else
                 fwd_row_tile<NC>(tbase + (uint64_t)sr[rt1] * 64, xp, CS, tiles_in_row(mb, rt1), acc1);
 
-            // ---- epilogue: lane holds rows 8 rt + g of both tiles, columns 8j + 2 q4 + {0,1}; destinations come from
-            // the per-column table built once per CTA
+            // ---- epilogue: lane holds rows 8 rt + g of both tiles, columns 8j + 2 q4 + {0,1}.  Column c of the panel is
+            // (function f0 + c / cpf, sign, part = c & 1), so the lane's eight destinations differ only by the function
+            // and the re / im array: closed form, no per-column table (its shared-memory reads cost more wavefronts
+            // than the main loop's fragments, profiles/r2_ncu_legendre.md).  The signs are +-1: flip the sign bit on the
+            // integer pipe instead of a DMUL that competes with the DMMAs.
+            const int sgn = real_fmt ? 0 : (q4 & 1);
+            const int fl0 = real_fmt ? q4 : (q4 >> 1), flstep = real_fmt ? 4 : 2;
+            const long run0 = (long)(f0 + fl0) * coef_stride + (sgn ? coef_base(-m, bw) : coef_base(m, bw));
+            const long mrun0 = (long)(f0 + fl0) * coef_stride + coef_base(-m, bw);
+            const unsigned long long flip = (sgn && (m & 1)) ? 0x8000000000000000ull : 0ull;  // (-1)^m, FST_semi_memo.c:181-186
+            const bool live_sign = !(sgn && m == 0);
+            const bool mirror = real_fmt && m > 0;  // f^(-m,l) = (-1)^m conj f^(m,l), FST_semi_memo.c:131-145
     #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int r = 8 * (h ? rt1 : rt0) + g;
-                if ((h == 0 && rt0 < 0) || r >= mb.rows) continue;
+                if ((h == 0 && rt0 < 0) || r >= mb.rows || !live_sign) continue;
                 const int off = p + 2 * r;  // l - m
     #pragma unroll
                 for (int j = 0; j < NC / 8; ++j) {
+                    if (f0 + fl0 + j * flstep >= nfun) continue;
     #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        const ColOut co = cinfo[8 * j + 2 * q4 + e];
-                        const double v = h ? acc1[j][e] : acc0[j][e];
-                        if (co.dst) co.dst[off] = v * co.scale;
-                        if (co.mirror) co.mirror[off] = v * co.mscale;
+                        const unsigned long long bits =
+                            (unsigned long long)__double_as_longlong(h ? acc1[j][e] : acc0[j][e]);
+                        double* arr = e ? ico : rco;
+                        arr[run0 + (long)j * flstep * coef_stride + off] = __longlong_as_double((long long)(bits ^ flip));
+                        if (mirror) {
+                            const unsigned long long mflip = ((m & 1) ^ e) ? 0x8000000000000000ull : 0ull;
+                            arr[mrun0 + (long)j * flstep * coef_stride + off] =
+                                __longlong_as_double((long long)(bits ^ mflip));
+                        }
                     }
                 }
             }
@@ -230,6 +249,7 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_inv(
 
     prefetch_order_l2(table + (order_start[m] - table_shift) * 64, order_start[m + 1] - order_start[m], tid, blockDim.x,
                       l2pf_cap);
+    const BlockMeta mb0 = meta[2 * m], mb1 = meta[2 * m + 1];  // in flight while the panel is staged
     const int base_pos = coef_base(m, bw), base_neg = coef_base(-m, bw);
     for (int col = warp; col < PC; col += LEG_WARPS) {
         int fl = col / cols_per_fn, sub = col % cols_per_fn;
@@ -247,14 +267,10 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_inv(
         for (int c = h0 + lane; c < CS; c += 32) d0[c] = 0.0;
         for (int c = h1 + lane; c < CS; c += 32) d1[c] = 0.0;
     }
-    cp_async_wait_all();
-    __syncthreads();
-
-    const BlockMeta mb0 = meta[2 * m], mb1 = meta[2 * m + 1];
     const int nct = (((bw + 1) / 2) + 7) >> 3;  // column tiles needed to cover every k < bw of one parity
     uint32_t* srt = reinterpret_cast<uint32_t*>(Cs + 2 * PC * CS);
     ColOut* cinfo = reinterpret_cast<ColOut*>(srt + ((bw / 8 + 8 + 3) & ~3));
-    if (tid < NC) {
+    if (NC < 32 && tid < NC) {
         ColOut co = {nullptr, nullptr, 1.0, 1.0};
         const int fl = tid / cols_per_fn, sub = tid % cols_per_fn, f = f0 + fl;
         const int sgn = real_fmt ? 0 : (sub >> 1), part = sub & 1;
@@ -264,6 +280,7 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_inv(
     }
     for (int i = tid; i < mb0.nrt + mb1.nrt; i += blockDim.x)
         srt[i] = rt_start[(i < mb0.nrt ? mb0.rt_base : mb1.rt_base - mb0.nrt) + i];
+    cp_async_wait_all();
     __syncthreads();
     const double* tbase = table + (order_start[m] - table_shift) * 64 + lane * 2;  // B-fragment-ordered tiles
     const int g = lane >> 2, q4 = lane & 3;
@@ -281,18 +298,21 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_inv(
             double acc0[NC / 8][2], acc1[NC / 8][2];
 #pragma unroll
             for (int j = 0; j < NC / 8; ++j) acc0[j][0] = acc0[j][1] = acc1[j][0] = acc1[j][1] = 0.0;
-            inv_col_tile2<NC>(tbase, srt + (p ? mb0.nrt : 0), mb, ct, Cs + (p * PC + g) * CS + q4, CS, acc0, acc1);
+            inv_col_tile2<NC, LEG_PF2_INV>(tbase, srt + (p ? mb0.nrt : 0), mb, ct, Cs + (p * PC + g) * CS + q4, CS, acc0, acc1);
             // ---- epilogue: lane holds column 8j + g, cosine slots c = 8 (ct + h) + 2 q4 + {0,1} of parity p, adjacent in
-            // the parity-split plane
+            // the parity-split plane.  Column c = (function f0 + c / cpf, sign, part): closed-form destinations.
             const int hp = p ? bw / 2 : (bw + 1) / 2;
+            const int part = g & 1, sgn = real_fmt ? 0 : ((g >> 1) & 1);
+            const int fl0 = real_fmt ? (g >> 1) : (g >> 2), flstep = real_fmt ? 4 : 2;
+            if (sgn && m == 0) continue;
+            double* row0 = V + (((long)(f0 + fl0) * n + (sgn ? n - m : m)) * 2 + part) * bw + p * ((bw + 1) / 2);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int c0 = 8 * (ct + h) + 2 * q4;
 #pragma unroll
                 for (int j = 0; j < NC / 8; ++j) {
-                    double* dst = cinfo[8 * j + g].dst;
-                    if (!dst) continue;
-                    double* d = dst + p * ((bw + 1) / 2) + c0;
+                    if (f0 + fl0 + j * flstep >= nfun) continue;
+                    double* d = row0 + (long)j * flstep * n * 2 * bw + c0;
                     const double v0 = h ? acc1[j][0] : acc0[j][0], v1 = h ? acc1[j][1] : acc0[j][1];
                     if (c0 + 1 < hp && ((bw & 3) == 0)) {
                         *reinterpret_cast<double2*>(d) = make_double2(v0, v1);

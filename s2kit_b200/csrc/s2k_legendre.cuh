@@ -163,24 +163,27 @@ __device__ __forceinline__ void inv_col_tile(const double* __restrict__ tbase, c
 // The panel fragments come from shared memory: one 64-bit load per lane and DMMA, which at NC = 32 keeps the LSU /
 // shared-memory pipe busier than the FP64 tensor pipe (profiles/r1_ncu_summary.md: 71-88 % vs 53-55 %).  Handling TWO
 // table tiles that need the same panel fragments per step -- two adjacent row tiles of one parity in the forward
-// direction, two adjacent column tiles in the inverse -- halves that traffic.  Two tiles of register prefetch per
-// stream: with up to 24 warps per SM sharing the DMMA pipe, two tiles (16-32 DMMAs) cover an L2 hit.
-constexpr int LEG_PF2 = 2;
+// direction, two adjacent column tiles in the inverse -- halves that traffic.  Four tiles of register prefetch per
+// stream (two left the first DMMA of every step waiting ~30 % of the step on the tile load, ncu source view); the
+// kernels give up the third CTA per SM for the registers (128 instead of 80, which also stops ptxas from
+// rematerialising the panel address from S2R / S2UR in every step).
+constexpr int LEG_PF2_FWD = 4;  // k_legendre_fwd: 2 CTAs per SM, 128 registers
+constexpr int LEG_PF2_INV = 2;  // k_legendre_inv: measured faster with 3 CTAs per SM (80 registers) and two tiles
 
 // Forward: row tiles rt (tp0, ctn0 column tiles) and rt + 1 (tp1, ctn1 >= ctn0) of one parity block.
-template <int NC>
+template <int NC, int PF>
 __device__ __forceinline__ void fwd_row_tile2(const double* __restrict__ tp0, int ctn0, const double* __restrict__ tp1,
                                               int ctn1, const double* xp, int CS, double (&acc0)[NC / 8][2],
                                               double (&acc1)[NC / 8][2]) {
-    double2 a0[LEG_PF2], a1[LEG_PF2];
+    double2 a0[PF], a1[PF];
 #pragma unroll
-    for (int u = 0; u < LEG_PF2; ++u) {
+    for (int u = 0; u < PF; ++u) {
         a0[u] = __ldg(reinterpret_cast<const double2*>(tp0 + min(u, ctn0 - 1) * 64));
         a1[u] = __ldg(reinterpret_cast<const double2*>(tp1 + min(u, ctn1 - 1) * 64));
     }
-    for (int ct0 = 0; ct0 < ctn1; ct0 += LEG_PF2) {
+    for (int ct0 = 0; ct0 < ctn1; ct0 += PF) {
 #pragma unroll
-        for (int u = 0; u < LEG_PF2; ++u) {
+        for (int u = 0; u < PF; ++u) {
             const int ct = ct0 + u;
             if (ct < ctn1) {
                 double b[NC / 8][2];
@@ -201,8 +204,8 @@ __device__ __forceinline__ void fwd_row_tile2(const double* __restrict__ tp0, in
                 }
 #pragma unroll
                 for (int j = 0; j < NC / 8; ++j) dmma(acc1[j], a1[u].y, b[j][1]);
-                a0[u] = __ldg(reinterpret_cast<const double2*>(tp0 + min(ct + LEG_PF2, ctn0 - 1) * 64));
-                a1[u] = __ldg(reinterpret_cast<const double2*>(tp1 + min(ct + LEG_PF2, ctn1 - 1) * 64));
+                a0[u] = __ldg(reinterpret_cast<const double2*>(tp0 + min(ct + PF, ctn0 - 1) * 64));
+                a1[u] = __ldg(reinterpret_cast<const double2*>(tp1 + min(ct + PF, ctn1 - 1) * 64));
             }
         }
     }
@@ -217,7 +220,7 @@ __device__ __forceinline__ int first_row_tile_reaching(const BlockMeta& mb, int 
 }
 
 // Inverse: column tiles ct and ct + 1 of one parity block; the coefficient fragments of a row tile serve both.
-template <int NC>
+template <int NC, int PF>
 __device__ __forceinline__ void inv_col_tile2(const double* __restrict__ tbase, const uint32_t* srt, const BlockMeta& mb,
                                               int ct, const double* cp, int CS, double (&acc0)[NC / 8][2],
                                               double (&acc1)[NC / 8][2]) {
@@ -225,17 +228,17 @@ __device__ __forceinline__ void inv_col_tile2(const double* __restrict__ tbase, 
     const int rt_min1 = first_row_tile_reaching(mb, ct + 1);  // >= rt_min: rows only grow
     const int cnt = mb.nrt - rt_min;
     if (cnt <= 0) return;
-    double2 b0[LEG_PF2], b1[LEG_PF2];
+    double2 b0[PF], b1[PF];
 #pragma unroll
-    for (int u = 0; u < LEG_PF2; ++u) {
+    for (int u = 0; u < PF; ++u) {
         const int rt = rt_min + min(u, cnt - 1);
         const double* t = tbase + ((uint64_t)srt[rt] + ct) * 64;
         b0[u] = __ldg(reinterpret_cast<const double2*>(t));
         b1[u] = __ldg(reinterpret_cast<const double2*>(t + (rt >= rt_min1 ? 64 : 0)));
     }
-    for (int i0 = 0; i0 < cnt; i0 += LEG_PF2) {
+    for (int i0 = 0; i0 < cnt; i0 += PF) {
 #pragma unroll
-        for (int u = 0; u < LEG_PF2; ++u) {
+        for (int u = 0; u < PF; ++u) {
             const int i = i0 + u;
             if (i < cnt) {
                 const int rt = rt_min + i;
@@ -258,7 +261,7 @@ __device__ __forceinline__ void inv_col_tile2(const double* __restrict__ tbase, 
 #pragma unroll
                     for (int j = 0; j < NC / 8; ++j) dmma(acc1[j], a[j][1], b1[u].y);
                 }
-                const int rn = rt_min + min(i + LEG_PF2, cnt - 1);
+                const int rn = rt_min + min(i + PF, cnt - 1);
                 const double* t = tbase + ((uint64_t)srt[rn] + ct) * 64;
                 b0[u] = __ldg(reinterpret_cast<const double2*>(t));
                 b1[u] = __ldg(reinterpret_cast<const double2*>(t + (rn >= rt_min1 ? 64 : 0)));
