@@ -1,0 +1,338 @@
+// kernels_pipe.cu -- the batched forward path as ONE persistent, warp-specialised kernel per launch: K2 + K3 fused.
+//
+//   weights . DCT-II(2bw) . triangular contraction . coefficient placement
+//   (DLTSemi, src/legendre_transform/seminaive.c:153-198, inside the m-loops of FSTSemiMemo,
+//    src/FST_semi_memo.c:96-108,131-145,175-201)
+//
+// Why: the separate kernels were bound by phases, not by a pipe (profiles/r1_ncu_legendre_pipeline.md).  A CTA of
+// k_legendre_fwd spends ~55 % of its warp time outside the DMMA loop -- waiting for its panel (DRAM latency + 64 KB),
+// for the first table tiles, in the epilogue -- and with two or three CTAs per SM the FP64 tensor pipe idles whenever all
+// of them are in such a phase (DMMA pipe 56 % active).  One warp per SM sub-partition with >= 2 independent accumulators
+// already saturates the pipe (tools/probes/dmma_probe.cu), so what is needed is not occupancy but a panel that is always
+// ready.  Here one CTA per SM runs for the whole launch:
+//   * 8 DCT warps (producers) turn the spectral-plane rows of the next work item into its cosine panel directly in shared
+//     memory (the panel never goes through HBM: 4 of 17 MiB per function less traffic), with the loads of the next
+//     transform in flight while the current one is computed;
+//   * 8 MMA warps (consumers) contract the current panel against the order's table tiles (streamed from L2 into DMMA A
+//     fragments) and store the coefficients;
+//   * two panel buffers and two mbarriers per buffer (full / empty) decouple them; no CTA-wide barrier in the loop, a
+//     consumer warp that runs out of sub-items moves on to the next panel.
+// Work items = (order m, column tile of 32 columns = (function, +-m, re/im)), ordered by decreasing cost and dealt
+// round-robin to the CTAs, so consecutive CTAs share an order's table through L2.
+#include <stdlib.h>
+
+#include "s2k_fft.cuh"
+#include "s2k_legendre.cuh"
+
+namespace s2k {
+
+constexpr int PIPE_NC = 32;             // panel columns
+constexpr int PIPE_MMA_WARPS = 8;       // consumers: warps 0..7
+constexpr int PIPE_DCT_THREADS = 256;   // producers: warps 8..15
+constexpr int PIPE_THREADS = PIPE_MMA_WARPS * 32 + PIPE_DCT_THREADS;
+constexpr int PIPE_STAGES = 2;
+
+__device__ __forceinline__ void mbar_init(unsigned addr, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned addr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(unsigned addr, unsigned parity) {
+    unsigned done = 0;
+    unsigned long long spins = 0;
+    while (!done) {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (++spins > (1ull << 26)) __trap();  // a lost arrival must not hang the device
+    }
+}
+
+struct PipeArgs {
+    const double* table;
+    const uint64_t* order_start;
+    uint64_t table_shift;
+    const BlockMeta* meta;
+    const uint32_t* rt_start;
+    const double* S;        // spectral planes [f][part][order row][latitude slot]
+    const double* weights;  // 4bw, load order (s2k_host_reordered)
+    const double2* tw;
+    const double2* qtab;
+    double* rco;
+    double* ico;
+    long coef_stride;
+    int nfun, m_lo, norders, ncoltiles, real_fmt, lat_perm;
+    const int* order_list;
+};
+
+// item index -> (order, first function)
+__device__ __forceinline__ void pipe_item(const PipeArgs& a, int t, int NF, int& m, int& f0) {
+    const int oi = t / a.ncoltiles, x = t - oi * a.ncoltiles;
+    m = a.order_list ? a.order_list[oi] : a.m_lo + oi;
+    f0 = x * NF;
+}
+
+template <int N>
+__global__ void __launch_bounds__(PIPE_THREADS, 1) k_fwd_pipe(const PipeArgs a) {
+    constexpr int B = N / 2, T8 = N / 8, FPB = PIPE_DCT_THREADS / T8, NP = fft_padded_len(N), NC = PIPE_NC;
+    constexpr int NPAIR = NC / 2;  // one complex FFT serves the re and im column of one (function, sign)
+    static_assert(T8 >= 32 && NPAIR % FPB == 0, "FFT groups are whole warps and tile the panel");
+    extern __shared__ __align__(16) double smem[];
+    const int CS = panel_stride(B), half = B / 2;
+    const int panel_doubles = 2 * NC * CS;
+    double* panels = smem;                                                                   // [STAGES][2][NC][CS]
+    double2* ex = reinterpret_cast<double2*>(smem + PIPE_STAGES * panel_doubles);            // [FPB][NP]
+    const unsigned bar0 = static_cast<unsigned>(__cvta_generic_to_shared(ex + FPB * NP));   // full[2], empty[2]
+    const int tid = threadIdx.x;
+    const int cols_per_fn = a.real_fmt ? 2 : 4, NF = NC / cols_per_fn;
+    const int nitems = a.norders * a.ncoltiles;
+
+    if (tid == 0) {
+        for (int s = 0; s < PIPE_STAGES; ++s) {
+            mbar_init(bar0 + 8 * s, PIPE_DCT_THREADS);                  // full[s]: every producer thread arrives
+            mbar_init(bar0 + 8 * (PIPE_STAGES + s), PIPE_MMA_WARPS);    // empty[s]: one arrival per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // panel slots beyond the bw/2 cosine indices of a parity are only ever multiplied by zero table padding, but must not
+    // hold NaN garbage; the producers never write them
+    for (int i = tid; i < PIPE_STAGES * 2 * NC * (CS - half); i += PIPE_THREADS)
+        panels[(i / (CS - half)) * CS + half + i % (CS - half)] = 0.0;
+    __syncthreads();
+
+    if (tid >= PIPE_MMA_WARPS * 32) {
+        // =========================================================================================== producers: DCT
+        const int ptid = tid - PIPE_MMA_WARPS * 32, g = ptid / T8, t = ptid % T8;
+        double2* sx = ex + g * NP;
+        constexpr int ROUNDS = NPAIR / FPB;
+        constexpr int R = fft_last_radix(N);
+        const double s_all = 1.0 / sqrt(2.0 * (double)N);  // 1/sqrt(2*size), seminaive.c:174
+        const int nsteps = ((nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * ROUNDS;
+
+        // raw inputs of the NEXT step, in flight while the current transform is computed
+        double nr[8], ni[8], nw[8];
+        bool nlive = false;
+        auto issue_loads = [&](int step) {
+            const int k = step / ROUNDS, round = step % ROUNDS;
+            int m, f0;
+            pipe_item(a, blockIdx.x + k * gridDim.x, NF, m, f0);
+            const int q = round * FPB + g;  // pair index: panel columns 2q (re) and 2q + 1 (im)
+            const int fl = a.real_fmt ? q : (q >> 1), sgn = a.real_fmt ? 0 : (q & 1);
+            const int f = f0 + fl;
+            nlive = (f < a.nfun) && !(sgn && m == 0);
+            if (nlive) {
+                const int mp = sgn ? N - m : m;
+                const double* Sr = a.S + ((long)f * 2 * N + mp) * N;
+                const double* Si = Sr + (long)N * N;
+                const double* w = a.weights + ((m & 1) ? N : 0);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int p = t + e * T8;
+                    const int at = a.lat_perm ? p : ((p < B) ? 2 * p : 2 * (N - 1 - p) + 1);
+                    nr[e] = __ldg(Sr + at);
+                    ni[e] = __ldg(Si + at);
+                    nw[e] = __ldg(w + p);
+                }
+            }
+        };
+        if (nsteps > 0) issue_loads(0);
+#pragma unroll 1
+        for (int step = 0; step < nsteps; ++step) {
+            const int k = step / ROUNDS, round = step % ROUNDS, b = k & 1;
+            const bool live = nlive;
+            double xr[8], xi[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                xr[e] = live ? nr[e] * nw[e] : 0.0;
+                xi[e] = live ? ni[e] * nw[e] : 0.0;
+            }
+            if (step + 1 < nsteps) issue_loads(step + 1);
+            if (round == 0) {
+                // the consumers reach this item's order within microseconds: pull its table tiles into L2 now
+                int m, f0;
+                pipe_item(a, blockIdx.x + k * gridDim.x, NF, m, f0);
+                prefetch_order_l2(a.table + (a.order_start[m] - a.table_shift) * 64,
+                                  a.order_start[m + 1] - a.order_start[m], ptid, PIPE_DCT_THREADS, 1u << 20);
+                mbar_wait_parity(bar0 + 8 * (PIPE_STAGES + b), ((k >> 1) & 1) ^ 1);  // panel b drained
+            }
+            if (live) {  // uniform over the transform's threads (whole warps)
+                fft_block<N>(xr, xi, sx, t, g, a.tw);
+                // Z[k] stays in registers; only the upper half of the spectrum is exchanged (kernels_fft.cu, K2)
+                fft_sync<N>(g);
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    if (fft_slot<R>(e) >= 4) sx[fft_pad(fft_out_index<N>(e, t) - B)] = make_double2(xr[e], xi[e]);
+                fft_sync<N>(g);
+                const int q = round * FPB + g;
+                double* x_re = panels + b * panel_doubles + (2 * q) * CS;  // parity 0; parity 1 is NC*CS further
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    if (fft_slot<R>(e) >= 4) continue;
+                    const int kk = fft_out_index<N>(e, t);
+                    const double ar = xr[e], ai = xi[e];
+                    double br = ar, bi = ai;  // k = 0: Z[n] = Z[0]
+                    if (kk != 0) {
+                        const double2 zb = sx[fft_pad(B - kk)];
+                        br = zb.x;
+                        bi = zb.y;
+                    }
+                    const double2 qq = __ldg(a.qtab + kk);
+                    double y1 = qq.x * (ar + br) + qq.y * (ai - bi);
+                    double y2 = qq.x * (ai + bi) - qq.y * (ar - br);
+                    if (kk == 0) {
+                        y1 *= 0.70710678118654752440;  // M_SQRT1_2, seminaive.c:173
+                        y2 *= 0.70710678118654752440;
+                    }
+                    double* dst = x_re + (kk & 1) * NC * CS + (kk >> 1);
+                    dst[0] = y1 * s_all;
+                    dst[CS] = y2 * s_all;
+                }
+            }
+            if (round == ROUNDS - 1) mbar_arrive(bar0 + 8 * b);  // this thread's part of panel b is written
+        }
+        return;
+    }
+
+    // =============================================================================================== consumers: DMMA
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, q4 = lane & 3;
+#pragma unroll 1
+    for (int k = 0, item = blockIdx.x; item < nitems; ++k, item += gridDim.x) {
+        int m, f0;
+        pipe_item(a, item, NF, m, f0);
+        const int b = k & 1;
+        const BlockMeta mb0 = a.meta[2 * m], mb1 = a.meta[2 * m + 1];
+        const double* tbase = a.table + (a.order_start[m] - a.table_shift) * 64 + lane * 2;
+        const double* Xs = panels + b * panel_doubles;
+        // sub-items: (parity, pair of adjacent row tiles) while that gives every warp work, single row tiles otherwise;
+        // heaviest first, snake over the warps, direction alternating from item to item so that a warp with the
+        // heavy end of one item gets the light end of the next (warps may drift one panel apart)
+        const int unit = mb0.nrt >= 7 ? 2 : 1;
+        const int nunit0 = (mb0.nrt + unit - 1) / unit;  // mb0.nrt >= mb1.nrt
+        const int slot = (k & 1) ? PIPE_MMA_WARPS - 1 - warp : warp;
+        // epilogue addressing (kernels_legendre.cu, K3): the lane's columns 8j + 2 q4 + {0,1}
+        const int sgn = a.real_fmt ? 0 : (q4 & 1);
+        const int fl0 = a.real_fmt ? q4 : (q4 >> 1), flstep = a.real_fmt ? 4 : 2;
+        const long run0 = (long)(f0 + fl0) * a.coef_stride + (sgn ? coef_base(-m, B) : coef_base(m, B));
+        const long mrun0 = (long)(f0 + fl0) * a.coef_stride + coef_base(-m, B);
+        const unsigned long long flip = (sgn && (m & 1)) ? 0x8000000000000000ull : 0ull;  // FST_semi_memo.c:181-186
+        const bool live_sign = !(sgn && m == 0);
+        const bool mirror = a.real_fmt && m > 0;  // FST_semi_memo.c:131-145
+
+        mbar_wait_parity(bar0 + 8 * b, (k >> 1) & 1);  // panel b is complete
+#pragma unroll 1
+        for (int round = 0; round * PIPE_MMA_WARPS < 2 * nunit0; ++round) {
+            const int q = snake_item(round, slot, PIPE_MMA_WARPS);
+            if (q >= 2 * nunit0) continue;
+            const int p = q & 1;
+            const BlockMeta mb = p ? mb1 : mb0;
+            const int rt1 = mb.nrt - 1 - unit * (q >> 1), rt0 = unit == 2 ? rt1 - 1 : -1;  // rt0 = -1: single tile
+            if (rt1 < 0) continue;
+            const uint32_t* sr = a.rt_start + mb.rt_base;
+            const double* xp = Xs + (p * NC + g) * CS + q4;
+            double acc0[NC / 8][2], acc1[NC / 8][2];
+#pragma unroll
+            for (int j = 0; j < NC / 8; ++j) acc0[j][0] = acc0[j][1] = acc1[j][0] = acc1[j][1] = 0.0;
+            if (rt0 >= 0)
+                fwd_row_tile2<NC, LEG_PF2_FWD>(tbase + (uint64_t)__ldg(sr + rt0) * 64, tiles_in_row(mb, rt0),
+                                               tbase + (uint64_t)__ldg(sr + rt1) * 64, tiles_in_row(mb, rt1), xp, CS,
+                                               acc0, acc1);
+            else
+                fwd_row_tile<NC>(tbase + (uint64_t)__ldg(sr + rt1) * 64, xp, CS, tiles_in_row(mb, rt1), acc1);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = 8 * (h ? rt1 : rt0) + g;
+                if ((h == 0 && rt0 < 0) || r >= mb.rows || !live_sign) continue;
+                const int off = p + 2 * r;  // l - m
+#pragma unroll
+                for (int j = 0; j < NC / 8; ++j) {
+                    if (f0 + fl0 + j * flstep >= a.nfun) continue;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const unsigned long long bits =
+                            (unsigned long long)__double_as_longlong(h ? acc1[j][e] : acc0[j][e]);
+                        double* arr = e ? a.ico : a.rco;
+                        arr[run0 + (long)j * flstep * a.coef_stride + off] = __longlong_as_double((long long)(bits ^ flip));
+                        if (mirror) {
+                            const unsigned long long mflip = ((m & 1) ^ e) ? 0x8000000000000000ull : 0ull;
+                            arr[mrun0 + (long)j * flstep * a.coef_stride + off] =
+                                __longlong_as_double((long long)(bits ^ mflip));
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar0 + 8 * (PIPE_STAGES + b));  // this warp is done with panel b
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ launcher
+static bool pipe_enabled() {
+    static int on = [] {
+        const char* e = getenv("S2KIT_CUDA_PIPE");
+        return (e && e[0] == '0') ? 0 : 1;
+    }();
+    return on != 0;
+}
+
+// batched launches at bw = 128 / 256 whose columns fill at least one 32-column panel
+bool fwd_pipe_supported(const s2kit_cuda_plan* p, int nfun, int data_format) {
+    if (!pipe_enabled() || !p->fast || p->fuse) return false;
+    if (p->n != 256 && p->n != 512) return false;
+    return nfun * (data_format == S2KIT_REAL ? 2 : 4) >= PIPE_NC;
+}
+
+template <int N>
+static cudaError_t fwd_pipe_n(s2kit_cuda_plan* p, const PipeArgs& a) {
+    constexpr int FPB = PIPE_DCT_THREADS / (N / 8);
+    const int CS = panel_stride(N / 2);
+    const size_t smem = sizeof(double) * PIPE_STAGES * 2 * PIPE_NC * CS + sizeof(double2) * FPB * fft_padded_len(N) +
+                        8 * 2 * PIPE_STAGES;
+    cudaError_t e = ensure_smem(reinterpret_cast<const void*>(k_fwd_pipe<N>), smem);
+    if (e != cudaSuccess) return e;
+    cudaDeviceProp prop;
+    static int sms = 0;
+    if (!sms) {
+        e = cudaGetDeviceProperties(&prop, p->device);
+        if (e != cudaSuccess) return e;
+        sms = prop.multiProcessorCount;
+    }
+    const int nitems = a.norders * a.ncoltiles;
+    k_fwd_pipe<N><<<nitems < sms ? nitems : sms, PIPE_THREADS, smem, p->stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fwd_pipe(s2kit_cuda_plan* p, const double* table, uint64_t shift, const double* S, double* rco,
+                            double* ico, long coef_stride, int nfun, int m_lo, int m_hi, int data_format, int lat_perm) {
+    if (m_hi <= m_lo || nfun <= 0) return cudaSuccess;
+    PipeArgs a;
+    a.table = table;
+    a.order_start = p->d_order_start;
+    a.table_shift = shift;
+    a.meta = p->d_meta;
+    a.rt_start = p->d_rt_start;
+    a.S = S;
+    a.weights = p->d_wv;
+    a.tw = p->d_tw_n;
+    a.qtab = p->d_q_n;
+    a.rco = rco;
+    a.ico = ico;
+    a.coef_stride = coef_stride;
+    a.nfun = nfun;
+    a.m_lo = m_lo;
+    a.norders = m_hi - m_lo;
+    a.real_fmt = data_format == S2KIT_REAL;
+    const int NF = PIPE_NC / (a.real_fmt ? 2 : 4);
+    a.ncoltiles = (nfun + NF - 1) / NF;
+    a.lat_perm = lat_perm;
+    a.order_list = nullptr;
+    int slot = prof_begin(p, S2KIT_K_FUSED_FWD);
+    cudaError_t e = p->n == 512 ? fwd_pipe_n<512>(p, a) : fwd_pipe_n<256>(p, a);
+    prof_end(p, slot);
+    return e;
+}
+
+}  // namespace s2k

@@ -443,10 +443,15 @@ static int fst_device(s2kit_cuda_plan* p, const double* rdata, const double* ida
         s2k::PlaneView pv = s2k::default_view(p->n);
         pv.lat_perm = !fused && s2k::tma_planes_ok(p, nf);
         CK(s2k::launch_phi_fft_fwd(p, rd, id, data_stride, p->d_S, nf, fmt, &pv));
-        if (!fused) CK(s2k::launch_dct_fwd(p, p->d_S, p->d_X, nf, 0, nrows, fmt, &pv));
+        // batched: one persistent kernel does the DCTs and the contraction (kernels_pipe.cu)
+        const bool pipe = !fused && s2k::fwd_pipe_supported(p, nf, fmt);
+        if (!fused && !pipe) CK(s2k::launch_dct_fwd(p, p->d_S, p->d_X, nf, 0, nrows, fmt, &pv));
         for (const OrderGroup& g : order_groups(p, 0, bw)) {
             if (p->variant == S2KIT_CUDA_FLY) CK(s2k::launch_table_gen(p, p->d_table, g.shift, g.lo, g.hi));
-            if (fused)
+            if (pipe)
+                CK(s2k::launch_fwd_pipe(p, p->d_table, g.shift, p->d_S, rc, ic, coef_stride, nf, g.lo, g.hi, fmt,
+                                        pv.lat_perm));
+            else if (fused)
                 CK(s2k::launch_fused_fwd(p, p->d_table, g.shift, p->d_S, rc, ic, coef_stride, nf, g.lo, g.hi, fmt));
             else
                 CK(s2k::launch_legendre_fwd(p, p->d_table, g.shift, p->d_X, rc, ic, coef_stride, nf, g.lo, g.hi, fmt));

@@ -175,6 +175,11 @@ cudaError_t launch_fused_inv(s2kit_cuda_plan* p, const double* table, uint64_t t
                              const double* ico, long coef_stride, double* G, int nfun, int m_lo, int m_hi,
                              int data_format);
 
+// persistent warp-specialised K2+K3 for batched launches (kernels_pipe.cu)
+bool fwd_pipe_supported(const s2kit_cuda_plan* p, int nfun, int data_format);
+cudaError_t launch_fwd_pipe(s2kit_cuda_plan* p, const double* table, uint64_t table_shift, const double* S, double* rco,
+                            double* ico, long coef_stride, int nfun, int m_lo, int m_hi, int data_format, int lat_perm);
+
 // peaks
 cudaError_t measure_fp64(double* fma_tflops, double* dmma_tflops);
 cudaError_t measure_copy(size_t bytes, double* gbs);

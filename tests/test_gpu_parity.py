@@ -224,6 +224,37 @@ def test_batched_device_pointers(s2, oracles):
     P.close()
 
 
+@pytest.mark.parametrize("bw,batch", [(128, 19), (256, 11)])
+def test_batched_wide_panels_match_oracle(s2, oracles, bw, batch):
+    """Batches wide enough for the persistent warp-specialised kernels (kernels_pipe.cu: 32-column panels, ragged last
+    panel, chunking), every function checked against the oracle in both data formats; fully complex coefficients so
+    that the negative orders carry independent data."""
+    import torch
+
+    n = 2 * bw
+    O = oracles(bw)
+    P = s2.Plan(bw, s2.MEMO, max_batch=12)
+    rng = np.random.RandomState(bw + batch)
+    coefs = [O.gen_coeffs(2000 + k) for k in range(batch)]
+    for k in range(1, batch, 2):  # independent +-m data on every other function
+        coefs[k] = (rng.uniform(-1, 1, bw * bw), rng.uniform(-1, 1, bw * bw))
+    rc = torch.tensor(np.stack([c[0] for c in coefs]), device="cuda")
+    ic = torch.tensor(np.stack([c[1] for c in coefs]), device="cuda")
+    for fmt in (0, 1):
+        rd = torch.zeros(batch, n, n, device="cuda", dtype=torch.float64)
+        idt = torch.zeros_like(rd)
+        P.inv_fst(rc, ic, rd, idt, fmt)
+        rc2, ic2 = torch.full_like(rc, float("nan")), torch.full_like(ic, float("nan"))
+        P.fst(rd, idt, rc2, ic2, fmt)
+        P.synchronize()
+        for k in range(batch):
+            want_g = O.inverse(coefs[k][0], coefs[k][1], fmt)
+            assert relerr(cat((rd[k].cpu().numpy(), idt[k].cpu().numpy())), cat(want_g)) < TOL
+            want_c = O.forward(want_g[0], want_g[1], fmt)
+            assert relerr(cat((rc2[k].cpu().numpy(), ic2[k].cpu().numpy())), cat(want_c)) < TOL
+    P.close()
+
+
 def test_batched_convolution_device(s2, oracles):
     import torch
 
