@@ -156,6 +156,8 @@ NCU_DRAM_BYTES_PER_FUNCTION_BW256_COMPLEX = {
     "phi_fft_fwd": (1.074085e9 + 1.027033e9) / 256, "phi_fft_inv": (1.07166e9 + 1.028037e9) / 256,
     "dct_fwd": (1.071721e9 + 0.508014e9) / 256, "dct_inv": (0.545191e9 + 1.017913e9) / 256,
     "legendre_fwd": (0.570337e9 + 0.271074e9) / 256, "legendre_inv": (0.294773e9 + 0.484361e9) / 256,
+    # persistent K2+K3 kernel (kernels_pipe.cu), profiles/r1_ncu_pipe_summary.md
+    "fused_fwd": (1.099542e9 + 0.270152e9) / 256,
 }
 
 
@@ -303,6 +305,10 @@ def run_ours(a):
             plan.inv_fst(hc_r, hc_i, hg_r, hg_i, fmt)   # H2D coefficients, D2H grids
             plan.fst(hg_r, hg_i, ho_r, ho_i, fmt)       # H2D grids, D2H coefficients
 
+        # One host thread, the two calls back to back.  (Measured: running the inverse of one half of the batch and the
+        # forward of the other half concurrently from two threads / two plans, so that both PCIe directions are busy at
+        # once, gives the same throughput -- 6318 vs 6303 pairs/s: the box moves ~66 GB/s host<->device in total,
+        # whatever the mix of directions.  profiles/r1_ncu_summary.md)
         e2e_step()
         barrier()
         t0 = time.perf_counter()

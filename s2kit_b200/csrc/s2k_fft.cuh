@@ -25,7 +25,10 @@ __host__ __device__ constexpr int fft_padded_len(int n) { return n + (n >> 3) + 
 // warps, the CTA-wide barrier otherwise -- then every thread of the CTA must take part)
 template <int N>
 __device__ __forceinline__ void fft_sync(int group) {
-    if constexpr (N / 8 >= 32) {
+    if constexpr (N / 8 == 32) {
+        (void)group;
+        __syncwarp();  // the transform is exactly one warp (groups are cut at multiples of N/8 threads)
+    } else if constexpr (N / 8 > 32) {
         asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "n"(N / 8) : "memory");
     } else {
         (void)group;
