@@ -56,6 +56,14 @@ void DLTSemi(double* data, const int bw, const int m, double* result, double* wo
 void InvDLTSemi(double* coeffs, const int bw, const int m, double* result, double* trans_cos_pml_table,
                 double* sin_values, double* workspace, fftw_plan* plan);
 
+/* include/s2kit/naive.h:4-6 (theta-space table from GeneratePmlTable; the GPU does the dense products) */
+void DLTNaive(double* data, const int bw, const int m, double* weights, double* result, double* pml_table,
+              double* workspace);
+void InvDLTNaive(double* coeffs, const int bw, const int m, double* result, double* pml_table);
+
+/* include/s2kit/pmm.h:4 */
+void Pmm_L2(const int m, double* eval_points, const int n, double* result);
+
 /* include/s2kit/chebyshev_nodes.h:4-6 */
 void AcosOfChebyshevNodes(const int n, double* eval_points);
 void ChebyshevNodes(const int n, double* eval_points);

@@ -100,6 +100,13 @@ int s2kit_cuda_trans_mult(s2kit_cuda_plan* plan, const double* rdata, const doub
 int s2kit_cuda_dlt_semi(s2kit_cuda_plan* plan, const double* data, int m, double* result, int ncols, int where);
 int s2kit_cuda_inv_dlt_semi(s2kit_cuda_plan* plan, const double* coeffs, int m, double* result, int ncols, int where);
 
+/* The reference's naive algorithm on one column (replace DLTNaive / InvDLTNaive, src/legendre_transform/naive.c:35,77):
+ * dense products with the caller's theta-space table pml_table[bw-m][2bw] (GeneratePmlTable, pml.c:41-79).  No plan:
+ * nothing is precomputed.  forward: data[2bw], weights[>= 2bw] -> result[bw-m]; inverse: coeffs[bw-m] -> result[2bw] */
+int s2kit_cuda_dlt_naive(const double* data, int bw, int m, const double* weights, double* result,
+                         const double* pml_table, int where);
+int s2kit_cuda_inv_dlt_naive(const double* coeffs, int bw, int m, double* result, const double* pml_table, int where);
+
 /* ---- sharded single-field halves (see s2kit_cuda_plan_create_sharded) ---------------------------- */
 /* forward, stage 1: this rank's latitude rings [ring_lo, ring_lo+nrings) -> longitude FFT, written as
  * send blocks: out[dest_rank][part][local order][local ring]; all pointers device memory */

@@ -64,6 +64,8 @@ def lib():
     L.s2kit_cuda_trans_mult.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci, cl, ci]
     L.s2kit_cuda_dlt_semi.argtypes = [vp, vp, ci, vp, ci, ci]
     L.s2kit_cuda_inv_dlt_semi.argtypes = [vp, vp, ci, vp, ci, ci]
+    L.s2kit_cuda_dlt_naive.argtypes = [vp, ci, ci, vp, vp, vp, ci]
+    L.s2kit_cuda_inv_dlt_naive.argtypes = [vp, ci, ci, vp, vp, ci]
     L.s2kit_cuda_fst_rings.argtypes = [vp, vp, vp, vp]
     L.s2kit_cuda_fst_orders.argtypes = [vp, vp, vp, vp]
     L.s2kit_cuda_inv_fst_orders.argtypes = [vp, vp, vp, vp]
@@ -426,6 +428,44 @@ def GenerateCosPmlTable(bw, m):
     fn = lib().GenerateCosPmlTable
     fn.restype = None
     fn(ctypes.c_int(bw), ctypes.c_int(m), out.ctypes.data_as(_P), None)
+    return out
+
+
+def GeneratePmlTable(bw, m):
+    """Theta-space table of order m, [bw - m][2bw] (pml.c:41-79); host-side setup."""
+    out = np.zeros((bw - m) * 2 * bw)
+    fn = lib().GeneratePmlTable
+    fn.restype = None
+    fn(ctypes.c_int(bw), ctypes.c_int(m), out.ctypes.data_as(_P), None)
+    return out
+
+
+def Pmm_L2(m, eval_points):
+    pts, pp = _np(eval_points)
+    out = np.zeros(pts.size)
+    fn = lib().Pmm_L2
+    fn.restype = None
+    fn(ctypes.c_int(m), pp, ctypes.c_int(pts.size), out.ctypes.data_as(_P))
+    return out
+
+
+def DLTNaive(data, bw, m, weights, pml_table):
+    """naive.c:35-60 through the relinkable C API: the dense product runs on the GPU."""
+    (d, pd), (w, pw), (t, pt) = _np(data), _np(weights), _np(pml_table)
+    out = np.zeros(bw - m)
+    fn = lib().DLTNaive
+    fn.restype = None
+    fn(pd, ctypes.c_int(bw), ctypes.c_int(m), pw, out.ctypes.data_as(_P), pt, None)
+    return out
+
+
+def InvDLTNaive(coeffs, bw, m, pml_table):
+    """naive.c:77-95."""
+    (c, pc), (t, pt) = _np(coeffs), _np(pml_table)
+    out = np.zeros(2 * bw)
+    fn = lib().InvDLTNaive
+    fn.restype = None
+    fn(pc, ctypes.c_int(bw), ctypes.c_int(m), out.ctypes.data_as(_P), pt)
     return out
 
 

@@ -85,6 +85,42 @@ cudaError_t launch_spectral_mul(s2kit_cuda_plan* p, const double* rd, const doub
     return e;
 }
 
+// ------------------------------------------------------------------------------------------------ naive DLT
+// DLTNaive / InvDLTNaive (src/legendre_transform/naive.c:35-60, 77-95): dense products with the caller's theta-space
+// table pml[(l - m)][j], j < 2bw.  One warp per degree forward (fixed shuffle-tree summation), one thread per sample
+// point inverse (degrees accumulated in the reference's order).
+__global__ void k_naive_dlt(const double* __restrict__ data, const double* __restrict__ weights,
+                            const double* __restrict__ pml, double* __restrict__ result, int size, int rows) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const double* t = pml + (long)row * size;
+    double sum = 0.0;
+    for (int j = lane; j < size; j += 32) sum += (data[j] * weights[j]) * t[j];
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
+    if (lane == 0) result[row] = sum;
+}
+
+__global__ void k_naive_inv_dlt(const double* __restrict__ coeffs, const double* __restrict__ pml,
+                                double* __restrict__ result, int size, int rows) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= size) return;
+    double acc = 0.0;
+    for (int i = 0; i < rows; ++i) acc += coeffs[i] * pml[(long)i * size + j];
+    result[j] = acc;
+}
+
+cudaError_t launch_naive_dlt(const double* data, const double* weights, const double* pml, double* result, int size,
+                             int rows, cudaStream_t st) {
+    k_naive_dlt<<<(rows + 7) / 8, 256, 0, st>>>(data, weights, pml, result, size, rows);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_naive_inv_dlt(const double* coeffs, const double* pml, double* result, int size, int rows,
+                                 cudaStream_t st) {
+    k_naive_inv_dlt<<<(size + 127) / 128, 128, 0, st>>>(coeffs, pml, result, size, rows);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------ peaks
 __global__ void k_peak_dfma(double* out, int iters) {
     double a[8];

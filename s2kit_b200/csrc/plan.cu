@@ -831,6 +831,51 @@ extern "C" int s2kit_cuda_inv_dlt_semi(s2kit_cuda_plan* p, const double* coeffs,
     return rc;
 }
 
+// naive algorithm (naive.c): no plan, the table comes from the caller.  Host pointers are staged through the device.
+static int naive_common(const double* vec, long vec_len, const double* weights, const double* pml, double* result,
+                        long res_len, int bw, int m, int where, bool forward) {
+    if (bw < 1 || m < 0 || m >= bw) return fail_msg("order out of range");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail_msg("no CUDA device available: s2kit_cuda has no CPU fallback");
+    const int size = 2 * bw, rows = bw - m;
+    const size_t tab = (size_t)size * rows;
+    const double *dv = vec, *dw = weights, *dt = pml;
+    double* dr = result;
+    double* stage = nullptr;
+    if (where != S2KIT_CUDA_DEVICE) {
+        CK(cudaMalloc((void**)&stage, sizeof(double) * (tab + vec_len + res_len + size)));
+        double *sv = stage + tab, *sw = sv + vec_len, *sr = sw + size;
+        cudaError_t e = cudaMemcpy(stage, pml, tab * 8, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(sv, vec, vec_len * 8, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && weights) e = cudaMemcpy(sw, weights, (size_t)size * 8, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            cudaFree(stage);
+            return fail("naive DLT H2D", e);
+        }
+        dt = stage, dv = sv, dw = sw, dr = sr;
+    }
+    cudaError_t e = forward ? s2k::launch_naive_dlt(dv, dw, dt, dr, size, rows, 0)
+                            : s2k::launch_naive_inv_dlt(dv, dt, dr, size, rows, 0);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+    if (e == cudaSuccess && stage) e = cudaMemcpy(result, dr, res_len * 8, cudaMemcpyDeviceToHost);
+    if (stage) cudaFree(stage);
+    if (e != cudaSuccess) return fail("naive DLT", e);
+    return 0;
+}
+
+extern "C" int s2kit_cuda_dlt_naive(const double* data, int bw, int m, const double* weights, double* result,
+                                    const double* pml_table, int where) {
+    if (!data || !weights || !result || !pml_table) return fail_msg("null pointer");
+    return naive_common(data, 2L * bw, weights, pml_table, result, (long)bw - m, bw, m, where, true);
+}
+
+extern "C" int s2kit_cuda_inv_dlt_naive(const double* coeffs, int bw, int m, double* result, const double* pml_table,
+                                        int where) {
+    if (!coeffs || !result || !pml_table) return fail_msg("null pointer");
+    return naive_common(coeffs, (long)bw - m, nullptr, pml_table, result, 2L * bw, bw, m, where, false);
+}
+
 // ------------------------------------------------------------------------------------------------ tables
 static int table_to_host(s2kit_cuda_plan* p, const double* table, uint64_t shift, int m, double* host_out) {
     int size = 0;

@@ -166,6 +166,11 @@ cudaError_t launch_zonal_rowsum(s2kit_cuda_plan* p, const double* rdata, const d
 cudaError_t launch_spectral_mul(s2kit_cuda_plan* p, const double* rd, const double* id, long coef_stride,
                                 const double* rf, const double* ifl, long filt_stride, double* rres, double* ires,
                                 long res_stride, int nfun);
+// DLTNaive / InvDLTNaive products with a caller-provided theta-space table (all pointers device memory)
+cudaError_t launch_naive_dlt(const double* data, const double* weights, const double* pml, double* result, int size,
+                             int rows, cudaStream_t st);
+cudaError_t launch_naive_inv_dlt(const double* coeffs, const double* pml, double* result, int size, int rows,
+                                 cudaStream_t st);
 int table_unit_rows(int bw);
 // fused K2+K3 / K4+K5 (kernels_fused.cu)
 bool fused_supported(const s2kit_cuda_plan* p, int nfun, int data_format);

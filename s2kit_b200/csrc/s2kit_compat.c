@@ -6,6 +6,8 @@
  *   include/s2kit/FST_semi_memo.h:8-16   FSTSemiMemo InvFSTSemiMemo FZTSemiMemo ConvOn2SphereSemiMemo
  *   include/s2kit/FST_semi_fly.h:8-16    FSTSemiFly  InvFSTSemiFly  FZTSemiFly  ConvOn2SphereSemiFly
  *   include/s2kit/seminaive.h:6-8        DLTSemi InvDLTSemi
+ *   include/s2kit/naive.h:4-6            DLTNaive InvDLTNaive
+ *   include/s2kit/pmm.h:4                Pmm_L2
  *   include/s2kit/cospml.h:6-30          TableSize ... Transpose_SemiNaive_Naive_Pml_Table
  *   include/s2kit/weights.h:4            GenerateWeightsForDLT
  *   include/s2kit/util.h:15-17           IndexOfHarmonicCoeff TransMult
@@ -161,6 +163,15 @@ void ChebyshevNodes(const int n, double* eval_points) {
 }
 
 void GenerateWeightsForDLT(const int bw, double* weights) { s2k_host_weights(bw, weights); }
+
+/* pmm.c:21-33 (setup seed, libm in the reference's expression order like the other seeds in host_setup.c) */
+void Pmm_L2(const int m, double* eval_points, const int n, double* result) {
+    double c = sqrt(m + 0.5);
+    for (int i = 0; i < m; ++i) c *= sqrt((m - (i / 2.)) / ((double)m - i));
+    if (m) c *= pow(2., -m / 2.);
+    if (m % 2) c *= -1.;
+    for (int i = 0; i < n; ++i) result[i] = c * pow(sin(eval_points[i]), m);
+}
 
 /* cospml.c:161-242: generated on the device, exported in the reference's packed layout */
 void GenerateCosPmlTable(const int bw, const int m, double* tablespace, double* workspace) {
@@ -367,6 +378,18 @@ void InvDLTSemi(double* coeffs, const int bw, const int m, double* result, doubl
     (void)trans_cos_pml_table; (void)sin_values; (void)workspace; (void)plan;
     if (s2kit_cuda_inv_dlt_semi(plan_for(bw, S2KIT_CUDA_MEMO), coeffs, m, result, 1, S2KIT_CUDA_HOST))
         die("InvDLTSemi");
+}
+
+/* naive.c:35-60 */
+void DLTNaive(double* data, const int bw, const int m, double* weights, double* result, double* pml_table,
+              double* workspace) {
+    (void)workspace;
+    if (s2kit_cuda_dlt_naive(data, bw, m, weights, result, pml_table, S2KIT_CUDA_HOST)) die("DLTNaive");
+}
+
+/* naive.c:77-95 */
+void InvDLTNaive(double* coeffs, const int bw, const int m, double* result, double* pml_table) {
+    if (s2kit_cuda_inv_dlt_naive(coeffs, bw, m, result, pml_table, S2KIT_CUDA_HOST)) die("InvDLTNaive");
 }
 
 /* util.c:68-103 */

@@ -194,6 +194,41 @@ def test_zonal_transmult_dlt(s2, oracles):
     P.close()
 
 
+def test_naive_dlt_matches_reference_and_seminaive(s2, oracles):
+    """DLTNaive / InvDLTNaive (naive.c) on the GPU with the theta-space table of GeneratePmlTable: against the
+    reference's own functions where the compiled reference is available, and against the seminaive transform of the
+    same column (the two algorithms compute the same coefficients, test/test_DLT_naive.c vs test_DLT_semi.c)."""
+    bw = 32
+    n = 2 * bw
+    O, P = oracles(bw), s2.Plan(bw)
+    rng = np.random.RandomState(11)
+    w = s2.GenerateWeightsForDLT(bw)
+    theta = (2.0 * np.arange(n) + 1.0) * np.pi / (2.0 * n)
+    for m in (0, 1, 6, 31):
+        tab = s2.GeneratePmlTable(bw, m)
+        assert relerr(tab[:n], s2.Pmm_L2(m, theta)) < 1e-14  # first row is P_m^m itself (pml.c:52-56)
+        co = rng.uniform(-1, 1, bw - m)
+        grid = s2.InvDLTNaive(co, bw, m, tab)
+        assert relerr(grid, tab.reshape(bw - m, n).T @ co) < 1e-14
+        back = s2.DLTNaive(grid, bw, m, w, tab)
+        assert relerr(back, co) < 1e-11  # exact quadrature for band-limited columns
+        assert relerr(P.dlt_semi(grid, m)[0], back) < TOL
+        if O.kind == "ref":
+            import ctypes
+
+            from oracle import _p
+            rtab, want = np.zeros_like(tab), np.zeros(bw - m)
+            ws = np.zeros(16 * bw)
+            O.L.GeneratePmlTable(ctypes.c_int(bw), ctypes.c_int(m), _p(rtab), _p(ws))
+            assert relerr(tab, rtab) < 1e-14
+            O.L.DLTNaive(_p(grid), ctypes.c_int(bw), ctypes.c_int(m), _p(w), _p(want), _p(rtab), _p(ws))
+            assert relerr(back, want) < 1e-13
+            wantg = np.zeros(n)
+            O.L.InvDLTNaive(_p(co), ctypes.c_int(bw), ctypes.c_int(m), _p(wantg), _p(rtab))
+            assert relerr(grid, wantg) < 1e-14
+    P.close()
+
+
 # ------------------------------------------------------------------------------------------------ batched device path
 def test_batched_device_pointers(s2, oracles):
     """Device-resident batch through s2kit_cuda_inv_fst / s2kit_cuda_fst: ragged chunking (batch 5, chunk 2)."""
