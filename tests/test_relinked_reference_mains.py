@@ -73,7 +73,8 @@ def test_inverse_main_round_trip(tmp_path, vectors):
 
 
 @pytest.mark.parametrize("exe_name,args", [("test_s2_semi_memo", ["64", "2"]), ("test_s2_semi_fly", ["64", "2"]),
-                                            ("test_DLT_semi", ["3", "128", "4"])])
+                                            ("test_DLT_semi", ["3", "128", "4"]),
+                                            ("test_DLT_naive", ["3", "128", "4"])])
 def test_round_trip_mains_report_small_errors(tmp_path, exe_name, args):
     """The self-consistency mains print their round-trip errors (HowTo 2.2: ~1e-12 at bw 123)."""
     exe = _need(exe_name)
