@@ -445,12 +445,15 @@ static int fst_device(s2kit_cuda_plan* p, const double* rdata, const double* ida
         CK(s2k::launch_phi_fft_fwd(p, rd, id, data_stride, p->d_S, nf, fmt, &pv));
         // batched: one persistent kernel does the DCTs and the contraction (kernels_pipe.cu)
         const bool pipe = !fused && s2k::fwd_pipe_supported(p, nf, fmt);
-        if (!fused && !pipe) CK(s2k::launch_dct_fwd(p, p->d_S, p->d_X, nf, 0, nrows, fmt, &pv));
+        const bool pipe_fused = pipe && s2k::fwd_pipe_fused();
+        if (!fused && !pipe_fused) CK(s2k::launch_dct_fwd(p, p->d_S, p->d_X, nf, 0, nrows, fmt, &pv));
         for (const OrderGroup& g : order_groups(p, 0, bw)) {
             if (p->variant == S2KIT_CUDA_FLY) CK(s2k::launch_table_gen(p, p->d_table, g.shift, g.lo, g.hi));
-            if (pipe)
+            if (pipe_fused)
                 CK(s2k::launch_fwd_pipe(p, p->d_table, g.shift, p->d_S, rc, ic, coef_stride, nf, g.lo, g.hi, fmt,
                                         pv.lat_perm));
+            else if (pipe)
+                CK(s2k::launch_leg_fwd_stream(p, p->d_table, g.shift, p->d_X, rc, ic, coef_stride, nf, g.lo, g.hi, fmt));
             else if (fused)
                 CK(s2k::launch_fused_fwd(p, p->d_table, g.shift, p->d_S, rc, ic, coef_stride, nf, g.lo, g.hi, fmt));
             else

@@ -185,6 +185,12 @@ bool fwd_pipe_supported(const s2kit_cuda_plan* p, int nfun, int data_format);
 cudaError_t launch_fwd_pipe(s2kit_cuda_plan* p, const double* table, uint64_t table_shift, const double* S, double* rco,
                             double* ico, long coef_stride, int nfun, int m_lo, int m_hi, int data_format, int lat_perm);
 
+bool fwd_pipe_fused();  // default: the DCT runs inside the persistent kernel; S2KIT_CUDA_PIPE=1: K2 + streamed K3
+// K3 as a persistent kernel with cp.async-streamed table tiles (kernels_pipe.cu); X = K2's cosine planes
+cudaError_t launch_leg_fwd_stream(s2kit_cuda_plan* p, const double* table, uint64_t table_shift, const double* X,
+                                  double* rco, double* ico, long coef_stride, int nfun, int m_lo, int m_hi,
+                                  int data_format);
+
 // peaks
 cudaError_t measure_fp64(double* fma_tflops, double* dmma_tflops);
 cudaError_t measure_copy(size_t bytes, double* gbs);

@@ -74,6 +74,29 @@ __device__ __forceinline__ int snake_item(int round, int slot, int nslots) {
     return round * nslots + ((round & 1) ? nslots - 1 - slot : slot);
 }
 
+// ---- the tile layout in closed form (what build_layout, plan.cu, tabulates in meta[] / rt_start[]) ----------------
+// Kernels that want the addresses of tiles they will need LATER (prefetch) compute them instead of chasing the tables
+// through dependent global loads.
+__host__ __device__ inline BlockMeta block_meta_of(int m, int par, int bw) {
+    BlockMeta mb;
+    mb.rt_base = 0;  // not used with the closed form
+    int rows = (bw - m - par + 1) / 2;
+    mb.rows = rows < 0 ? 0 : rows;
+    const int l = m + par;
+    mb.len0 = (m & 1) ? (l - 1) / 2 + 1 : l / 2 + 1;  // RowSize(m, m + par), cospml.c:250-258
+    mb.nrt = (mb.rows + 7) / 8;
+    return mb;
+}
+// first tile of row tile rt (rt < nrt) relative to the block's first tile: rows grow by 8 entries = one tile per row tile
+__host__ __device__ inline uint32_t row_tile_start_of(const BlockMeta& mb, int rt) {
+    return (uint32_t)(rt * (rt - 1) / 2 + rt * ((mb.len0 + 14) >> 3));
+}
+// tiles of a whole parity block (= where the other parity's block starts inside the order)
+__host__ __device__ inline uint32_t block_tiles_of(const BlockMeta& mb) {
+    if (mb.nrt == 0) return 0;
+    return row_tile_start_of(mb, mb.nrt - 1) + (uint32_t)((mb.len0 + mb.rows - 1 + 7) >> 3);
+}
+
 // number of 8-wide column tiles of row tile rt in a parity block
 __device__ __forceinline__ int tiles_in_row(const BlockMeta& mb, int rt) {
     return (mb.len0 + min(8 * rt + 7, mb.rows - 1) + 7) >> 3;
@@ -81,13 +104,13 @@ __device__ __forceinline__ int tiles_in_row(const BlockMeta& mb, int rt) {
 
 // Forward main loop for one (parity, row tile): acc[j] += T_tile * X_panel for NC/8 column tiles.
 // tp: first tile of the row tile (+ 2*lane); xp: panel base of this lane (parity, column g, slot q4).
-template <int NC>
+template <int NC, int PFD = leg_prefetch(NC)>
 __device__ __forceinline__ void fwd_row_tile(const double* __restrict__ tp, const double* xp, int CS, int ctn,
                                              double (&acc)[NC / 8][2], bool dead_lane = false) {
     // Ring of LEG_PREFETCH tiles in registers.  The refill is UNCONDITIONAL (index clamped to the last tile): a
     // predicated refill made ptxas load into a temporary and copy it into the ring slot right away, which waits
     // for the load and serialises the whole prefetch.
-    constexpr int LEG_PREFETCH = leg_prefetch(NC);
+    constexpr int LEG_PREFETCH = PFD;
     double2 abuf[LEG_PREFETCH];
 #pragma unroll
     for (int u = 0; u < LEG_PREFETCH; ++u)
