@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, NC >= 32 ? 2 : 3) k_legendre_f
             // ---- epilogue: lane holds rows 8 rt + g of both tiles, columns 8j + 2 q4 + {0,1}.  Column c of the panel is
             // (function f0 + c / cpf, sign, part = c & 1), so the lane's eight destinations differ only by the function
             // and the re / im array: closed form, no per-column table (its shared-memory reads cost more wavefronts
-            // than the main loop's fragments, profiles/r2_ncu_legendre.md).  The signs are +-1: flip the sign bit on the
+            // than the main loop's fragments, profiles/r1_ncu_pipe_summary.md).  The signs are +-1: flip the sign bit on the
             // integer pipe instead of a DMUL that competes with the DMMAs.
             const int sgn = real_fmt ? 0 : (q4 & 1);
             const int fl0 = real_fmt ? q4 : (q4 >> 1), flstep = real_fmt ? 4 : 2;
@@ -249,7 +249,6 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_inv(
 
     prefetch_order_l2(table + (order_start[m] - table_shift) * 64, order_start[m + 1] - order_start[m], tid, blockDim.x,
                       l2pf_cap);
-    const BlockMeta mb0 = meta[2 * m], mb1 = meta[2 * m + 1];  // in flight while the panel is staged
     const int base_pos = coef_base(m, bw), base_neg = coef_base(-m, bw);
     for (int col = warp; col < PC; col += LEG_WARPS) {
         int fl = col / cols_per_fn, sub = col % cols_per_fn;
@@ -267,10 +266,14 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_inv(
         for (int c = h0 + lane; c < CS; c += 32) d0[c] = 0.0;
         for (int c = h1 + lane; c < CS; c += 32) d1[c] = 0.0;
     }
+    cp_async_wait_all();
+    __syncthreads();
+
+    const BlockMeta mb0 = meta[2 * m], mb1 = meta[2 * m + 1];
     const int nct = (((bw + 1) / 2) + 7) >> 3;  // column tiles needed to cover every k < bw of one parity
     uint32_t* srt = reinterpret_cast<uint32_t*>(Cs + 2 * PC * CS);
     ColOut* cinfo = reinterpret_cast<ColOut*>(srt + ((bw / 8 + 8 + 3) & ~3));
-    if (NC < 32 && tid < NC) {
+    if (tid < NC) {
         ColOut co = {nullptr, nullptr, 1.0, 1.0};
         const int fl = tid / cols_per_fn, sub = tid % cols_per_fn, f = f0 + fl;
         const int sgn = real_fmt ? 0 : (sub >> 1), part = sub & 1;
@@ -280,7 +283,6 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_inv(
     }
     for (int i = tid; i < mb0.nrt + mb1.nrt; i += blockDim.x)
         srt[i] = rt_start[(i < mb0.nrt ? mb0.rt_base : mb1.rt_base - mb0.nrt) + i];
-    cp_async_wait_all();
     __syncthreads();
     const double* tbase = table + (order_start[m] - table_shift) * 64 + lane * 2;  // B-fragment-ordered tiles
     const int g = lane >> 2, q4 = lane & 3;
@@ -300,19 +302,16 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_inv(
             for (int j = 0; j < NC / 8; ++j) acc0[j][0] = acc0[j][1] = acc1[j][0] = acc1[j][1] = 0.0;
             inv_col_tile2<NC, LEG_PF2_INV>(tbase, srt + (p ? mb0.nrt : 0), mb, ct, Cs + (p * PC + g) * CS + q4, CS, acc0, acc1);
             // ---- epilogue: lane holds column 8j + g, cosine slots c = 8 (ct + h) + 2 q4 + {0,1} of parity p, adjacent in
-            // the parity-split plane.  Column c = (function f0 + c / cpf, sign, part): closed-form destinations.
+            // the parity-split plane
             const int hp = p ? bw / 2 : (bw + 1) / 2;
-            const int part = g & 1, sgn = real_fmt ? 0 : ((g >> 1) & 1);
-            const int fl0 = real_fmt ? (g >> 1) : (g >> 2), flstep = real_fmt ? 4 : 2;
-            if (sgn && m == 0) continue;
-            double* row0 = V + (((long)(f0 + fl0) * n + (sgn ? n - m : m)) * 2 + part) * bw + p * ((bw + 1) / 2);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int c0 = 8 * (ct + h) + 2 * q4;
 #pragma unroll
                 for (int j = 0; j < NC / 8; ++j) {
-                    if (f0 + fl0 + j * flstep >= nfun) continue;
-                    double* d = row0 + (long)j * flstep * n * 2 * bw + c0;
+                    double* dst = cinfo[8 * j + g].dst;
+                    if (!dst) continue;
+                    double* d = dst + p * ((bw + 1) / 2) + c0;
                     const double v0 = h ? acc1[j][0] : acc0[j][0], v1 = h ? acc1[j][1] : acc0[j][1];
                     if (c0 + 1 < hp && ((bw & 3) == 0)) {
                         *reinterpret_cast<double2*>(d) = make_double2(v0, v1);

@@ -4,21 +4,23 @@
 //   (DLTSemi, src/legendre_transform/seminaive.c:153-198, inside the m-loops of FSTSemiMemo,
 //    src/FST_semi_memo.c:96-108,131-145,175-201)
 //
-// Why: the separate kernels were bound by phases, not by a pipe (profiles/r1_ncu_legendre_pipeline.md).  A CTA of
-// k_legendre_fwd spends ~55 % of its warp time outside the DMMA loop -- waiting for its panel (DRAM latency + 64 KB),
-// for the first table tiles, in the epilogue -- and with two or three CTAs per SM the FP64 tensor pipe idles whenever all
-// of them are in such a phase (DMMA pipe 56 % active).  One warp per SM sub-partition with >= 2 independent accumulators
-// already saturates the pipe (tools/probes/dmma_probe.cu), so what is needed is not occupancy but a panel that is always
-// ready.  Here one CTA per SM runs for the whole launch:
+// Why: K2 writes the cosine planes to HBM only for K3 to read them back (4 of 17 MiB per function and direction), and a
+// CTA of k_legendre_fwd spends about half of its warp time outside the DMMA loop -- waiting for its panel, for the
+// first table tiles of every row tile, in the epilogue (profiles/r1_ncu_pipe_summary.md).  Here one CTA per SM runs for
+// the whole launch:
 //   * 8 DCT warps (producers) turn the spectral-plane rows of the next work item into its cosine panel directly in shared
-//     memory (the panel never goes through HBM: 4 of 17 MiB per function less traffic), with the loads of the next
-//     transform in flight while the current one is computed;
+//     memory (the panel never goes through HBM), with the loads of the next transform in flight while the current one
+//     is computed;
 //   * 8 MMA warps (consumers) contract the current panel against the order's table tiles (streamed from L2 into DMMA A
 //     fragments) and store the coefficients;
 //   * two panel buffers and two mbarriers per buffer (full / empty) decouple them; no CTA-wide barrier in the loop, a
 //     consumer warp that runs out of sub-items moves on to the next panel.
 // Work items = (order m, column tile of 32 columns = (function, +-m, re/im)), ordered by decreasing cost and dealt
 // round-robin to the CTAs, so consecutive CTAs share an order's table through L2.
+// Measured (bw = 256, 256 functions per launch): 660 us against 342 + 347 us for K2 + K3 as separate kernels.  The
+// kernel is bound by its producers: DFMA and DMMA share the FP64 pipe, the consumers wait for panels a third of their
+// time; other role splits (4 + 16, 8 + 16 warps) were slower.  The second half of this file is the unfused alternative,
+// K3 alone as a persistent kernel with cp.async-streamed table tiles (S2KIT_CUDA_PIPE=1).
 #include <stdlib.h>
 
 #include "s2k_fft.cuh"
