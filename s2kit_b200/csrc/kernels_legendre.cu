@@ -105,6 +105,8 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, NC >= 32 ? 2 : 3) k_legendre_f
     const int total = mb0.nrt + mb1.nrt;
     uint32_t* srt = reinterpret_cast<uint32_t*>(Xs + 2 * PC * CS);  // row-tile starts of both parity blocks
     ColOut* cinfo = reinterpret_cast<ColOut*>(srt + ((bw / 8 + 8 + 3) & ~3));
+    // narrow panels: lane-private table-tile ring [LEG_WARPS][LEG_RING][32] behind the column table (s2k_legendre.cuh)
+    double2* ring = reinterpret_cast<double2*>(cinfo + NC) + (warp * LEG_RING * 32 + lane);
     if (NC < 32 && tid < NC) {
         // where column `tid` of the panel lands: f^(+-m, l) of function f, re or im array, with its sign
         ColOut co = {nullptr, nullptr, 1.0, 1.0};
@@ -204,11 +206,11 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, NC >= 32 ? 2 : 3) k_legendre_f
             double acc0[NC / 8][2], acc1[NC / 8][2];
     #pragma unroll
             for (int j = 0; j < NC / 8; ++j) acc0[j][0] = acc0[j][1] = acc1[j][0] = acc1[j][1] = 0.0;
-            fwd_row_tile<NC>(tbase + (uint64_t)srt[rt] * 64, Xs + gsel * CS + q4, CS, tiles_in_row(mb0, rt), acc0,
-                             PC < NC && g >= PC);
+            fwd_row_tile_async<NC>(tbase + (uint64_t)srt[rt] * 64, Xs + gsel * CS + q4, CS, tiles_in_row(mb0, rt), acc0,
+                                   PC < NC && g >= PC, ring);
             if (rt < mb1.nrt)
-                fwd_row_tile<NC>(tbase + (uint64_t)srt[mb0.nrt + rt] * 64, Xs + (PC + gsel) * CS + q4, CS,
-                                 tiles_in_row(mb1, rt), acc1, PC < NC && g >= PC);
+                fwd_row_tile_async<NC>(tbase + (uint64_t)srt[mb0.nrt + rt] * 64, Xs + (PC + gsel) * CS + q4, CS,
+                                       tiles_in_row(mb1, rt), acc1, PC < NC && g >= PC, ring);
 
             // ---- epilogue: lane holds row r = 8rt + g of both parities = degrees l - m = 2r, 2r+1, columns 8j + 2 q4 + {0,1}
             const int r = 8 * rt + g;
@@ -273,6 +275,7 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_inv(
     const int nct = (((bw + 1) / 2) + 7) >> 3;  // column tiles needed to cover every k < bw of one parity
     uint32_t* srt = reinterpret_cast<uint32_t*>(Cs + 2 * PC * CS);
     ColOut* cinfo = reinterpret_cast<ColOut*>(srt + ((bw / 8 + 8 + 3) & ~3));
+    double2* ring = reinterpret_cast<double2*>(cinfo + NC) + (warp * LEG_RING * 32 + lane);  // narrow panels only
     if (tid < NC) {
         ColOut co = {nullptr, nullptr, 1.0, 1.0};
         const int fl = tid / cols_per_fn, sub = tid % cols_per_fn, f = f0 + fl;
@@ -332,9 +335,8 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_inv(
         double acc[NC / 8][2];
 #pragma unroll
         for (int j = 0; j < NC / 8; ++j) acc[j][0] = acc[j][1] = 0.0;
-        inv_col_tile<NC>(tbase, srt + (p ? mb0.nrt : 0), mb, ct,
-                         Cs + (p * PC + (PC < NC ? (g & (PC - 1)) : g)) * CS + q4, CS, acc,
-                         PC < NC && g >= PC);
+        inv_col_tile_async<NC>(tbase, srt + (p ? mb0.nrt : 0), mb, ct,
+                               Cs + (p * PC + (PC < NC ? (g & (PC - 1)) : g)) * CS + q4, CS, acc, PC < NC && g >= PC, ring);
         // ---- epilogue: lane holds column 8j + g, cosine slots c = 8ct + 2 q4 + {0,1}
         // slots c0, c0+1 of parity p are adjacent in the parity-split plane
         const int c0 = 8 * ct + 2 * q4, hp = p ? bw / 2 : (bw + 1) / 2;
@@ -375,7 +377,7 @@ static cudaError_t leg_fwd_nc(s2kit_cuda_plan* p, const double* table, uint64_t 
     int cols_per_fn = real_fmt ? 2 : 4;
     int NF = PC / cols_per_fn;
     size_t smem = sizeof(double) * 2 * PC * panel_stride(p->bw) + sizeof(uint32_t) * ((p->bw / 8 + 8 + 3) & ~3) +
-                  sizeof(ColOut) * NC;
+                  sizeof(ColOut) * NC + (NC < 32 ? sizeof(double2) * LEG_WARPS * LEG_RING * 32 : 0);
     if (smem > 48 * 1024) {
         cudaError_t e = ensure_smem(reinterpret_cast<const void*>(k_legendre_fwd<NC, PC>), smem);
         if (e != cudaSuccess) return e;
@@ -394,7 +396,7 @@ static cudaError_t leg_inv_nc(s2kit_cuda_plan* p, const double* table, uint64_t 
     int cols_per_fn = real_fmt ? 2 : 4;
     int NF = PC / cols_per_fn;
     size_t smem = sizeof(double) * 2 * PC * panel_stride(p->bw) + sizeof(uint32_t) * ((p->bw / 8 + 8 + 3) & ~3) +
-                  sizeof(ColOut) * NC;
+                  sizeof(ColOut) * NC + (NC < 32 ? sizeof(double2) * LEG_WARPS * LEG_RING * 32 : 0);
     if (smem > 48 * 1024) {
         cudaError_t e = ensure_smem(reinterpret_cast<const void*>(k_legendre_inv<NC, PC>), smem);
         if (e != cudaSuccess) return e;

@@ -293,4 +293,81 @@ __device__ __forceinline__ void inv_col_tile2(const double* __restrict__ tbase, 
     }
 }
 
+// ---- table tiles through a lane-private shared-memory ring (narrow panels: single fields stream the table from HBM) ---
+// A register ring of N loads does not give N tiles of look-ahead: a warp has six scoreboards, the loads of a ring share
+// them, and waiting for the oldest load also waits for younger ones (profiles/r1_ncu_pipe_summary.md).  Here every lane
+// copies the 16 bytes it will feed to the DMMAs into its own slot of a ring in shared memory with cp.async;
+// cp.async.wait_group counts completions exactly and in order, so LEG_RING tiles (x 512 bytes per warp) really are in
+// flight -- what a single field needs to keep HBM busy, since every tile is used exactly once.  No other lane ever
+// touches a slot: no barrier.  ring: this lane's slot 0 (slots are 32 double2 apart).
+constexpr int LEG_RING = 8;
+
+template <int NC>
+__device__ __forceinline__ void fwd_row_tile_async(const double* __restrict__ tp, const double* xp, int CS, int ctn,
+                                                   double (&acc)[NC / 8][2], bool dead_lane, double2* ring) {
+#pragma unroll
+    for (int u = 0; u < LEG_RING; ++u) {
+        if (u < ctn) cp_async16(reinterpret_cast<double*>(ring + u * 32), tp + u * 64);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+#pragma unroll 1
+    for (int ct = 0; ct < ctn; ++ct) {
+        double2* slot = ring + (ct & (LEG_RING - 1)) * 32;
+        asm volatile("cp.async.wait_group %0;" ::"n"(LEG_RING - 1) : "memory");
+        const double2 av = *slot;
+        double b[NC / 8][2];
+#pragma unroll
+        for (int j = 0; j < NC / 8; ++j) {
+            b[j][0] = xp[j * 8 * CS + 8 * ct];
+            b[j][1] = xp[j * 8 * CS + 8 * ct + 4];
+            if (dead_lane) b[j][0] = b[j][1] = 0.0;  // MMA columns beyond a half-width panel
+        }
+#pragma unroll
+        for (int j = 0; j < NC / 8; ++j) dmma(acc[j], av.x, b[j][0]);
+#pragma unroll
+        for (int j = 0; j < NC / 8; ++j) dmma(acc[j], av.y, b[j][1]);
+        // the DMMAs above have consumed the slot's registers: refill it with the tile LEG_RING ahead
+        if (ct + LEG_RING < ctn) cp_async16(reinterpret_cast<double*>(slot), tp + (ct + LEG_RING) * 64);
+        asm volatile("cp.async.commit_group;" ::: "memory");  // one group per step, possibly empty
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+template <int NC>
+__device__ __forceinline__ void inv_col_tile_async(const double* __restrict__ tbase, const uint32_t* srt,
+                                                   const BlockMeta& mb, int ct, const double* cp, int CS,
+                                                   double (&acc)[NC / 8][2], bool dead_lane, double2* ring) {
+    const int rt_min = first_row_tile_reaching(mb, ct);
+    const int cnt = mb.nrt - rt_min;
+    if (cnt <= 0) return;
+#pragma unroll
+    for (int u = 0; u < LEG_RING; ++u) {
+        if (u < cnt)
+            cp_async16(reinterpret_cast<double*>(ring + u * 32), tbase + ((uint64_t)srt[rt_min + u] + ct) * 64);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+#pragma unroll 1
+    for (int i = 0; i < cnt; ++i) {
+        const int rt = rt_min + i;
+        double2* slot = ring + (i & (LEG_RING - 1)) * 32;
+        asm volatile("cp.async.wait_group %0;" ::"n"(LEG_RING - 1) : "memory");
+        const double2 bv = *slot;
+        double a[NC / 8][2];
+#pragma unroll
+        for (int j = 0; j < NC / 8; ++j) {
+            a[j][0] = cp[j * 8 * CS + 8 * rt];
+            a[j][1] = cp[j * 8 * CS + 8 * rt + 4];
+            if (dead_lane) a[j][0] = a[j][1] = 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < NC / 8; ++j) dmma(acc[j], a[j][0], bv.x);
+#pragma unroll
+        for (int j = 0; j < NC / 8; ++j) dmma(acc[j], a[j][1], bv.y);
+        if (i + LEG_RING < cnt)
+            cp_async16(reinterpret_cast<double*>(slot), tbase + ((uint64_t)srt[rt + LEG_RING] + ct) * 64);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 }  // namespace s2k
