@@ -147,7 +147,9 @@ static void build_layout(s2kit_cuda_plan* p, const std::vector<char>& owned) {
     p->h_unit_first.assign(bw + 1, 0);
     for (int m = 0; m < bw; ++m) {
         p->h_unit_first[m] = (int)p->h_units.size() / 2;
-        for (int l0 = m; l0 < bw; l0 += lch) {
+        // longest recurrence roll-up first: a launch ends with its slowest CTA
+        int last = m + ((bw - 1 - m) / lch) * lch;
+        for (int l0 = last; l0 >= m; l0 -= lch) {
             p->h_units.push_back(m);
             p->h_units.push_back(l0);
         }
@@ -329,10 +331,16 @@ int s2k_plan_create_impl(s2kit_cuda_plan** out, int bw, int variant, int max_bat
             m = hi;
         }
     } else {
-        // Fly: scratch ring sized for the largest order (order 0) times a few, at most ~64 MiB so it stays in L2
+        // Fly: scratch table for a group of orders.  A group must be large enough to fill the GPU with generator CTAs
+        // (two 256-thread CTAs per SM, one per 2 x 64 degrees of one order): at bw = 1024 a 64 MiB group gave 221 CTAs
+        // per launch, 17 % of the warp slots, and 23 launches per direction each waiting for its slowest CTA (ncu,
+        // profiles/r1_ncu_summary.md section 6).  A 1 GiB group no longer stays in L2, but writing and re-reading the
+        // tiles through HBM costs far less than the idle SMs did: bw = 1024 forward 5.7 -> 3.1 ms (64 MiB -> 1 GiB).
         uint64_t biggest = 0;
         for (int m = 0; m < bw; ++m) biggest = std::max(biggest, p->h_order_start[m + 1] - p->h_order_start[m]);
-        uint64_t cap = std::max<uint64_t>(biggest, (64ull << 20) / 512);
+        uint64_t ring_mb = 1024;
+        if (const char* e = getenv("S2KIT_CUDA_FLY_RING_MB")) ring_mb = std::max(1L, atol(e));
+        uint64_t cap = std::max<uint64_t>(biggest, (ring_mb << 20) / 512);
         p->fly_tiles = std::min<uint64_t>(cap, total_tiles);
         p->table_bytes = p->fly_tiles * 64 * sizeof(double);
         CK(cudaMalloc((void**)&p->d_table, p->table_bytes));
