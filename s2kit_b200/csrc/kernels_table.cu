@@ -70,7 +70,16 @@ __global__ void __launch_bounds__(NB / 8 * G) k_table_gen(double* __restrict__ t
         prev[e] = 0.0;
     }
     const double2* rc = rec + (long)m * NB;
-    for (int l = m; l < l0; ++l) rec_step(x, prev, cur, __ldg(rc + l));
+    {
+        // roll the recurrence up to the unit's first degree; the next step's (a, c) pair is loaded one step ahead (the
+        // load used to sit in front of every step: 19 % of the kernel's samples, profiles/r1_ncu_summary.md section 6)
+        double2 ac = __ldg(rc + m);
+        for (int l = m; l < l0; ++l) {
+            const double2 nx = __ldg(rc + min(l + 1, NB - 1));
+            rec_step(x, prev, cur, ac);
+            ac = nx;
+        }
+    }
 
     const double fudge = 1.0 / sqrt((double)NB);  // cospml.c:206
     for (int pair = 0; pair < lch / 2; ++pair) {
