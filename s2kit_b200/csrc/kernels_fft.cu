@@ -315,6 +315,7 @@ __global__ void __launch_bounds__(N / 8 * FPB) k_dct_fwd(const double* __restric
     // consecutive lanes hold consecutive k: even and odd k go to slot k/2 of their half of the parity-split plane, so
     // a warp writes two contiguous 128-byte runs per store
     constexpr int HALF = B / 2;
+    const double2 q0 = __ldg(qtab + t);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         if (fft_slot<R>(e) >= 4) continue;
@@ -327,7 +328,7 @@ __global__ void __launch_bounds__(N / 8 * FPB) k_dct_fwd(const double* __restric
             bi = zb.y;
         }
         // V1 = (Z[k] + conj Z[n-k]) / 2 ; V2 = (Z[k] - conj Z[n-k]) / 2i ; REDFT10 = 2 Re(e^{-i pi k/2n} V)
-        const double2 q = __ldg(qtab + k);
+        const double2 q = quarter_rot(q0, fft_slot<R>(e));  // k = t + slot n/8
         double y1 = q.x * (ar + br) + q.y * (ai - bi);
         double y2 = q.x * (ai + bi) - q.y * (ar - br);
         if (k == 0) {
@@ -359,6 +360,10 @@ __global__ void __launch_bounds__(N / 8 * FPB) k_dct_inv(const double* __restric
     const double* Vb = Va + B;
     const double c_rest = 1.0 / sqrt(2.0 * (double)N);  // 0.5/sqrt(bw), seminaive.c:72
     const double c_zero = 1.0 / sqrt((double)N);        // fcos[0] / sqrt(2 bw), seminaive.c:98
+    // e^{i pi k / 2n} for k = t + e n/8 is e^{i pi t / 2n} e^{i pi e / 16}: one table load and seven constant rotations
+    // instead of eight 16-byte loads -- K5 sits at 95 % of the LSU pipe with the FP64 pipe half idle
+    // (profiles/r1_ncu_full_metrics_final2.csv)
+    const double2 q0 = __ldg(qtab + t);
     double xr[8], xi[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -369,7 +374,7 @@ __global__ void __launch_bounds__(N / 8 * FPB) k_dct_inv(const double* __restric
             int src = k < B ? k : N - k;
             double sc = (src == 0) ? c_zero : c_rest;
             double a = __ldg(Va + cos_slot(src, B)) * sc, b = __ldg(Vb + cos_slot(src, B)) * sc;
-            double2 q = __ldg(qtab + k);
+            const double2 q = quarter_rot(q0, e);
             double ur = (k < B) ? a : b, ui = (k < B) ? b : -a;  // (a + ib) or -i (a + ib)
             wr = q.x * ur - q.y * ui;
             wi = q.x * ui + q.y * ur;

@@ -170,6 +170,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_fwd_pipe(const PipeArgs a) 
                 fft_sync<N>(g);
                 const int q = round * FPB + g;
                 double* x_re = panels + b * panel_doubles + (2 * q) * CS;  // parity 0; parity 1 is NC*CS further
+                const double2 q0 = __ldg(a.qtab + t);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     if (fft_slot<R>(e) >= 4) continue;
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) k_fwd_pipe(const PipeArgs a) 
                         br = zb.x;
                         bi = zb.y;
                     }
-                    const double2 qq = __ldg(a.qtab + kk);
+                    const double2 qq = quarter_rot(q0, fft_slot<R>(e));  // kk = t + slot n/8
                     double y1 = qq.x * (ar + br) + qq.y * (ai - bi);
                     double y2 = qq.x * (ai + bi) - qq.y * (ar - br);
                     if (kk == 0) {

@@ -190,6 +190,18 @@ struct FftRest {
     }
 };
 
+// (cos, sin)(pi k / 2n) for k = t + s n/8 is (cos, sin)(pi t / 2n) rotated by pi s / 16: the DCT kernels load one entry
+// of the quarter-wave table per thread and rotate it by these constants instead of loading eight entries (K5 sat at
+// 95 % of the LSU pipe with the FP64 pipe half idle, profiles/r1_ncu_full_metrics_final2.csv).
+__device__ __forceinline__ double2 quarter_rot(double2 q0, int s) {
+    constexpr double QC[8] = {1.0, 0.9807852804032304491, 0.9238795325112867561, 0.8314696123025452371,
+                              0.7071067811865475244, 0.5555702330196022247, 0.3826834323650897717, 0.1950903220161282678};
+    constexpr double QS[8] = {0.0, 0.1950903220161282678, 0.3826834323650897717, 0.5555702330196022247,
+                              0.7071067811865475244, 0.8314696123025452371, 0.9238795325112867561, 0.9807852804032304491};
+    if (s == 0) return q0;
+    return make_double2(q0.x * QC[s] - q0.y * QS[s], q0.x * QS[s] + q0.y * QC[s]);
+}
+
 // Forward DFT of N points spread over N/8 threads.  On entry register e holds x[t + e*N/8]; on exit it
 // holds X[fft_out_index<N>(e, t)].  sx: this transform's padded exchange row (fft_padded_len(N) double2).
 // Synchronises with fft_sync<N>(group): all N/8 threads of the transform must call it (for N < 256 every thread
