@@ -175,9 +175,12 @@ def algorithmic_per_function(bw, fmt_real):
     T0 = sum(l // 2 + 1 for l in range(bw))
     lg = math.log2(2 * bw)
     return {
-        "phi_fft": {"bytes": 128 * B2, "flops": 20 * B2 * lg},
+        # REAL format: both grid arrays are still moved (64 B^2), but only the order rows m' < bw of the spectral planes
+        # (32 B^2 instead of 64 B^2), and the contraction reads half of the cosine planes
+        "phi_fft": {"bytes": (96 if fmt_real else 128) * B2, "flops": 20 * B2 * lg},
         "dct": {"bytes": (48 if fmt_real else 96) * B2, "flops": (10 if fmt_real else 20) * B2 * lg},
-        "legendre": {"bytes": 48 * B2, "table_bytes": 8 * S, "flops": (4 * S) if fmt_real else (8 * S - 4 * T0)},
+        "legendre": {"bytes": (32 if fmt_real else 48) * B2, "table_bytes": 8 * S,
+                     "flops": (4 * S) if fmt_real else (8 * S - 4 * T0)},
     }
 
 
