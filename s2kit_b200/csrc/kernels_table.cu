@@ -13,6 +13,8 @@
 // consecutive degrees in registers, roll the recurrence from l = m up to l0 (cheap), then per pair of
 // degrees run ONE complex FFT of length bw (two real DCT-IIs via even/odd reordering + conjugate symmetry)
 // and scatter the kept entries straight into the DMMA-tiled layout (s2k_internal.cuh).
+#include <stdlib.h>
+
 #include "s2k_fft.cuh"
 #include "s2k_internal.cuh"
 
@@ -222,7 +224,17 @@ static cudaError_t table_gen_nb(s2kit_cuda_plan* p, double* table, uint64_t shif
     return cudaGetLastError();
 }
 
-int table_unit_rows(int bw) { return bw <= 512 ? 32 : 64; }
+// degrees per generator work unit: every unit rolls the recurrence up from l = m, so longer units repeat less of it, but
+// a unit is one CTA's serial chain (S2KIT_CUDA_TABLE_LCH overrides for tuning; must be even)
+int table_unit_rows(int bw) {
+    static int forced = [] {
+        const char* e = getenv("S2KIT_CUDA_TABLE_LCH");
+        int v = e ? atoi(e) : 0;
+        return (v >= 2 && v % 2 == 0) ? v : 0;
+    }();
+    if (forced) return forced;
+    return bw <= 512 ? 32 : 128;  // bw = 1024 Fly forward: 32 -> 3.57 ms, 64 -> 3.06, 128 -> 2.91, 256 -> 3.09
+}
 
 cudaError_t launch_table_gen(s2kit_cuda_plan* p, double* table, uint64_t shift, int m_lo, int m_hi, int transposed) {
     if (m_hi <= m_lo) return cudaSuccess;
