@@ -105,3 +105,20 @@ def test_product_does_not_touch_the_oracle():
                 assert "import oracle" not in txt and "liboracle" not in txt and "libs2kit_ref" not in txt, f
     out = os.popen(f"ldd {os.path.join(pkg, 'libs2kit_cuda.so')}").read()
     assert "oracle" not in out and "fftw" not in out
+
+
+def test_closed_form_tile_layout_matches_tabulated_layout(tmp_path):
+    """The persistent kernels name table tiles in closed form instead of chasing the layout tables through dependent
+    loads; a host-only program checks those formulas against the tabulated layout for bandwidths 2 .. 2048."""
+    import shutil
+    import subprocess
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "layout_check")
+    src = os.path.join(ROOT, "tests", "host_checks", "layout_check.cu")
+    r = subprocess.run([nvcc, "-std=c++17", "-O1", "-o", exe, src], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "layout mismatches: 0" in r.stdout, r.stdout + r.stderr

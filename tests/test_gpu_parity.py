@@ -290,6 +290,24 @@ def test_batched_wide_panels_match_oracle(s2, oracles, bw, batch):
     P.close()
 
 
+@pytest.mark.parametrize("mode", ["0", "1"])
+def test_alternative_forward_contractions(mode):
+    """The batched forward contraction has three implementations selected once per process by S2KIT_CUDA_PIPE: the fused
+    persistent kernel (default, covered by every other test), K2 + plain K3 ("0") and K2 + the streamed persistent K3
+    ("1").  Re-run the wide-panel parity test in a child process for the two alternatives."""
+    import os
+    import subprocess
+    import sys
+
+    env = dict(os.environ, S2KIT_CUDA_PIPE=mode)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-x", "-m", "gpu",
+                        "-k", "test_batched_wide_panels_match_oracle"], env=env, cwd=root, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "2 passed" in r.stdout, r.stdout[-500:]
+
+
 def test_batched_convolution_device(s2, oracles):
     import torch
 
