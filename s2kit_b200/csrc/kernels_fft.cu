@@ -560,6 +560,9 @@ static cudaError_t dct_fwd_n(s2kit_cuda_plan* p, const double* S, double* X, int
 template <int N>
 static cudaError_t dct_inv_n(s2kit_cuda_plan* p, const double* V, double* G, int nfun, int lo, int hi,
                              const PlaneView& pv) {
+    if constexpr (N == 512) {
+        if (fft16_enabled()) return launch_dct_inv16(p, V, G, nfun, lo, hi, pv);
+    }
     constexpr int T8 = N / 8;
     constexpr int FPB = (256 / T8) < 1 ? 1 : ((256 / T8) > 8 ? 8 : (256 / T8));
     size_t smem = sizeof(double2) * FPB * fft_padded_len(N);

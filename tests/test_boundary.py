@@ -107,18 +107,20 @@ def test_product_does_not_touch_the_oracle():
     assert "oracle" not in out and "fftw" not in out
 
 
-def test_closed_form_tile_layout_matches_tabulated_layout(tmp_path):
-    """The persistent kernels name table tiles in closed form instead of chasing the layout tables through dependent
-    loads; a host-only program checks those formulas against the tabulated layout for bandwidths 2 .. 2048."""
+@pytest.mark.parametrize("check,expect", [("layout_check", "layout mismatches: 0"), ("fft16_check", "exactly once: 0")])
+def test_host_side_checks_of_device_helpers(tmp_path, check, expect):
+    """Host-only programs built from the same headers as the kernels: (1) the closed-form tile layout the persistent
+    kernels use instead of dependent loads against the tabulated layout for bandwidths 2 .. 2048; (2) the register-level
+    pieces of the one-warp 512-point FFT (s2k_fft16.cuh) for 32 emulated lanes against a long-double DFT."""
     import shutil
     import subprocess
 
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         pytest.skip("nvcc not available")
-    exe = str(tmp_path / "layout_check")
-    src = os.path.join(ROOT, "tests", "host_checks", "layout_check.cu")
+    exe = str(tmp_path / check)
+    src = os.path.join(ROOT, "tests", "host_checks", check + ".cu")
     r = subprocess.run([nvcc, "-std=c++17", "-O1", "-o", exe, src], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
-    assert r.returncode == 0 and "layout mismatches: 0" in r.stdout, r.stdout + r.stderr
+    assert r.returncode == 0 and expect in r.stdout, r.stdout + r.stderr
