@@ -1,6 +1,6 @@
-// kernels_fft16.cu -- K5 (DCT-III along latitude) on the one-warp 512-point FFT of s2k_fft16.cuh.  Opt-in
-// (S2KIT_CUDA_FFT16=1) until it has been measured on the GPU: the arithmetic pieces are checked on the host
-// (tests/host_checks/fft16_check.cu), the kernel itself by the GPU parity tests when the switch is on.
+// kernels_fft16.cu -- K5 (DCT-III along latitude) at bw = 256 on the one-warp 512-point FFT of s2k_fft16.cuh
+// (S2KIT_CUDA_FFT16=0 falls back to k_dct_inv).  The arithmetic pieces are checked on the host
+// (tests/host_checks/fft16_check.cu), the kernel by the GPU parity tests.
 //
 // Same mathematics as k_dct_inv (kernels_fft.cu; InvDLTSemi, src/legendre_transform/seminaive.c:92-114, and the
 // (-1)^m / 1/sqrt(2 pi) of InvFSTSemiMemo, src/FST_semi_memo.c:294-348), different distribution: one warp per
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(F16_WARPS * 32, 2) k_dct_inv16(const double* _
 bool fft16_enabled() {
     static int on = [] {
         const char* e = getenv("S2KIT_CUDA_FFT16");
-        return (e && e[0] == '1') ? 1 : 0;
+        return (e && e[0] == '0') ? 0 : 1;  // default on: 1248 -> 1203 us per 1024 functions at bw = 256 (0.79 -> 0.82 of HBM peak)
     }();
     return on != 0;
 }

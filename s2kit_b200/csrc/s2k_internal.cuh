@@ -191,7 +191,7 @@ cudaError_t launch_leg_fwd_stream(s2kit_cuda_plan* p, const double* table, uint6
                                   double* rco, double* ico, long coef_stride, int nfun, int m_lo, int m_hi,
                                   int data_format);
 
-// K5 on the one-warp 512-point FFT (kernels_fft16.cu), opt-in with S2KIT_CUDA_FFT16=1
+// K5 on the one-warp 512-point FFT (kernels_fft16.cu); S2KIT_CUDA_FFT16=0 disables
 bool fft16_enabled();
 cudaError_t launch_dct_inv16(s2kit_cuda_plan* p, const double* V, double* G, int nfun, int lo, int hi, const PlaneView& pv);
 
