@@ -73,3 +73,21 @@ for k in range(1, N // 2):
     if k1 != 0:
         assert (ph, pq, pr) == (1 - h, 15 - q, 1 - r)
 print("Z[k] and Z[N-k] always live in the same warp: lane (k1, h) <-> lane ((16 - k1) % 16, 1 - h)")
+
+# The exchange the forward DCT (K2, the DCT producers of the fused kernel) needs after the FFT: lane L finishes the outputs
+# k < 256, i.e. its registers o = 2 qi (r = 0), and needs Z[N - k] for each of them.  Source lane and source register:
+out_index = lambda lane, o: (lane & 15) + 16 * ((o >> 1) + 8 * (lane >> 4)) + 256 * (o & 1)  # noqa: E731  (f16_out_index)
+where = {out_index(lane, o): (lane, o) for lane in range(32) for o in range(16)}
+rule_generic, rule_k1_zero = set(), []
+for lane in range(32):
+    k1, h = lane & 15, lane >> 4
+    for qi in range(8):
+        k = out_index(lane, 2 * qi)
+        src_lane, src_o = where[(N - k) % N]
+        if k1:
+            assert src_lane == ((16 - k1) % 16) + 16 * (1 - h) and src_o == 2 * (7 - qi) + 1
+            rule_generic.add("lane (k1, h), o = 2 qi  <-  lane (16 - k1, 1 - h), o = 2 (7 - qi) + 1")
+        else:
+            rule_k1_zero.append(((h, qi), (src_lane >> 4, src_o)))
+print("Z[N-k] for the DCT separation, k1 != 0:", *rule_generic)
+print("k1 = 0 lanes, (h, qi) <- (h', o'):", rule_k1_zero)
