@@ -126,3 +126,25 @@ def test_layout_helpers(oracle_mod):
     # totals quoted in SURVEY.md section 3.5
     for bw, total in ((64, 44736), (128, 353664), (256, 2812672)):
         assert sum(oracle_mod.table_size(m, bw) for m in range(bw)) == total
+
+
+def test_port_matches_reference_samples_bw512(oracle_mod):
+    """The port against the committed samples of the REFERENCE's bw = 512 outputs (make_golden_large.py)."""
+    import os
+
+    from conftest import GOLDEN, relerr
+
+    large = np.load(os.path.join(GOLDEN, "oracle_vectors_large.npz"))
+    bw = 512
+    gs, cs = (int(v) for v in large[f"bw{bw}_strides"])
+    O = oracle_mod.Oracle(bw, "port")
+    rc, ic = O.gen_coeffs(1000)
+    rd, idt = O.inverse(rc, ic, 0)
+    assert relerr(rd.ravel()[::gs], large[f"bw{bw}_inv_sample_r"]) < 1e-12
+    fr, fi = O.forward(rd, idt, 0)
+    assert relerr(fr[::cs], large[f"bw{bw}_fwd_sample_r"]) < 1e-12
+    assert relerr(fi[::cs], large[f"bw{bw}_fwd_sample_i"]) < 1e-12
+    O.close()
+    # the bw = 2048 fixtures: the reference returns NaN exactly for the eight orders |m| >= 2044 (pmm.c:22-30)
+    assert sorted(int(m) for m in large["bw2048_ref_nan_orders"]) == [-2047, -2046, -2045, -2044, 2044, 2045, 2046, 2047]
+    assert np.isfinite(large["bw2048_inv_sample_r"]).all()
