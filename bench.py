@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="functions in the CPU sample (0 = auto)")
+    ap.add_argument("--single-bw", type=int, default=2048, help="bandwidth of the single-field block (0 = skip)")
+    ap.add_argument("--single-steps", type=int, default=10)
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling pass (batch / n_gpus functions per GPU)")
     return ap.parse_args()
 
 
@@ -161,6 +164,26 @@ NCU_DRAM_BYTES_PER_FUNCTION_BW256_COMPLEX = {
 }
 
 
+def measured_traffic(kind, bw, fmt_real, functions_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of kernel kind `kind`, from the committed
+    `ncu --set full` capture of THIS command at the SAME launch size (profiles/r2_dram_traffic.json, written by
+    tools/ncu_traffic.py); falls back to the round-1 capture at 256 functions per launch, scaled."""
+    path = os.path.join(ROOT, "profiles", "r2_dram_traffic.json")
+    if os.path.exists(path):
+        try:
+            rec = json.load(open(path))
+            if rec.get("bw") == bw and bool(rec.get("format_real")) == bool(fmt_real):
+                ent = rec.get("kernels", {}).get(kind)
+                if ent and abs(ent["functions_per_launch"] - functions_per_launch) < 0.5:
+                    return ent["dram_bytes_per_launch"], "profiles/r2_dram_traffic.json (ncu --set full, same launch size)"
+        except Exception:
+            pass
+    if bw == 256 and not fmt_real and kind in NCU_DRAM_BYTES_PER_FUNCTION_BW256_COMPLEX:
+        return (NCU_DRAM_BYTES_PER_FUNCTION_BW256_COMPLEX[kind] * functions_per_launch,
+                "profiles/r1_ncu_full_metrics_final.csv (256 functions per launch, scaled)")
+    return None, None
+
+
 def table_doubles(bw):
     tot = 0
     for m in range(bw):
@@ -206,6 +229,167 @@ def synth_coeffs(torch, bw, batch, device, seed):
     ic[:, neg] = -ic[:, pos] * sgn
     ic[:, :bw] = 0.0
     return rc, ic
+
+
+def _event_ms(torch, fn, warmup, steps, barrier):
+    for _ in range(warmup):
+        fn()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1) / steps
+
+
+def single_field_block(a, torch, dist, s2, world, rank, local, dev, hbm_peak):
+    """The second half of BASELINE.json's metric: ONE field at bw = 2048 (configs[4], FSTSemiMemo with m-sharded tables).
+    N = 1: the whole 11.7 GB table streams through one GPU per transform.  N > 1 (torchrun): (a) every rank runs its
+    share, ring -> order exchange by NCCL all_to_all; (b) rank 0 alone drives all N GPUs through the in-library
+    s2kit_cuda_multi_* path (exchange inside the DCT kernels over peer memory).  Forward results are checked against
+    the committed sample of the reference's own output (tests/golden/oracle_vectors_large.npz)."""
+    import numpy as np
+
+    bw = a.single_bw
+    n = 2 * bw
+    steps = a.single_steps
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    golden = None
+    gpath = os.path.join(ROOT, "tests", "golden", "oracle_vectors_large.npz")
+    if bw == 2048 and os.path.exists(gpath):
+        golden = np.load(gpath)
+    rng = np.random.RandomState(2048)  # the grid the golden sample was computed from
+    rd, idt = rng.uniform(-1, 1, (n, n)), rng.uniform(-1, 1, (n, n))
+
+    def sample_err(fr, fi):
+        if golden is None:
+            return None
+        wr, wi = golden["bw2048_fwd_sample_r"], golden["bw2048_fwd_sample_i"]
+        ok = np.isfinite(wr) & np.isfinite(wi)  # the reference is NaN for |m| >= 2044 (pmm.c:22-30)
+        scale = max(np.abs(wr[ok]).max(), np.abs(wi[ok]).max())
+        return float(max(np.abs(fr[::509][ok] - wr[ok]).max(), np.abs(fi[::509][ok] - wi[ok]).max()) / scale)
+
+    out = {"workload": f"single field, FSTSemiMemo + InvFSTSemiMemo at bw={bw}, COMPLEX format, Memo tables, "
+                       f"{'sharded by order over ' + str(world) + ' GPUs' if world > 1 else 'one GPU'}",
+           "bw": bw, "n_gpus": world, "steps": steps,
+           "note": "inverse parity at bw = 2048 is pinned per order (tests/test_gpu_large.py); the reference's own 2-D "
+                   "inverse is NaN at this size and its tables lose orders ~550-950 to seed underflow (DESIGN.md section 4)"}
+    if world == 1:
+        P = s2.Plan(bw, s2.MEMO, max_batch=1, device=local)
+        P.set_stream(torch.cuda.current_stream().cuda_stream)
+        gr, gi = torch.tensor(rd, device=dev), torch.tensor(idt, device=dev)
+        cr = torch.zeros(bw * bw, device=dev, dtype=torch.float64)
+        ci = torch.zeros_like(cr)
+        og_r, og_i = torch.empty_like(gr), torch.empty_like(gi)
+        ms_f = _event_ms(torch, lambda: P.fst(gr, gi, cr, ci, s2.COMPLEX), 3, steps, barrier)
+        ms_i = _event_ms(torch, lambda: P.inv_fst(cr, ci, og_r, og_i, s2.COMPLEX), 3, steps, barrier)
+        P.profile(True)
+        P.fst(gr, gi, cr, ci, s2.COMPLEX)
+        P.inv_fst(cr, ci, og_r, og_i, s2.COMPLEX)
+        prof = {k: v[0] for k, v in P.profile_get().items() if v[1]}
+        P.profile(False)
+        one_copy = P.table_bytes() / 2  # the Memo plan keeps the tiles in A- and in B-fragment order
+        out.update({"ms_forward": ms_f, "ms_inverse": ms_i, "pairs_per_s": 1e3 / (ms_f + ms_i),
+                    "table_bytes_streamed_per_transform": one_copy, "kernel_ms_one_pair": prof,
+                    "table_stream_gbs_forward": one_copy / (ms_f * 1e-3) / 1e9,
+                    "table_stream_gbs_inverse": one_copy / (ms_i * 1e-3) / 1e9,
+                    "frac_of_hbm_peak_forward": one_copy / (ms_f * 1e-3) / 1e9 / hbm_peak,
+                    "frac_of_hbm_peak_inverse": one_copy / (ms_i * 1e-3) / 1e9 / hbm_peak,
+                    "legendre_fwd_table_stream_frac": (one_copy / (prof["legendre_fwd"] * 1e-3) / 1e9 / hbm_peak
+                                                       if "legendre_fwd" in prof else None),
+                    "legendre_inv_table_stream_frac": (one_copy / (prof["legendre_inv"] * 1e-3) / 1e9 / hbm_peak
+                                                       if "legendre_inv" in prof else None),
+                    "forward_rel_err_vs_reference_sample": sample_err(cr.cpu().numpy(), ci.cpu().numpy())})
+        P.close()
+        return out
+    # ---- (a) one process per GPU, NCCL all_to_all between the two halves of the transform
+    P = s2.ShardedPlan(bw, rank, world, device=local)
+    P.set_stream(torch.cuda.current_stream().cuda_stream)
+    nr, blk = P.rings, P.block_doubles
+    my_r = torch.tensor(rd[rank * nr:(rank + 1) * nr], device=dev)
+    my_i = torch.tensor(idt[rank * nr:(rank + 1) * nr], device=dev)
+    send = torch.zeros(world * blk, device=dev, dtype=torch.float64)
+    recv = torch.zeros_like(send)
+    cr = torch.zeros(bw * bw, device=dev, dtype=torch.float64)
+    ci = torch.zeros_like(cr)
+    out_r, out_i = torch.zeros_like(my_r), torch.zeros_like(my_i)
+
+    def forward():
+        P.fst_rings(my_r, my_i, send)
+        dist.all_to_all_single(recv, send)
+        P.fst_orders(recv, cr, ci)
+
+    def inverse():
+        P.inv_fst_orders(cr, ci, send)
+        dist.all_to_all_single(recv, send)
+        P.inv_fst_rings(recv, out_r, out_i)
+
+    ms_f = allmax(_event_ms(torch, forward, 3, steps, barrier))
+    ms_i = allmax(_event_ms(torch, inverse, 3, steps, barrier))
+    ms_x = allmax(_event_ms(torch, lambda: dist.all_to_all_single(recv, send), 3, steps, barrier))
+    forward()
+    torch.cuda.synchronize()
+    full_r, full_i = cr.clone(), ci.clone()
+    dist.all_reduce(full_r)  # owned positions are disjoint, everything else is zero
+    dist.all_reduce(full_i)
+    x_bytes = 8 * blk * (world - 1)
+    nccl = {"ms_forward": ms_f, "ms_inverse": ms_i, "pairs_per_s": 1e3 / (ms_f + ms_i), "ms_exchange_only": ms_x,
+            "exchange_share_of_forward": ms_x / ms_f, "exchange_bytes_per_gpu": x_bytes,
+            "exchange_gbs_per_gpu": x_bytes / (ms_x * 1e-3) / 1e9, "table_bytes_per_gpu": P.table_bytes(),
+            "table_stream_gbs_per_gpu_forward": 0.5 * P.table_bytes() / (ms_f * 1e-3) / 1e9,
+            "forward_rel_err_vs_reference_sample": sample_err(full_r.cpu().numpy(), full_i.cpu().numpy())}
+    out["nccl_all_to_all"] = nccl
+    P.close()
+    del send, recv
+    barrier()
+    # ---- (b) rank 0 drives all GPUs through the C-ABI (s2kit_cuda_multi_*): no NCCL, the DCT kernels do the exchange
+    if rank == 0:
+        try:
+            M = s2.MultiPlan(bw, world)
+            got_r, got_i = M.forward(rd, idt)  # host-pointer call: also loads the device-resident buffers
+            ms_mf = M.run(inverse=False, iters=steps)
+            ms_mf = M.run(inverse=False, iters=steps)
+            ms_mi = M.run(inverse=True, iters=steps)
+            ms_mi = M.run(inverse=True, iters=steps)
+            t0 = time.perf_counter()
+            M.forward(rd, idt)
+            wall = time.perf_counter() - t0
+            fr, fi = full_r.cpu().numpy(), full_i.cpu().numpy()
+            ok = np.isfinite(fr) & np.isfinite(got_r)
+            out["in_library_p2p"] = {
+                "ms_forward": ms_mf, "ms_inverse": ms_mi, "pairs_per_s": 1e3 / (ms_mf + ms_mi),
+                "table_bytes_per_gpu": M.table_bytes_per_gpu(),
+                "table_stream_gbs_per_gpu_forward": 0.5 * M.table_bytes_per_gpu() / (ms_mf * 1e-3) / 1e9,
+                "host_pointer_forward_wall_ms": wall * 1e3,
+                "forward_rel_err_vs_reference_sample": sample_err(got_r, got_i),
+                "rel_err_vs_nccl_path": float(max(np.abs(got_r - fr)[ok].max(), np.abs(got_i - fi)[ok].max()) /
+                                              np.abs(fr[ok]).max()),
+                "note": "one process, s2kit_cuda_multi_run: device-resident rings/coefficients, CUDA-event time per "
+                        "transform, maximum over the GPUs; ring<->order exchange = NVLink loads/stores inside K2/K5"}
+            M.close()
+        except Exception as ex:  # noqa: BLE001 -- e.g. no peer access on this box: report, do not lose the line
+            out["in_library_p2p"] = {"unavailable": repr(ex)[:300]}
+    barrier()
+    best = out["nccl_all_to_all"]
+    if rank == 0 and "ms_forward" in out.get("in_library_p2p", {}):
+        if out["in_library_p2p"]["pairs_per_s"] > best["pairs_per_s"]:
+            best = out["in_library_p2p"]
+    out.update({"ms_forward": best["ms_forward"], "ms_inverse": best["ms_inverse"], "pairs_per_s": best["pairs_per_s"]})
+    return out
 
 
 def run_ours(a):
@@ -292,6 +476,35 @@ def run_ours(a):
         ms = float(t.item())
     value = world * batch * a.steps / (ms * 1e-3)
 
+    # ---- strong scaling: BASELINE configs[2] as written -- the SAME 1024 functions sharded over the N GPUs
+    strong = None
+    if not a.no_strong:
+        sb = max(1, batch // world)
+
+        def sstep():
+            plan.inv_fst(rc[:sb], ic[:sb], rd[:sb], idt[:sb], fmt)
+            plan.fst(rd[:sb], idt[:sb], rc2[:sb], ic2[:sb], fmt)
+
+        if world == 1:
+            strong = {"total_functions": sb, "functions_per_gpu": sb, "value": value, "unit": UNIT,
+                      "ms_per_step": ms / a.steps, "note": "N = 1: identical to the weak-scaling run above"}
+        else:
+            for _ in range(3):
+                sstep()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(a.steps):
+                sstep()
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sms = float(t.item())
+            strong = {"total_functions": sb * world, "functions_per_gpu": sb, "value": sb * world * a.steps / (sms * 1e-3),
+                      "unit": UNIT, "ms_per_step": sms / a.steps,
+                      "note": "same total work as the 1-GPU run, independent functions per rank, no collective"}
+
     # ---- end to end through the C-ABI with pinned host buffers
     e2e = None
     if not a.no_e2e:
@@ -367,11 +580,9 @@ def run_ours(a):
     roofline = None
     if dom:
         d = stages[dom]
-        traffic = None
-        if bw == 256 and fmt == s2.COMPLEX and dom in NCU_DRAM_BYTES_PER_FUNCTION_BW256_COMPLEX:
-            traffic = NCU_DRAM_BYTES_PER_FUNCTION_BW256_COMPLEX[dom] * d["functions_per_launch"]
+        traffic, traffic_src = measured_traffic(dom, bw, fmt == s2.REAL, d["functions_per_launch"])
         roofline = {"kernel": dom, "bound": d["bound"], "achieved": d["achieved"], "peak": d["peak"], "unit": d["unit"],
-                    "frac": d["frac"], "traffic": traffic,
+                    "frac": d["frac"], "traffic": traffic, "traffic_source": traffic_src,
                     "alg_bytes_per_launch": d["alg_bytes_per_launch"], "alg_flops_per_launch": d["alg_flops_per_launch"],
                     "peak_source": (hbm_src if d["bound"] == "hbm" else
                                     "FP64 tensor (DMMA mma.sync.m8n8k4.f64) micro-benchmark measured in this run; "
@@ -388,6 +599,16 @@ def run_ours(a):
                "sample": f"{sample} functions on {cores} host threads, InvFSTSemiMemo+FSTSemiMemo of the reference "
                          f"(FFTW replaced by oracle/fftw_stub), tables excluded"}
 
+    single = None
+    if a.single_bw:
+        plan.close()
+        del rd, idt, rc2, ic2
+        torch.cuda.empty_cache()
+        try:
+            single = single_field_block(a, torch, dist, s2, world, rank, local, dev, hbm_peak)
+        except Exception as ex:  # noqa: BLE001 -- never lose the headline line to the second block
+            single = {"error": repr(ex)[:400]}
+
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
@@ -399,6 +620,7 @@ def run_ours(a):
                        "sharding": "independent functions per rank, no collective"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "stages": stages,
             "fp64_peak_measured": fp64, "cpu_baseline": cpu, "roundtrip_max_abs_err": err,
+            "strong_scaling": strong, "single_field": single,
         }
         print(json.dumps(out))
     plan.close()

@@ -59,6 +59,11 @@ int s2kit_cuda_plan_create(s2kit_cuda_plan** out, int bw, int variant, int max_b
  * s2kit_cuda_fst_rings() / s2kit_cuda_fst_orders(). */
 int s2kit_cuda_plan_create_sharded(s2kit_cuda_plan** out, int bw, int variant, int device, int rank, int nranks);
 
+/* A second plan object for the same bandwidth that shares `src`'s device tables and constants (read-only after
+ * creation) and owns its stream and workspaces.  A plan object runs one transform at a time (every entry point takes
+ * the plan's lock); concurrent host threads use one clone each.  `src` must outlive its clones. */
+int s2kit_cuda_plan_clone(s2kit_cuda_plan** out, const s2kit_cuda_plan* src, int max_batch);
+
 int s2kit_cuda_plan_destroy(s2kit_cuda_plan* plan);
 
 /* Run on a caller-provided cudaStream_t (e.g. the framework's current stream) instead of the plan's own. */
@@ -121,6 +126,29 @@ int s2kit_cuda_inv_fst_rings(s2kit_cuda_plan* plan, const double* recvbuf, doubl
 int s2kit_cuda_shard_layout(int bw, int nranks, int rank, int* orders_out, int* rows_out);
 /* geometry of the exchange: doubles per (src,dst) block, rings per rank, orders rows per rank */
 int s2kit_cuda_shard_info(const s2kit_cuda_plan* plan, long* block_doubles, int* rings_per_rank, int* rows_per_rank);
+
+/* ---- one transform on several GPUs of one process (multi.cu) ---------------------------------------
+ * Single large-bandwidth field (BASELINE configs[4]: FSTSemiMemo, src/FST_semi_memo.c:68-202, at bw = 2048): latitude
+ * rings and orders are split over `ngpu` devices (NULL devices = 0..ngpu-1), every GPU keeps only its orders' tables,
+ * and the ring <-> order exchange happens inside the DCT kernels as NVLink loads / stores on peer-mapped buffers -- no
+ * separate collective, no NCCL.  Needs peer access between the devices.  COMPLEX format.
+ * The drop-in layer routes FSTSemiMemo / InvFSTSemiMemo through this when S2KIT_CUDA_NGPU > 1 (bw >= 512). */
+typedef struct s2kit_cuda_multi s2kit_cuda_multi;
+int s2kit_cuda_multi_create(s2kit_cuda_multi** out, int bw, int ngpu, const int* devices);
+int s2kit_cuda_multi_destroy(s2kit_cuda_multi* mp);
+int s2kit_cuda_multi_ngpu(const s2kit_cuda_multi* mp);
+size_t s2kit_cuda_multi_table_bytes_per_gpu(const s2kit_cuda_multi* mp);
+/* host pointers: full 2bw x 2bw grids, full bw*bw coefficient arrays (every entry written); synchronous */
+int s2kit_cuda_multi_fst(s2kit_cuda_multi* mp, const double* rdata, const double* idata, double* rcoeffs,
+                         double* icoeffs);
+int s2kit_cuda_multi_inv_fst(s2kit_cuda_multi* mp, const double* rcoeffs, const double* icoeffs, double* rdata,
+                             double* idata);
+/* device-resident form: GPU g's latitude rings [2bw/ngpu][2bw] and its full-size coefficient arrays (only the owned
+ * orders are read / written) live in the plan's own buffers; `iters` transforms run back to back and
+ * *ms_per_transform is the device time (CUDA events on every GPU's stream, maximum over the GPUs). */
+int s2kit_cuda_multi_buffers(s2kit_cuda_multi* mp, int g, int* device, double** ring_r, double** ring_i,
+                             double** coef_r, double** coef_i);
+int s2kit_cuda_multi_run(s2kit_cuda_multi* mp, int inverse, int iters, double* ms_per_transform);
 
 /* ---- tables -------------------------------------------------------------------------------------- */
 /* Copies order m's table to host memory in the reference's packed layout (GenerateCosPmlTable,

@@ -50,6 +50,17 @@ def lib():
     L.s2kit_cuda_plan_create.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci]
     L.s2kit_cuda_plan_create_sharded.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, ci]
     L.s2kit_cuda_plan_destroy.argtypes = [vp]
+    L.s2kit_cuda_plan_clone.argtypes = [ctypes.POINTER(vp), vp, ci]
+    L.s2kit_cuda_multi_create.argtypes = [ctypes.POINTER(vp), ci, ci, ctypes.POINTER(ci)]
+    L.s2kit_cuda_multi_destroy.argtypes = [vp]
+    L.s2kit_cuda_multi_ngpu.argtypes = [vp]
+    L.s2kit_cuda_multi_table_bytes_per_gpu.restype = cs
+    L.s2kit_cuda_multi_table_bytes_per_gpu.argtypes = [vp]
+    L.s2kit_cuda_multi_fst.argtypes = [vp, vp, vp, vp, vp]
+    L.s2kit_cuda_multi_inv_fst.argtypes = [vp, vp, vp, vp, vp]
+    L.s2kit_cuda_multi_buffers.argtypes = [vp, ci, ctypes.POINTER(ci), ctypes.POINTER(vp), ctypes.POINTER(vp),
+                                           ctypes.POINTER(vp), ctypes.POINTER(vp)]
+    L.s2kit_cuda_multi_run.argtypes = [vp, ci, ci, _P]
     L.s2kit_cuda_plan_set_stream.argtypes = [vp, vp]
     L.s2kit_cuda_plan_stream.restype = vp
     L.s2kit_cuda_plan_stream.argtypes = [vp]
@@ -147,6 +158,15 @@ class Plan:
             self.close()
         except Exception:
             pass
+
+    def clone(self, max_batch=1):
+        """A plan that shares this plan's device tables but owns its stream and workspaces (one per host thread)."""
+        q = Plan.__new__(Plan)
+        q.bw, q.n, q.variant = self.bw, self.n, self.variant
+        h = ctypes.c_void_p()
+        _check(lib().s2kit_cuda_plan_clone(ctypes.byref(h), self.h, max_batch), "plan_clone")
+        q.h = h
+        return q
 
     # -- stream / measurement
     def set_stream(self, cuda_stream_ptr):
@@ -318,6 +338,52 @@ class ShardedPlan:
                 a = index_of_harmonic_coeff(sm, m, self.bw)
                 mask[a:a + self.bw - m] = True
         return mask
+
+
+class MultiPlan:
+    """One single-field transform on `ngpu` GPUs of this process (s2kit_cuda_multi_*, csrc/multi.cu): rings and orders
+    split over the devices, the ring <-> order exchange done by the DCT kernels on peer-mapped memory."""
+
+    def __init__(self, bw, ngpu, devices=None):
+        self.bw, self.n, self.ngpu = bw, 2 * bw, ngpu
+        h = ctypes.c_void_p()
+        devs = (ctypes.c_int * ngpu)(*devices) if devices is not None else None
+        _check(lib().s2kit_cuda_multi_create(ctypes.byref(h), bw, ngpu, devs), "multi_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().s2kit_cuda_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def table_bytes_per_gpu(self):
+        return lib().s2kit_cuda_multi_table_bytes_per_gpu(self.h)
+
+    def forward(self, rdata, idata):
+        rd, idt = (np.ascontiguousarray(a, dtype=np.float64) for a in (rdata, idata))
+        rc, ic = np.full(self.bw * self.bw, np.nan), np.full(self.bw * self.bw, np.nan)
+        _check(lib().s2kit_cuda_multi_fst(self.h, rd.ctypes.data, idt.ctypes.data, rc.ctypes.data, ic.ctypes.data),
+               "multi_fst")
+        return rc, ic
+
+    def inverse(self, rco, ico):
+        rc, ic = (np.ascontiguousarray(a, dtype=np.float64) for a in (rco, ico))
+        rd, idt = np.full((self.n, self.n), np.nan), np.full((self.n, self.n), np.nan)
+        _check(lib().s2kit_cuda_multi_inv_fst(self.h, rc.ctypes.data, ic.ctypes.data, rd.ctypes.data, idt.ctypes.data),
+               "multi_inv_fst")
+        return rd, idt
+
+    def run(self, inverse=False, iters=1):
+        """`iters` device-resident transforms on the plan's own buffers; returns ms per transform (device time)."""
+        ms = ctypes.c_double()
+        _check(lib().s2kit_cuda_multi_run(self.h, 1 if inverse else 0, iters, ctypes.byref(ms)), "multi_run")
+        return ms.value
 
 
 def measure_fp64_peak(device=0):

@@ -283,17 +283,27 @@ __global__ void __launch_bounds__(N / 8 * FPB) k_dct_fwd(const double* __restric
     const int mp = pv.rowlist ? pv.rowlist[rsel] : ridx_to_row(rsel, B);
     const int m = mp < B ? mp : N - mp;
     const double* w = weights + ((m & 1) ? N : 0);
-    const double* Sr = S + (long)f * 2 * N * N + (long)(pv.rowlist ? rsel : mp) * pv.lrow_stride;
+    const long rowoff = (long)(pv.rowlist ? rsel : mp) * pv.lrow_stride;
+    const double* Sr = S + (long)f * 2 * N * N + rowoff;
     const double* Si = Sr + pv.part_stride;
     double xr[8], xi[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         int p = t + e * T8;
         double wj = __ldg(w + p);  // weights are stored in load order (s2k_host_reordered)
+        if (pv.use_segptr) {
+            // single field over the GPUs of one process: the segment lives in a peer's memory -- the ring -> order
+            // exchange IS these loads (NVLink reads of contiguous runs, overlapped with the transforms of other CTAs)
+            const int j = (p < B) ? 2 * p : 2 * (N - 1 - p) + 1;
+            const double* src = pv.segptr[j >> pv.seg_shift] + rowoff + (j & pv.seg_mask);
+            xr[e] = src[0] * wj;
+            xi[e] = src[pv.part_stride] * wj;
+            continue;
+        }
         long at = p;               // lat_perm: the row already is in load order
         if (!pv.lat_perm) {
             int j = (p < B) ? 2 * p : 2 * (N - 1 - p) + 1;
-            at = (long)(j >> pv.seg_shift) * pv.seg_stride + (j & pv.seg_mask);
+            at = seg_offset(pv, j);
         }
         xr[e] = __ldg(Sr + at) * wj;
         xi[e] = __ldg(Si + at) * wj;
@@ -385,16 +395,25 @@ __global__ void __launch_bounds__(N / 8 * FPB) k_dct_inv(const double* __restric
     fft_block<N>(xr, xi, sx, t, g, tw);
     if (!live) return;
     double sign = ((mp > B) && (m & 1)) ? -out_scale : out_scale;  // (-1)^m for negative orders
-    double* Gr = G + (long)f * 2 * N * N + (long)(pv.rowlist ? rsel : mp) * pv.lrow_stride;
+    const long rowoff = (long)(pv.rowlist ? rsel : mp) * pv.lrow_stride;
+    double* Gr = G + (long)f * 2 * N * N + rowoff;
     double* Gi = Gr + pv.part_stride;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         int i = fft_out_index<N>(e, t);
         double s = (m & 1) ? __ldg(sinv + i) * sign : sign;  // sines stored in output order (s2k_host_reordered)
+        if (pv.use_segptr) {
+            // order -> ring exchange as NVLink stores into the ring owner's receive block (multi.cu)
+            const int j = (i < B) ? 2 * i : 2 * (N - 1 - i) + 1;
+            double* dst = const_cast<double*>(pv.segptr[j >> pv.seg_shift]) + rowoff + (j & pv.seg_mask);
+            dst[0] = xi[e] * s;
+            dst[pv.part_stride] = xr[e] * s;
+            continue;
+        }
         long at = i;  // lat_perm: the row is kept in output order
         if (!pv.lat_perm) {
             int j = (i < B) ? 2 * i : 2 * (N - 1 - i) + 1;
-            at = (long)(j >> pv.seg_shift) * pv.seg_stride + (j & pv.seg_mask);
+            at = seg_offset(pv, j);
         }
         Gr[at] = xi[e] * s;  // Re z -> column a (real part)
         Gi[at] = xr[e] * s;  // Im z -> column b (imaginary part)

@@ -54,16 +54,24 @@ __global__ void __launch_bounds__(F16_WARPS * 32, 2) k_dct_inv16(const double* _
     }
     f16_fft512_warp(xr, xi, ex, lane, tw);
     const double sign = ((mp > B) && (m & 1)) ? -out_scale : out_scale;  // (-1)^m for negative orders
-    double* Gr = G + (long)f * 2 * N * N + (long)(pv.rowlist ? ridx : mp) * pv.lrow_stride;
+    const long rowoff = (long)(pv.rowlist ? ridx : mp) * pv.lrow_stride;
+    double* Gr = G + (long)f * 2 * N * N + rowoff;
     double* Gi = Gr + pv.part_stride;
 #pragma unroll
     for (int o = 0; o < 16; ++o) {
         const int i = f16_out_index(lane, o);
         const double s = (m & 1) ? __ldg(sinv + i) * sign : sign;  // sines stored in output order (s2k_host_reordered)
+        if (pv.use_segptr) {  // peer-mapped ring blocks (multi.cu)
+            const int j = (i < B) ? 2 * i : 2 * (N - 1 - i) + 1;
+            double* dst = const_cast<double*>(pv.segptr[j >> pv.seg_shift]) + rowoff + (j & pv.seg_mask);
+            dst[0] = xi[o] * s;
+            dst[pv.part_stride] = xr[o] * s;
+            continue;
+        }
         long at = i;  // lat_perm: the row is kept in output order
         if (!pv.lat_perm) {
             const int j = (i < B) ? 2 * i : 2 * (N - 1 - i) + 1;
-            at = (long)(j >> pv.seg_shift) * pv.seg_stride + (j & pv.seg_mask);
+            at = seg_offset(pv, j);
         }
         Gr[at] = xi[o] * s;  // Re z -> column a (real part)
         Gi[at] = xr[o] * s;  // Im z -> column b (imaginary part)

@@ -519,7 +519,7 @@ static bool pipe_enabled() {
 
 // batched launches at bw = 128 / 256 whose columns fill at least one 32-column panel
 bool fwd_pipe_supported(const s2kit_cuda_plan* p, int nfun, int data_format) {
-    if (!pipe_enabled() || !p->fast || p->fuse) return false;
+    if (!pipe_enabled() || !p->fast) return false;
     if (p->n != 256 && p->n != 512) return false;
     return nfun * (data_format == S2KIT_REAL ? 2 : 4) >= PIPE_NC;
 }
@@ -532,13 +532,7 @@ static cudaError_t fwd_pipe_n(s2kit_cuda_plan* p, const PipeArgs& a) {
                         8 * 2 * PIPE_STAGES;
     cudaError_t e = ensure_smem(reinterpret_cast<const void*>(k_fwd_pipe<N>), smem);
     if (e != cudaSuccess) return e;
-    cudaDeviceProp prop;
-    static int sms = 0;
-    if (!sms) {
-        e = cudaGetDeviceProperties(&prop, p->device);
-        if (e != cudaSuccess) return e;
-        sms = prop.multiProcessorCount;
-    }
+    const int sms = p->sm_count;
     const int nitems = a.norders * a.ncoltiles;
     k_fwd_pipe<N><<<nitems < sms ? nitems : sms, PIPE_THREADS, smem, p->stream>>>(a);
     return cudaGetLastError();
@@ -606,13 +600,7 @@ cudaError_t launch_leg_fwd_stream(s2kit_cuda_plan* p, const double* table, uint6
                         sizeof(double2) * STR_MMA_WARPS * STR_RING * 32;
     cudaError_t e = ensure_smem(reinterpret_cast<const void*>(k_leg_fwd_stream), smem);
     if (e != cudaSuccess) return e;
-    static int sms = 0;
-    if (!sms) {
-        cudaDeviceProp prop;
-        e = cudaGetDeviceProperties(&prop, p->device);
-        if (e != cudaSuccess) return e;
-        sms = prop.multiProcessorCount;
-    }
+    const int sms = p->sm_count;
     const int nitems = a.norders * a.ncoltiles;
     int slot = prof_begin(p, S2KIT_K_LEGENDRE_FWD);
     k_leg_fwd_stream<<<nitems < sms ? nitems : sms, STR_THREADS, smem, p->stream>>>(a);

@@ -119,27 +119,39 @@ __global__ void __launch_bounds__(NB / 8 * G) k_table_gen(double* __restrict__ t
     }
 }
 
-// Any bandwidth <= 1024: one CTA per order, thread i owns node i, DCT by the O(bw^2) definition.
+// Any bandwidth: one CTA per order, thread i owns the nodes i, i + blockDim, ... (two per thread above bw = 1024), DCT by
+// the O(bw^2) definition.  Used for bandwidths that are not powers of two (the reference accepts any bw).
+constexpr int DIRECT_NODES = 2;
 __global__ void k_table_gen_direct(double* __restrict__ table, const uint64_t* __restrict__ order_start, uint64_t shift,
                                    const BlockMeta* __restrict__ meta, const uint32_t* __restrict__ rt_start, int m_lo,
                                    int bw, int transposed, const double* __restrict__ nodes, const double* __restrict__ seeds,
                                    const double2* __restrict__ rec, const double2* __restrict__ qtab) {
     extern __shared__ double sm[];
-    const int m = m_lo + blockIdx.x, i = threadIdx.x;
+    const int m = m_lo + blockIdx.x;
     const BlockMeta mb0 = meta[2 * m], mb1 = meta[2 * m + 1];
     const uint64_t tile0 = order_start[m] - shift;
-    double x = 0.0, prev = 0.0, cur = 0.0;
-    if (i < bw) {
-        x = nodes[i];
-        cur = seeds[(long)m * bw + i];
+    double x[DIRECT_NODES], prev[DIRECT_NODES], cur[DIRECT_NODES];
+#pragma unroll
+    for (int u = 0; u < DIRECT_NODES; ++u) {
+        const int i = threadIdx.x + u * blockDim.x;
+        x[u] = prev[u] = cur[u] = 0.0;
+        if (i < bw) {
+            x[u] = nodes[i];
+            cur[u] = seeds[(long)m * bw + i];
+        }
     }
     const double fudge = 1.0 / sqrt((double)bw);
     for (int l = m; l < bw; ++l) {
-        if (i < bw) sm[i] = cur;
+#pragma unroll
+        for (int u = 0; u < DIRECT_NODES; ++u) {
+            const int i = threadIdx.x + u * blockDim.x;
+            if (i < bw) sm[i] = cur[u];
+        }
         __syncthreads();
-        const int k = i, p = (l - m) & 1, r = (l - m) >> 1;
+        const int p = (l - m) & 1, r = (l - m) >> 1;
         const BlockMeta& mb = p ? mb1 : mb0;
-        if (k < bw && (k & 1) == p && (k >> 1) < mb.len0 + r) {
+        for (int k = threadIdx.x; k < bw; k += blockDim.x) {
+            if ((k & 1) != p || (k >> 1) >= mb.len0 + r) continue;
             double acc = 0.0;
             for (int s = 0; s < bw; ++s) acc += sm[s] * qtab[(int)(((long)(2 * s + 1) * k) % (4 * bw))].x;
             acc *= 2.0;
@@ -147,13 +159,16 @@ __global__ void k_table_gen_direct(double* __restrict__ table, const uint64_t* _
             tile_store(table, tile0, mb, rt_start, r, k >> 1, acc * fudge, transposed);
         }
         __syncthreads();
-        if (i < bw && l + 1 < bw) {
-            double2 ac = rec[(long)m * bw + l];
-            double t1 = __dmul_rn(ac.y, prev);
-            double t2 = __dmul_rn(cur, x);
-            double t3 = __dmul_rn(ac.x, t2);
-            prev = cur;
-            cur = __dadd_rn(t3, t1);
+        if (l + 1 < bw) {
+            const double2 ac = rec[(long)m * bw + l];
+#pragma unroll
+            for (int u = 0; u < DIRECT_NODES; ++u) {
+                double t1 = __dmul_rn(ac.y, prev[u]);
+                double t2 = __dmul_rn(cur[u], x[u]);
+                double t3 = __dmul_rn(ac.x, t2);
+                prev[u] = cur[u];
+                cur[u] = __dadd_rn(t3, t1);
+            }
         }
     }
 }
@@ -257,6 +272,7 @@ cudaError_t launch_table_gen(s2kit_cuda_plan* p, double* table, uint64_t shift, 
         }
     } else {
         int nt = ((p->bw + 31) / 32) * 32;
+        if (nt > 1024) nt = ((p->bw + 63) / 64) * 32;  // two nodes per thread
         k_table_gen_direct<<<m_hi - m_lo, nt, sizeof(double) * p->bw, p->stream>>>(
             table, p->d_order_start, shift, p->d_meta, p->d_rt_start, m_lo, p->bw, transposed, p->d_nodes, p->d_seeds, p->d_rec,
             p->d_q_b);

@@ -57,8 +57,13 @@ cudaError_t ensure_smem(const void* kernel, size_t bytes) {
     return e;
 }
 
+void prof_collect_slots(s2kit_cuda_plan* p);
 int prof_begin(s2kit_cuda_plan* p, int kind) {
     if (!p->profiling) return -1;
+    if (p->prof_used >= 4096) {  // bounded: fold the finished brackets into the totals and recycle the slots
+        cudaStreamSynchronize(p->stream);
+        prof_collect_slots(p);
+    }
     if (p->prof_used == p->prof_slots.size()) {
         ProfileSlot s;
         cudaEventCreate(&s.a);
@@ -76,7 +81,7 @@ void prof_end(s2kit_cuda_plan* p, int slot) {
 }
 }  // namespace s2k
 
-static void prof_collect(s2kit_cuda_plan* p) {
+void s2k::prof_collect_slots(s2kit_cuda_plan* p) {
     for (size_t i = 0; i < p->prof_used; ++i) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, p->prof_slots[i].a, p->prof_slots[i].b) == cudaSuccess) {
@@ -89,11 +94,13 @@ static void prof_collect(s2kit_cuda_plan* p) {
 
 extern "C" int s2kit_cuda_profile_enable(s2kit_cuda_plan* p, int on) {
     if (!p) return fail_msg("null plan");
+    std::lock_guard<std::mutex> lock(*p->mu);
     p->profiling = on != 0;
     return 0;
 }
 extern "C" int s2kit_cuda_profile_reset(s2kit_cuda_plan* p) {
     if (!p) return fail_msg("null plan");
+    std::lock_guard<std::mutex> lock(*p->mu);
     CK(cudaStreamSynchronize(p->stream));
     p->prof_used = 0;
     for (int k = 0; k < S2KIT_K_COUNT; ++k) {
@@ -104,8 +111,9 @@ extern "C" int s2kit_cuda_profile_reset(s2kit_cuda_plan* p) {
 }
 extern "C" int s2kit_cuda_profile_get(s2kit_cuda_plan* p, double* ms, long* launches) {
     if (!p) return fail_msg("null plan");
+    std::lock_guard<std::mutex> lock(*p->mu);
     CK(cudaStreamSynchronize(p->stream));
-    prof_collect(p);
+    s2k::prof_collect_slots(p);
     for (int k = 0; k < S2KIT_K_COUNT; ++k) {
         if (ms) ms[k] = p->prof_ms[k];
         if (launches) launches[k] = p->prof_launches[k];
@@ -209,11 +217,15 @@ static void make_plane_tensor_map(s2kit_cuda_plan* p) {
     p->tma_S_ok = (r == CUDA_SUCCESS);
 }
 
+// Uploads go through the plan's own (non-blocking) stream, so the kernels launched on it afterwards are ordered behind
+// them; the host buffers are temporaries, hence the synchronisation before returning.
 template <typename T>
-static cudaError_t upload(T** dptr, const void* host, size_t count) {
+static cudaError_t upload(cudaStream_t st, T** dptr, const void* host, size_t count) {
     cudaError_t e = cudaMalloc((void**)dptr, count * sizeof(T));
     if (e != cudaSuccess) return e;
-    return cudaMemcpy(*dptr, host, count * sizeof(T), cudaMemcpyHostToDevice);
+    e = cudaMemcpyAsync(*dptr, host, count * sizeof(T), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(st);
 }
 
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
@@ -221,6 +233,19 @@ static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 void s2k_shard_destroy(s2kit_cuda_plan* p);
 int s2k_fail_msg(const char* what) { return fail_msg(what); }
 int s2k_fail_cuda(const char* what, cudaError_t e) { return fail(what, e); }
+
+// The caller's current device is left as it was found (plan creation and every entry point switch to the plan's).
+struct DeviceGuard {
+    int saved = -1;
+    DeviceGuard() {
+        if (cudaGetDevice(&saved) != cudaSuccess) saved = -1;
+    }
+    ~DeviceGuard() {
+        if (saved >= 0) cudaSetDevice(saved);
+    }
+};
+
+static int plan_build(s2kit_cuda_plan* p, int bw, int variant, int max_batch, int device, int rank, int nranks);
 
 int s2k_plan_create_impl(s2kit_cuda_plan** out, int bw, int variant, int max_batch, int device, int rank,
                          int nranks) {
@@ -233,9 +258,23 @@ int s2k_plan_create_impl(s2kit_cuda_plan** out, int bw, int variant, int max_bat
     if (e0 != cudaSuccess || ndev == 0)
         return fail_msg("no CUDA device available: s2kit_cuda has no CPU fallback");
     if (device < 0 || device >= ndev) return fail_msg("invalid device index");
+    DeviceGuard guard;
     CK(cudaSetDevice(device));
-
     s2kit_cuda_plan* p = new s2kit_cuda_plan();
+    p->mu = new std::mutex();
+    int rc = plan_build(p, bw, variant, max_batch, device, rank, nranks);
+    if (rc) {
+        // every partial allocation (stream, GBs of tables at large bw) goes back; the error text survives
+        std::string keep = g_last_error;
+        s2kit_cuda_plan_destroy(p);
+        g_last_error = keep;
+        return rc;
+    }
+    *out = p;
+    return 0;
+}
+
+static int plan_build(s2kit_cuda_plan* p, int bw, int variant, int max_batch, int device, int rank, int nranks) {
     p->bw = bw;
     p->n = 2 * bw;
     p->variant = variant;
@@ -244,18 +283,15 @@ int s2k_plan_create_impl(s2kit_cuda_plan** out, int bw, int variant, int max_bat
     p->nranks = nranks;
     p->fast = is_pow2(bw) && bw >= 16;
     {
-        // The fused DCT+Legendre kernels save 4 of 17 MiB of HBM traffic per function and direction but are ~4%
-        // slower than the separate kernels at bw = 256 today (profiles/r1_ncu_summary.md): opt-in.
-        const char* fu = getenv("S2KIT_CUDA_FUSE");
-        p->fuse = (fu && fu[0] == '1');
         // persisting-L2 carve-out for the tables: measured neutral with one table copy and harmful with two (it takes
         // L2 away from the streaming kernels), the per-CTA bulk prefetch already does the job -- opt-in
         const char* np = getenv("S2KIT_CUDA_L2PERSIST");
         p->l2_persist = (np && np[0] == '1');
     }
-    if (!p->fast && bw > 512) {
-        delete p;
-        return fail_msg("bandwidths above 512 must be powers of two");
+    {
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        p->sm_count = prop.multiProcessorCount;
     }
     CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     const int n = p->n;
@@ -271,20 +307,20 @@ int s2k_plan_create_impl(s2kit_cuda_plan** out, int bw, int variant, int max_bat
         s2k_host_twiddles(bw, tb.data());
         s2k_host_quarter(n, qn.data());
         s2k_host_quarter(bw, qb.data());
-        CK(upload(&p->d_weights, w.data(), w.size()));
-        CK(upload(&p->d_sin, s.data(), s.size()));
+        CK(upload(p->stream, &p->d_weights, w.data(), w.size()));
+        CK(upload(p->stream, &p->d_sin, s.data(), s.size()));
         std::vector<double> wv(4 * bw), sv(n);
         s2k_host_reordered(bw, w.data(), s.data(), wv.data(), sv.data());
-        CK(upload(&p->d_wv, wv.data(), wv.size()));
-        CK(upload(&p->d_sv, sv.data(), sv.size()));
-        CK(upload(&p->d_nodes, x.data(), x.size()));
-        CK(upload(&p->d_tw_n, tw.data(), (size_t)n));
-        CK(upload(&p->d_tw_b, tb.data(), (size_t)bw));
-        CK(upload(&p->d_q_n, qn.data(), 4 * (size_t)n));
-        CK(upload(&p->d_q_b, qb.data(), 4 * (size_t)bw));
+        CK(upload(p->stream, &p->d_wv, wv.data(), wv.size()));
+        CK(upload(p->stream, &p->d_sv, sv.data(), sv.size()));
+        CK(upload(p->stream, &p->d_nodes, x.data(), x.size()));
+        CK(upload(p->stream, &p->d_tw_n, tw.data(), (size_t)n));
+        CK(upload(p->stream, &p->d_tw_b, tb.data(), (size_t)bw));
+        CK(upload(p->stream, &p->d_q_n, qn.data(), 4 * (size_t)n));
+        CK(upload(p->stream, &p->d_q_b, qb.data(), 4 * (size_t)bw));
         std::vector<double> seeds((size_t)bw * bw);
         s2k_host_seeds(bw, 0, bw, seeds.data());
-        CK(upload(&p->d_seeds, seeds.data(), seeds.size()));
+        CK(upload(p->stream, &p->d_seeds, seeds.data(), seeds.size()));
     }
     CK(cudaMalloc((void**)&p->d_rec, sizeof(double2) * (size_t)bw * bw));
 
@@ -302,10 +338,10 @@ int s2k_plan_create_impl(s2kit_cuda_plan** out, int bw, int variant, int max_bat
     for (int m = 0; m < bw; ++m)
         if (owned[m]) p->my_orders.push_back(m);
     build_layout(p, owned);
-    CK(upload(&p->d_meta, p->h_meta.data(), p->h_meta.size()));
-    CK(upload(&p->d_rt_start, p->h_rt_start.data(), p->h_rt_start.size()));
-    CK(upload(&p->d_order_start, p->h_order_start.data(), p->h_order_start.size()));
-    CK(upload(&p->d_units, p->h_units.data(), p->h_units.size()));
+    CK(upload(p->stream, &p->d_meta, p->h_meta.data(), p->h_meta.size()));
+    CK(upload(p->stream, &p->d_rt_start, p->h_rt_start.data(), p->h_rt_start.size()));
+    CK(upload(p->stream, &p->d_order_start, p->h_order_start.data(), p->h_order_start.size()));
+    CK(upload(p->stream, &p->d_units, p->h_units.data(), p->h_units.size()));
     CK(s2k::launch_rec_coeffs(p));
 
     // ---- tables
@@ -359,7 +395,6 @@ int s2k_plan_create_impl(s2kit_cuda_plan** out, int bw, int variant, int max_bat
     make_plane_tensor_map(p);
     CK(cudaStreamSynchronize(p->stream));
     apply_table_l2_policy(p);
-    *out = p;
     return 0;
 }
 
@@ -367,28 +402,90 @@ extern "C" int s2kit_cuda_plan_create(s2kit_cuda_plan** out, int bw, int variant
     return s2k_plan_create_impl(out, bw, variant, max_batch, device, 0, 1);
 }
 
+struct HostPipe;
+static void host_pipe_destroy(void* hp);
+
 extern "C" int s2kit_cuda_plan_destroy(s2kit_cuda_plan* p) {
     if (!p) return 0;
+    DeviceGuard guard;
     cudaSetDevice(p->device);
-    cudaStreamSynchronize(p->stream);
+    if (p->stream) cudaStreamSynchronize(p->stream);
     s2k_shard_destroy(p);
-    void* ptrs[] = {p->d_wv, p->d_sv, p->d_weights, p->d_sin,      p->d_tw_n,       p->d_tw_b, p->d_q_n,  p->d_q_b,
-                    p->d_nodes,   p->d_seeds,    p->d_rec,        p->d_table, p->d_meta, p->d_rt_start,
-                    p->d_order_start, p->d_units, p->d_S,          p->d_X,    p->d_coef, p->d_coef2,
-                    p->d_filt,    p->d_stage};
-    for (void* q : ptrs)
+    // tables and constants of a clone belong to the plan it was cloned from
+    void* shared[] = {p->d_wv, p->d_sv, p->d_weights, p->d_sin, p->d_tw_n, p->d_tw_b, p->d_q_n, p->d_q_b, p->d_nodes,
+                      p->d_seeds, p->d_rec, p->d_meta, p->d_rt_start, p->d_order_start, p->d_units};
+    void* own[] = {p->d_S, p->d_X, p->d_coef, p->d_coef2, p->d_filt, p->d_stage};
+    if (!p->shares_tables)
+        for (void* q : shared)
+            if (q) cudaFree(q);
+    for (void* q : own)
         if (q) cudaFree(q);
+    if (p->own_table && p->d_table) cudaFree(p->d_table);
     for (auto& s : p->prof_slots) {
         cudaEventDestroy(s.a);
         cudaEventDestroy(s.b);
     }
+    host_pipe_destroy(p->host_pipe);
     if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
+    delete p->mu;
     delete p;
+    return 0;
+}
+
+// A second plan object for the same bandwidth that SHARES the device tables and constants of `src` (read-only after
+// creation) and owns its stream and workspaces: what concurrent callers need, one clone per thread.  `src` must
+// outlive its clones.
+extern "C" int s2kit_cuda_plan_clone(s2kit_cuda_plan** out, const s2kit_cuda_plan* src, int max_batch) {
+    if (!out) return fail_msg("null output pointer");
+    *out = nullptr;
+    if (!src) return fail_msg("null plan");
+    if (src->shard) return fail_msg("sharded plans cannot be cloned");
+    DeviceGuard guard;
+    CK(cudaSetDevice(src->device));
+    s2kit_cuda_plan* p = new s2kit_cuda_plan(*src);
+    p->mu = new std::mutex();
+    p->shares_tables = true;
+    p->own_table = false;
+    p->stream = nullptr;
+    p->own_stream = true;
+    p->host_pipe = nullptr;
+    p->d_S = p->d_X = p->d_coef = p->d_coef2 = p->d_filt = p->d_stage = nullptr;
+    p->stage_doubles = 0;
+    p->prof_slots.clear();
+    p->prof_used = 0;
+    p->profiling = false;
+    p->tma_S_ok = false;
+    auto build = [&]() -> int {
+        CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+        const int n = p->n, bw = p->bw;
+        if (p->variant == S2KIT_CUDA_FLY) {
+            // the Fly scratch ring is written per call: private
+            p->d_table = nullptr;
+            CK(cudaMalloc((void**)&p->d_table, p->table_bytes));
+            p->own_table = true;
+        }
+        p->chunk = std::max(1, std::min(max_batch, src->chunk));
+        CK(cudaMalloc((void**)&p->d_S, sizeof(double) * (size_t)p->chunk * 2 * n * n));
+        CK(cudaMalloc((void**)&p->d_X, sizeof(double) * (size_t)p->chunk * n * 2 * bw));
+        make_plane_tensor_map(p);
+        apply_table_l2_policy(p);
+        return 0;
+    };
+    if (int rc = build()) {
+        std::string keep = g_last_error;
+        s2kit_cuda_plan_destroy(p);
+        g_last_error = keep;
+        return rc;
+    }
+    *out = p;
     return 0;
 }
 
 extern "C" int s2kit_cuda_plan_set_stream(s2kit_cuda_plan* p, void* stream) {
     if (!p) return fail_msg("null plan");
+    std::lock_guard<std::mutex> lock(*p->mu);
+    DeviceGuard guard;
+    CK(cudaSetDevice(p->device));
     CK(cudaStreamSynchronize(p->stream));
     if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
     p->stream = (cudaStream_t)stream;
@@ -446,15 +543,14 @@ static int fst_device(s2kit_cuda_plan* p, const double* rdata, const double* ida
         const double* id = idata + (long)c0 * data_stride;
         double* rc = rco + (long)c0 * coef_stride;
         double* ic = ico + (long)c0 * coef_stride;
-        const bool fused = s2k::fused_supported(p, nf, fmt);
         // TMA variant of K1 available: keep the planes' latitudes in the DCT's own load order (PlaneView::lat_perm)
         s2k::PlaneView pv = s2k::default_view(p->n);
-        pv.lat_perm = !fused && s2k::tma_planes_ok(p, nf);
+        pv.lat_perm = s2k::tma_planes_ok(p, nf);
         CK(s2k::launch_phi_fft_fwd(p, rd, id, data_stride, p->d_S, nf, fmt, &pv));
         // batched: one persistent kernel does the DCTs and the contraction (kernels_pipe.cu)
-        const bool pipe = !fused && s2k::fwd_pipe_supported(p, nf, fmt);
+        const bool pipe = s2k::fwd_pipe_supported(p, nf, fmt);
         const bool pipe_fused = pipe && s2k::fwd_pipe_fused();
-        if (!fused && !pipe_fused) CK(s2k::launch_dct_fwd(p, p->d_S, p->d_X, nf, 0, nrows, fmt, &pv));
+        if (!pipe_fused) CK(s2k::launch_dct_fwd(p, p->d_S, p->d_X, nf, 0, nrows, fmt, &pv));
         for (const OrderGroup& g : order_groups(p, 0, bw)) {
             if (p->variant == S2KIT_CUDA_FLY) CK(s2k::launch_table_gen(p, p->d_table, g.shift, g.lo, g.hi));
             if (pipe_fused)
@@ -462,8 +558,6 @@ static int fst_device(s2kit_cuda_plan* p, const double* rdata, const double* ida
                                         pv.lat_perm));
             else if (pipe)
                 CK(s2k::launch_leg_fwd_stream(p, p->d_table, g.shift, p->d_X, rc, ic, coef_stride, nf, g.lo, g.hi, fmt));
-            else if (fused)
-                CK(s2k::launch_fused_fwd(p, p->d_table, g.shift, p->d_S, rc, ic, coef_stride, nf, g.lo, g.hi, fmt));
             else
                 CK(s2k::launch_legendre_fwd(p, p->d_table, g.shift, p->d_X, rc, ic, coef_stride, nf, g.lo, g.hi, fmt));
         }
@@ -481,18 +575,14 @@ static int inv_fst_device(s2kit_cuda_plan* p, const double* rco, const double* i
         const double* ic = ico + (long)c0 * coef_stride;
         double* rd = rdata + (long)c0 * data_stride;
         double* id = idata + (long)c0 * data_stride;
-        const bool fused = s2k::fused_supported(p, nf, fmt);
         s2k::PlaneView pv = s2k::default_view(p->n);
-        pv.lat_perm = !fused && s2k::tma_planes_ok(p, nf);
+        pv.lat_perm = s2k::tma_planes_ok(p, nf);
         for (const OrderGroup& g : order_groups(p, 0, bw)) {
             const double* tt = p->variant == S2KIT_CUDA_FLY ? p->d_table : p->d_table_t;
             if (p->variant == S2KIT_CUDA_FLY) CK(s2k::launch_table_gen(p, p->d_table, g.shift, g.lo, g.hi, 1));
-            if (fused)
-                CK(s2k::launch_fused_inv(p, tt, g.shift, rc, ic, coef_stride, p->d_S, nf, g.lo, g.hi, fmt));
-            else
-                CK(s2k::launch_legendre_inv(p, tt, g.shift, rc, ic, coef_stride, p->d_X, nf, g.lo, g.hi, fmt));
+            CK(s2k::launch_legendre_inv(p, tt, g.shift, rc, ic, coef_stride, p->d_X, nf, g.lo, g.hi, fmt));
         }
-        if (!fused) CK(s2k::launch_dct_inv(p, p->d_X, p->d_S, nf, 0, nrows, fmt, &pv));
+        CK(s2k::launch_dct_inv(p, p->d_X, p->d_S, nf, 0, nrows, fmt, &pv));
         CK(s2k::launch_phi_fft_inv(p, p->d_S, rd, id, data_stride, nf, fmt, &pv));
     }
     return 0;
@@ -573,10 +663,18 @@ static int check_common(s2kit_cuda_plan* p, int batch, int fmt) {
     return 0;
 }
 
+// Every public entry point runs under the plan's lock with the plan's device current, and puts the caller's device
+// back on return.
+#define S2K_ENTER(p, batch, fmt)                       \
+    if (!(p)) return fail_msg("null plan");            \
+    DeviceGuard guard__;                               \
+    std::lock_guard<std::mutex> lock__(*(p)->mu);      \
+    if (int r__ = check_common((p), (batch), (fmt))) return r__
+
 // Host-pointer calls: a three-stage pipeline over sub-chunks of the batch -- H2D of sub-chunk i+1, the kernels of
 // sub-chunk i and D2H of sub-chunk i-1 run concurrently on three streams with double-buffered device staging, so
 // PCIe runs full duplex and the GPU work hides behind the copies.  (Pinned host memory is needed for true overlap;
-// pageable memory still works, the copies just serialise.)
+// pageable memory still works, the copies just serialise.)  The copy streams and events live as long as the plan.
 struct HostPipe {
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t in_done[2] = {nullptr, nullptr}, comp_done[2] = {nullptr, nullptr}, out_done[2] = {nullptr, nullptr};
@@ -599,14 +697,26 @@ struct HostPipe {
         if (s_out) cudaStreamDestroy(s_out);
     }
 };
+static void host_pipe_destroy(void* hp) { delete reinterpret_cast<HostPipe*>(hp); }
 
-// in0/in1: host inputs (in_len doubles per function, stride in_stride); out0/out1 likewise.
-// compute(nf, din0, din1, dout0, dout1) enqueues the kernels for nf functions on p->stream (device strides = lens).
+// one strided host array of a batched call: `len` doubles per function, functions `stride` doubles apart
+// (stride 0 = one array shared by the whole batch: copied once per sub-chunk slot)
+struct HostSpan {
+    const double* in = nullptr;
+    double* out = nullptr;
+    long stride = 0, len = 0;
+};
+
+// ins / outs: the host arrays of the call.  compute(nf, din[], dout[]) enqueues the kernels for nf functions on
+// p->stream; device arrays are dense (function f at f * len).
 template <typename F>
-static int host_pipeline(s2kit_cuda_plan* p, int batch, const double* in0, const double* in1, long in_stride,
-                         long in_len, double* out0, double* out1, long out_stride, long out_len, F compute) {
+static int host_pipeline(s2kit_cuda_plan* p, int batch, const HostSpan* ins, int nin, const HostSpan* outs, int nout,
+                         F compute) {
     const int sub = std::max(1, std::min(p->chunk, 32));
-    const size_t need = (size_t)2 * sub * 2 * (size_t)(in_len + out_len);
+    size_t per_slot = 0;
+    for (int i = 0; i < nin; ++i) per_slot += (size_t)(ins[i].stride ? sub : 1) * ins[i].len;
+    for (int i = 0; i < nout; ++i) per_slot += (size_t)sub * outs[i].len;
+    const size_t need = 2 * per_slot;
     if (p->stage_doubles < need) {
         if (p->d_stage) cudaFree(p->d_stage);
         p->d_stage = nullptr;
@@ -614,17 +724,22 @@ static int host_pipeline(s2kit_cuda_plan* p, int batch, const double* in0, const
         CK(cudaMalloc((void**)&p->d_stage, need * sizeof(double)));
         p->stage_doubles = need;
     }
-    HostPipe hp;
+    if (!p->host_pipe) p->host_pipe = new HostPipe();
+    HostPipe& hp = *reinterpret_cast<HostPipe*>(p->host_pipe);
     if (!hp.ok) return fail_msg("could not create the copy streams");
-    double* din[2][2];
-    double* dout[2][2];
+    double* din[2][4];
+    double* dout[2][4];
     {
         double* q = p->d_stage;
         for (int b = 0; b < 2; ++b) {
-            din[b][0] = q; q += (size_t)sub * in_len;
-            din[b][1] = q; q += (size_t)sub * in_len;
-            dout[b][0] = q; q += (size_t)sub * out_len;
-            dout[b][1] = q; q += (size_t)sub * out_len;
+            for (int i = 0; i < nin; ++i) {
+                din[b][i] = q;
+                q += (size_t)(ins[i].stride ? sub : 1) * ins[i].len;
+            }
+            for (int i = 0; i < nout; ++i) {
+                dout[b][i] = q;
+                q += (size_t)sub * outs[i].len;
+            }
         }
     }
     int i = 0;
@@ -632,18 +747,24 @@ static int host_pipeline(s2kit_cuda_plan* p, int batch, const double* in0, const
         const int b = i & 1, nf = std::min(sub, batch - c0);
         // H2D: the input buffers of slot b are free once the kernels of sub-chunk i-2 are done
         if (i >= 2) CK(cudaStreamWaitEvent(hp.s_in, hp.comp_done[b], 0));
-        CK(copy_in(din[b][0], in_len, in0 + (long)c0 * in_stride, in_stride, in_len, nf, hp.s_in));
-        CK(copy_in(din[b][1], in_len, in1 + (long)c0 * in_stride, in_stride, in_len, nf, hp.s_in));
+        for (int k = 0; k < nin; ++k) {
+            if (ins[k].stride)
+                CK(copy_in(din[b][k], ins[k].len, ins[k].in + (long)c0 * ins[k].stride, ins[k].stride, ins[k].len, nf,
+                           hp.s_in));
+            else if (i < 2)  // shared array: once per slot
+                CK(copy_in(din[b][k], ins[k].len, ins[k].in, ins[k].len, ins[k].len, 1, hp.s_in));
+        }
         CK(cudaEventRecord(hp.in_done[b], hp.s_in));
         // kernels: need the inputs, and the output buffers of slot b drained (sub-chunk i-2)
         CK(cudaStreamWaitEvent(p->stream, hp.in_done[b], 0));
         if (i >= 2) CK(cudaStreamWaitEvent(p->stream, hp.out_done[b], 0));
-        if (int rc = compute(nf, din[b][0], din[b][1], dout[b][0], dout[b][1])) return rc;
+        if (int rc = compute(nf, din[b], dout[b])) return rc;
         CK(cudaEventRecord(hp.comp_done[b], p->stream));
         // D2H
         CK(cudaStreamWaitEvent(hp.s_out, hp.comp_done[b], 0));
-        CK(copy_out(out0 + (long)c0 * out_stride, out_stride, dout[b][0], out_len, out_len, nf, hp.s_out));
-        CK(copy_out(out1 + (long)c0 * out_stride, out_stride, dout[b][1], out_len, out_len, nf, hp.s_out));
+        for (int k = 0; k < nout; ++k)
+            CK(copy_out(outs[k].out + (long)c0 * outs[k].stride, outs[k].stride, dout[b][k], outs[k].len, outs[k].len,
+                        nf, hp.s_out));
         CK(cudaEventRecord(hp.out_done[b], hp.s_out));
     }
     CK(cudaStreamSynchronize(hp.s_out));
@@ -651,86 +772,84 @@ static int host_pipeline(s2kit_cuda_plan* p, int batch, const double* in0, const
     return 0;
 }
 
+static HostSpan span_in(const double* ptr, long stride, long len) {
+    HostSpan s;
+    s.in = ptr;
+    s.stride = stride;
+    s.len = len;
+    return s;
+}
+static HostSpan span_out(double* ptr, long stride, long len) {
+    HostSpan s;
+    s.out = ptr;
+    s.stride = stride;
+    s.len = len;
+    return s;
+}
+
 extern "C" int s2kit_cuda_fst(s2kit_cuda_plan* p, const double* rdata, const double* idata, double* rco, double* ico,
                               int batch, long data_stride, long coef_stride, int fmt, int where) {
-    if (int r = check_common(p, batch, fmt)) return r;
+    S2K_ENTER(p, batch, fmt);
     if (batch == 0) return 0;
     if (where == S2KIT_CUDA_DEVICE) return fst_device(p, rdata, idata, rco, ico, batch, data_stride, coef_stride, fmt);
     const long gs = (long)p->n * p->n, cs = (long)p->bw * p->bw;
-    return host_pipeline(p, batch, rdata, idata, data_stride, gs, rco, ico, coef_stride, cs,
-                         [&](int nf, double* gr, double* gi, double* cr, double* ci) {
-                             return fst_device(p, gr, gi, cr, ci, nf, gs, cs, fmt);
-                         });
+    HostSpan ins[2] = {span_in(rdata, data_stride, gs), span_in(idata, data_stride, gs)};
+    HostSpan outs[2] = {span_out(rco, coef_stride, cs), span_out(ico, coef_stride, cs)};
+    return host_pipeline(p, batch, ins, 2, outs, 2, [&](int nf, double** di, double** dout) {
+        return fst_device(p, di[0], di[1], dout[0], dout[1], nf, gs, cs, fmt);
+    });
 }
 
 extern "C" int s2kit_cuda_inv_fst(s2kit_cuda_plan* p, const double* rco, const double* ico, double* rdata,
                                   double* idata, int batch, long coef_stride, long data_stride, int fmt, int where) {
-    if (int r = check_common(p, batch, fmt)) return r;
+    S2K_ENTER(p, batch, fmt);
     if (batch == 0) return 0;
     if (where == S2KIT_CUDA_DEVICE)
         return inv_fst_device(p, rco, ico, rdata, idata, batch, coef_stride, data_stride, fmt);
     const long gs = (long)p->n * p->n, cs = (long)p->bw * p->bw;
-    return host_pipeline(p, batch, rco, ico, coef_stride, cs, rdata, idata, data_stride, gs,
-                         [&](int nf, double* cr, double* ci, double* gr, double* gi) {
-                             return inv_fst_device(p, cr, ci, gr, gi, nf, cs, gs, fmt);
-                         });
+    HostSpan ins[2] = {span_in(rco, coef_stride, cs), span_in(ico, coef_stride, cs)};
+    HostSpan outs[2] = {span_out(rdata, data_stride, gs), span_out(idata, data_stride, gs)};
+    return host_pipeline(p, batch, ins, 2, outs, 2, [&](int nf, double** di, double** dout) {
+        return inv_fst_device(p, di[0], di[1], dout[0], dout[1], nf, cs, gs, fmt);
+    });
 }
 
 extern "C" int s2kit_cuda_fzt(s2kit_cuda_plan* p, const double* rdata, const double* idata, double* rres, double* ires,
                               int batch, long data_stride, long res_stride, int fmt, int where) {
-    if (int r = check_common(p, batch, fmt)) return r;
+    S2K_ENTER(p, batch, fmt);
     if (batch == 0) return 0;
     if (where == S2KIT_CUDA_DEVICE) return fzt_device(p, rdata, idata, rres, ires, batch, data_stride, res_stride, fmt);
     const long gs = (long)p->n * p->n;
     const int bw = p->bw;
-    return host_pipeline(p, batch, rdata, idata, data_stride, gs, rres, ires, res_stride, (long)bw,
-                         [&](int nf, double* gr, double* gi, double* hr, double* hi) {
-                             return fzt_device(p, gr, gi, hr, hi, nf, gs, bw, fmt);
-                         });
+    HostSpan ins[2] = {span_in(rdata, data_stride, gs), span_in(idata, data_stride, gs)};
+    HostSpan outs[2] = {span_out(rres, res_stride, bw), span_out(ires, res_stride, bw)};
+    return host_pipeline(p, batch, ins, 2, outs, 2, [&](int nf, double** di, double** dout) {
+        return fzt_device(p, di[0], di[1], dout[0], dout[1], nf, gs, bw, fmt);
+    });
 }
 
 extern "C" int s2kit_cuda_conv(s2kit_cuda_plan* p, const double* rdata, const double* idata, const double* rfilter,
                                const double* ifilter, double* rres, double* ires, int batch, long data_stride,
                                long filter_stride, int where) {
-    if (int r = check_common(p, batch, S2KIT_REAL)) return r;
+    S2K_ENTER(p, batch, S2KIT_REAL);
     if (batch == 0) return 0;
     if (where == S2KIT_CUDA_DEVICE)
         return conv_device(p, rdata, idata, rfilter, ifilter, rres, ires, batch, data_stride, filter_stride);
-    // host pointers: stage signal and filter grids, run on the device, copy the result grids back
+    // host pointers: signal and filter grids stream in, result grids stream out, through the same three-stage
+    // pipeline and the plan's persistent staging as the transforms (no allocation per call)
     const long gs = (long)p->n * p->n;
-    double* d = nullptr;
-    CK(cudaMalloc((void**)&d, sizeof(double) * 6 * (size_t)gs));
-    double *sr = d, *si = d + gs, *fr = d + 2 * gs, *fi = d + 3 * gs, *orr = d + 4 * gs, *oi = d + 5 * gs;
-    int rc = 0;
-    for (int f = 0; f < batch && !rc; ++f) {
-        cudaError_t e = cudaMemcpyAsync(sr, rdata + (long)f * data_stride, gs * 8, cudaMemcpyHostToDevice, p->stream);
-        if (e == cudaSuccess)
-            e = cudaMemcpyAsync(si, idata + (long)f * data_stride, gs * 8, cudaMemcpyHostToDevice, p->stream);
-        if (e == cudaSuccess && (f == 0 || filter_stride != 0)) {
-            e = cudaMemcpyAsync(fr, rfilter + (long)f * filter_stride, gs * 8, cudaMemcpyHostToDevice, p->stream);
-            if (e == cudaSuccess)
-                e = cudaMemcpyAsync(fi, ifilter + (long)f * filter_stride, gs * 8, cudaMemcpyHostToDevice, p->stream);
-        }
-        if (e != cudaSuccess) {
-            rc = fail("conv H2D", e);
-            break;
-        }
-        rc = conv_device(p, sr, si, fr, fi, orr, oi, 1, gs, gs);
-        if (rc) break;
-        e = cudaMemcpyAsync(rres + (long)f * data_stride, orr, gs * 8, cudaMemcpyDeviceToHost, p->stream);
-        if (e == cudaSuccess)
-            e = cudaMemcpyAsync(ires + (long)f * data_stride, oi, gs * 8, cudaMemcpyDeviceToHost, p->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
-        if (e != cudaSuccess) rc = fail("conv D2H", e);
-    }
-    cudaFree(d);
-    return rc;
+    HostSpan ins[4] = {span_in(rdata, data_stride, gs), span_in(idata, data_stride, gs),
+                       span_in(rfilter, filter_stride, gs), span_in(ifilter, filter_stride, gs)};
+    HostSpan outs[2] = {span_out(rres, data_stride, gs), span_out(ires, data_stride, gs)};
+    return host_pipeline(p, batch, ins, 4, outs, 2, [&](int nf, double** di, double** dout) {
+        return conv_device(p, di[0], di[1], di[2], di[3], dout[0], dout[1], nf, gs, filter_stride ? gs : 0);
+    });
 }
 
 extern "C" int s2kit_cuda_trans_mult(s2kit_cuda_plan* p, const double* rd, const double* id, const double* rf,
                                      const double* ifl, double* rres, double* ires, int batch, long coef_stride,
                                      int where) {
-    if (int r = check_common(p, batch, S2KIT_COMPLEX)) return r;
+    S2K_ENTER(p, batch, S2KIT_COMPLEX);
     if (batch == 0) return 0;
     const int bw = p->bw;
     const long cs = (long)bw * bw;
@@ -763,7 +882,7 @@ extern "C" int s2kit_cuda_trans_mult(s2kit_cuda_plan* p, const double* rd, const
 // DLTSemi / InvDLTSemi on ncols independent real columns of one order: columns are fed through the batched
 // kernels as the real parts of ncols "functions" whose imaginary parts are zero.
 extern "C" int s2kit_cuda_dlt_semi(s2kit_cuda_plan* p, const double* data, int m, double* result, int ncols, int where) {
-    if (int r = check_common(p, ncols, S2KIT_COMPLEX)) return r;
+    S2K_ENTER(p, ncols, S2KIT_COMPLEX);
     if (m < 0 || m >= p->bw) return fail_msg("order out of range");
     if (ncols == 0) return 0;
     const int bw = p->bw, n = p->n;
@@ -799,7 +918,7 @@ extern "C" int s2kit_cuda_dlt_semi(s2kit_cuda_plan* p, const double* data, int m
 
 extern "C" int s2kit_cuda_inv_dlt_semi(s2kit_cuda_plan* p, const double* coeffs, int m, double* result, int ncols,
                                        int where) {
-    if (int r = check_common(p, ncols, S2KIT_COMPLEX)) return r;
+    S2K_ENTER(p, ncols, S2KIT_COMPLEX);
     if (m < 0 || m >= p->bw) return fail_msg("order out of range");
     if (ncols == 0) return 0;
     const int bw = p->bw, n = p->n;
@@ -901,16 +1020,22 @@ static int table_to_host(s2kit_cuda_plan* p, const double* table, uint64_t shift
     return 0;
 }
 
+static int table_generate_locked(s2kit_cuda_plan* p, int m, double* host_out);
+
 extern "C" int s2kit_cuda_table_export(s2kit_cuda_plan* p, int m, double* host_out) {
-    if (int r = check_common(p, 0, S2KIT_COMPLEX)) return r;
+    S2K_ENTER(p, 0, S2KIT_COMPLEX);
     if (m < 0 || m >= p->bw) return fail_msg("order out of range");
-    if (p->variant != S2KIT_CUDA_MEMO) return s2kit_cuda_table_generate(p, m, host_out);
+    if (p->variant != S2KIT_CUDA_MEMO) return table_generate_locked(p, m, host_out);
     if (p->h_order_start[m + 1] == p->h_order_start[m]) return fail_msg("order not resident on this rank");
     return table_to_host(p, p->d_table, 0, m, host_out);
 }
 
 extern "C" int s2kit_cuda_table_generate(s2kit_cuda_plan* p, int m, double* host_out) {
-    if (int r = check_common(p, 0, S2KIT_COMPLEX)) return r;
+    S2K_ENTER(p, 0, S2KIT_COMPLEX);
+    return table_generate_locked(p, m, host_out);
+}
+
+static int table_generate_locked(s2kit_cuda_plan* p, int m, double* host_out) {
     if (m < 0 || m >= p->bw) return fail_msg("order out of range");
     uint64_t tiles = 0;
     {

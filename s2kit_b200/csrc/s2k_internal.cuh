@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <vector>
 
 #include "../../include/s2kit_cuda.h"
@@ -17,6 +18,8 @@ namespace s2k {
 // DMMA fragment order: element (row i, col j) sits at 2*(4*i + (j&3)) + (j>>2), so that lane L of a warp
 // reads with ONE 128-bit load the two A-fragment values (row L/4, cols L%4 and L%4+4) of the two
 // mma.m8n8k4 k-steps covering the tile.  Entries outside the trapezoid are zero.
+constexpr int S2K_MAX_PEERS = 8;
+
 struct BlockMeta {
     int rt_base;  // index of this block's first row tile in rt_start[]
     int rows;     // R_p
@@ -46,7 +49,16 @@ struct PlaneView {
     // K2 loads / K5 stores contiguous runs.  Only the TMA variants of K1 / K6 write / read it (a tile of 8 positions is
     // 8 even or 8 odd grid rows); it is private to one fst / inv_fst call.
     int lat_perm = 0;
+    // K2/K5 on a single field split over the GPUs of one process (multi.cu): segment s of a row lives in the memory of
+    // peer s (peer-mapped pointers, NVLink loads / stores straight from the DCT kernels); null -> seg_stride addressing
+    const double* segptr[S2K_MAX_PEERS] = {nullptr};
+    int use_segptr = 0;
 };
+
+// address (doubles from the plane base of the local row) of latitude j in a row cut into segments
+__host__ __device__ inline long seg_offset(const PlaneView& pv, int j) {
+    return (long)(j >> pv.seg_shift) * pv.seg_stride + (j & pv.seg_mask);
+}
 
 struct ProfileSlot {
     cudaEvent_t a, b;
@@ -58,10 +70,17 @@ struct ProfileSlot {
 struct s2kit_cuda_plan {
     int bw = 0, n = 0, variant = 0, device = 0, chunk = 1;
     bool fast = false;  // power-of-two bandwidth >= 16: radix FFT kernels; otherwise direct O(n^2) kernels
-    bool fuse = false;  // fused DCT+Legendre kernels for batched calls (S2KIT_CUDA_FUSE=1 enables)
     bool l2_persist = false;  // persisting-L2 window on Memo tables that fit (S2KIT_CUDA_L2PERSIST=1 enables)
     cudaStream_t stream = nullptr;
     bool own_stream = true;
+    int sm_count = 148;         // multiProcessorCount of `device` (persistent-grid sizes)
+    // One transform at a time per plan object: every public entry point holds this lock for the whole call (the
+    // workspaces and the stream are per plan).  Callers that want concurrency use one clone per thread
+    // (s2kit_cuda_plan_clone: shared tables, private workspaces), which is what the drop-in layer does.
+    std::mutex* mu = nullptr;
+    bool shares_tables = false;  // a clone: tables / constants belong to the plan it was cloned from
+    bool own_table = true;       // d_table is this object's allocation (false for Memo clones)
+    void* host_pipe = nullptr;   // HostPipe (plan.cu): copy streams + events of the host-pointer pipeline, created once
 
     // sharding (single-field multi-GPU); nranks == 1 for ordinary plans
     int rank = 0, nranks = 1;
@@ -172,14 +191,6 @@ cudaError_t launch_naive_dlt(const double* data, const double* weights, const do
 cudaError_t launch_naive_inv_dlt(const double* coeffs, const double* pml, double* result, int size, int rows,
                                  cudaStream_t st);
 int table_unit_rows(int bw);
-// fused K2+K3 / K4+K5 (kernels_fused.cu)
-bool fused_supported(const s2kit_cuda_plan* p, int nfun, int data_format);
-cudaError_t launch_fused_fwd(s2kit_cuda_plan* p, const double* table, uint64_t table_shift, const double* S,
-                             double* rco, double* ico, long coef_stride, int nfun, int m_lo, int m_hi, int data_format);
-cudaError_t launch_fused_inv(s2kit_cuda_plan* p, const double* table, uint64_t table_shift, const double* rco,
-                             const double* ico, long coef_stride, double* G, int nfun, int m_lo, int m_hi,
-                             int data_format);
-
 // persistent warp-specialised K2+K3 for batched launches (kernels_pipe.cu)
 bool fwd_pipe_supported(const s2kit_cuda_plan* p, int nfun, int data_format);
 cudaError_t launch_fwd_pipe(s2kit_cuda_plan* p, const double* table, uint64_t table_shift, const double* S, double* rco,

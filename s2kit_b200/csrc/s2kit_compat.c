@@ -29,56 +29,147 @@
 #include "host_setup.h"
 
 /* ------------------------------------------------------------------------------------ plan cache */
-#define MAX_CACHED 16
-static struct {
+/* The reference's functions are re-entrant when every thread brings its own workspace (that is how a threaded caller
+   drives them, e.g. oracle/ref_harness.c:225-262).  Here a cache entry per (bandwidth, variant) holds ONE set of device
+   tables and up to MAX_CTX contexts -- the plan that owns the tables plus clones that share them
+   (s2kit_cuda_plan_clone), each with its own stream and workspaces.  A call checks a free context out, runs, and
+   checks it back in; concurrent callers therefore never share a workspace, and an entry is only evicted when nobody
+   is inside it. */
+#define MAX_CACHED 8
+#define MAX_CTX 8
+typedef struct {
     int bw, variant;
-    s2kit_cuda_plan* plan;
-} g_cache[MAX_CACHED];
-static int g_ncached = 0;
+    s2kit_cuda_plan* ctx[MAX_CTX]; /* ctx[0] owns the tables */
+    int busy[MAX_CTX];
+    int nctx, users;
+    unsigned long stamp;
+} CacheEntry;
+static CacheEntry g_cache[MAX_CACHED]; /* nctx == 0: free slot */
+static unsigned long g_clock = 0;
 static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+static pthread_cond_t g_cv = PTHREAD_COND_INITIALIZER;
 
 static void die(const char* where) {
     fprintf(stderr, "s2kit_cuda: %s failed: %s\n", where, s2kit_cuda_last_error());
     abort();
 }
 
-static int env_device(void) {
-    const char* s = getenv("S2KIT_CUDA_DEVICE");
-    return s ? atoi(s) : 0;
+static int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return s ? atoi(s) : dflt;
 }
 
-static s2kit_cuda_plan* plan_for(int bw, int variant) {
+static void entry_destroy(CacheEntry* e) {
+    for (int i = e->nctx - 1; i >= 0; --i) s2kit_cuda_plan_destroy(e->ctx[i]); /* clones first, the owner last */
+    e->nctx = 0;
+}
+
+typedef struct {
+    CacheEntry* entry;
+    int slot;
+    s2kit_cuda_plan* plan;
+} Checkout;
+
+static Checkout ctx_acquire(int bw, int variant) {
+    Checkout c = {NULL, 0, NULL};
+    int max_ctx = env_int("S2KIT_CUDA_CONTEXTS", 4);
+    if (max_ctx < 1) max_ctx = 1;
+    if (max_ctx > MAX_CTX) max_ctx = MAX_CTX;
     pthread_mutex_lock(&g_lock);
-    for (int i = 0; i < g_ncached; ++i)
-        if (g_cache[i].bw == bw && g_cache[i].variant == variant) {
-            s2kit_cuda_plan* p = g_cache[i].plan;
-            pthread_mutex_unlock(&g_lock);
-            return p;
+    for (;;) {
+        CacheEntry* e = NULL;
+        for (int i = 0; i < MAX_CACHED; ++i) /* entries never move: checked-out callers hold pointers to them */
+            if (g_cache[i].nctx && g_cache[i].bw == bw && g_cache[i].variant == variant) e = &g_cache[i];
+        if (!e) {
+            int at = -1;
+            for (int i = 0; i < MAX_CACHED && at < 0; ++i)
+                if (!g_cache[i].nctx) at = i;
+            if (at < 0) {
+                for (int i = 0; i < MAX_CACHED; ++i)
+                    if (g_cache[i].users == 0 && (at < 0 || g_cache[i].stamp < g_cache[at].stamp)) at = i;
+                if (at < 0) { /* every cached plan is in use: wait for one to come back */
+                    pthread_cond_wait(&g_cv, &g_lock);
+                    continue;
+                }
+                entry_destroy(&g_cache[at]);
+            }
+            e = &g_cache[at];
+            memset(e, 0, sizeof(*e));
+            e->bw = bw;
+            e->variant = variant;
+            if (s2kit_cuda_plan_create(&e->ctx[0], bw, variant, 1, env_int("S2KIT_CUDA_DEVICE", 0))) {
+                pthread_mutex_unlock(&g_lock);
+                die("plan_create");
+            }
+            e->nctx = 1;
         }
-    if (g_ncached == MAX_CACHED) {
-        s2kit_cuda_plan_destroy(g_cache[0].plan);
-        memmove(&g_cache[0], &g_cache[1], sizeof(g_cache[0]) * (MAX_CACHED - 1));
-        --g_ncached;
+        int slot = -1;
+        for (int i = 0; i < e->nctx; ++i)
+            if (!e->busy[i]) {
+                slot = i;
+                break;
+            }
+        if (slot < 0 && e->nctx < max_ctx) {
+            if (s2kit_cuda_plan_clone(&e->ctx[e->nctx], e->ctx[0], 1)) {
+                pthread_mutex_unlock(&g_lock);
+                die("plan_clone");
+            }
+            slot = e->nctx++;
+        }
+        if (slot < 0) {
+            pthread_cond_wait(&g_cv, &g_lock);
+            continue;
+        }
+        e->busy[slot] = 1;
+        e->users++;
+        e->stamp = ++g_clock;
+        c.entry = e;
+        c.slot = slot;
+        c.plan = e->ctx[slot];
+        break;
     }
-    s2kit_cuda_plan* p = NULL;
-    if (s2kit_cuda_plan_create(&p, bw, variant, 1, env_device())) {
-        pthread_mutex_unlock(&g_lock);
-        die("plan_create");
-    }
-    g_cache[g_ncached].bw = bw;
-    g_cache[g_ncached].variant = variant;
-    g_cache[g_ncached].plan = p;
-    ++g_ncached;
     pthread_mutex_unlock(&g_lock);
-    return p;
+    return c;
 }
 
-/* drops every cached plan (frees device memory); not part of the reference API */
+static void ctx_release(Checkout c) {
+    pthread_mutex_lock(&g_lock);
+    c.entry->busy[c.slot] = 0;
+    c.entry->users--;
+    pthread_cond_broadcast(&g_cv);
+    pthread_mutex_unlock(&g_lock);
+}
+
+/* ---- single large field on several GPUs: S2KIT_CUDA_NGPU > 1 routes COMPLEX-format FSTSemiMemo / InvFSTSemiMemo calls
+   at bw >= S2KIT_CUDA_MULTI_MIN_BW (default 512) through s2kit_cuda_multi_* (multi.cu) */
+static s2kit_cuda_multi* g_multi = NULL;
+static int g_multi_bw = 0;
+static pthread_mutex_t g_multi_lock = PTHREAD_MUTEX_INITIALIZER;
+
+static s2kit_cuda_multi* multi_for(int bw, int fmt) {
+    int ngpu = env_int("S2KIT_CUDA_NGPU", 1);
+    if (ngpu <= 1 || fmt != S2KIT_COMPLEX || bw < env_int("S2KIT_CUDA_MULTI_MIN_BW", 512)) return NULL;
+    if (s2kit_cuda_shard_layout(bw, ngpu, 0, NULL, NULL) < 0) return NULL;
+    if (g_multi && g_multi_bw != bw) {
+        s2kit_cuda_multi_destroy(g_multi);
+        g_multi = NULL;
+    }
+    if (!g_multi) {
+        if (s2kit_cuda_multi_create(&g_multi, bw, ngpu, NULL)) die("multi_create");
+        g_multi_bw = bw;
+    }
+    return g_multi;
+}
+
+/* drops every cached plan (frees device memory); not part of the reference API.  Must not race with transforms. */
 void s2kit_compat_release(void) {
     pthread_mutex_lock(&g_lock);
-    for (int i = 0; i < g_ncached; ++i) s2kit_cuda_plan_destroy(g_cache[i].plan);
-    g_ncached = 0;
+    for (int i = 0; i < MAX_CACHED; ++i) entry_destroy(&g_cache[i]);
     pthread_mutex_unlock(&g_lock);
+    pthread_mutex_lock(&g_multi_lock);
+    if (g_multi) s2kit_cuda_multi_destroy(g_multi);
+    g_multi = NULL;
+    pthread_mutex_unlock(&g_multi_lock);
 }
 
 /* ------------------------------------------------------------------------------------ layout arithmetic */
@@ -176,7 +267,10 @@ void Pmm_L2(const int m, double* eval_points, const int n, double* result) {
 /* cospml.c:161-242: generated on the device, exported in the reference's packed layout */
 void GenerateCosPmlTable(const int bw, const int m, double* tablespace, double* workspace) {
     (void)workspace;
-    if (s2kit_cuda_table_export(plan_for(bw, S2KIT_CUDA_MEMO), m, tablespace)) die("GenerateCosPmlTable");
+    Checkout c = ctx_acquire(bw, S2KIT_CUDA_MEMO);
+    int rc = s2kit_cuda_table_export(c.plan, m, tablespace);
+    ctx_release(c);
+    if (rc) die("GenerateCosPmlTable");
 }
 
 /* cospml.c:301-362: gather each cosine index's column of the packed table (ascending degree) */
@@ -291,28 +385,57 @@ double** Transpose_SemiNaive_Naive_Pml_Table(double** seminaive_naive_pml_table,
 /* ------------------------------------------------------------------------------------ transforms */
 
 static void run_fst(int variant, double* rdata, double* idata, double* rcoeffs, double* icoeffs, int bw, int fmt) {
-    s2kit_cuda_plan* p = plan_for(bw, variant);
     long gs = 4L * bw * bw, cs = (long)bw * bw;
-    if (s2kit_cuda_fst(p, rdata, idata, rcoeffs, icoeffs, 1, gs, cs, fmt, S2KIT_CUDA_HOST)) die("FSTSemi");
+    if (variant == S2KIT_CUDA_MEMO) {
+        pthread_mutex_lock(&g_multi_lock);
+        s2kit_cuda_multi* mp = multi_for(bw, fmt);
+        if (mp) {
+            int rc = s2kit_cuda_multi_fst(mp, rdata, idata, rcoeffs, icoeffs);
+            pthread_mutex_unlock(&g_multi_lock);
+            if (rc) die("FSTSemiMemo (multi-GPU)");
+            return;
+        }
+        pthread_mutex_unlock(&g_multi_lock);
+    }
+    Checkout c = ctx_acquire(bw, variant);
+    int rc = s2kit_cuda_fst(c.plan, rdata, idata, rcoeffs, icoeffs, 1, gs, cs, fmt, S2KIT_CUDA_HOST);
+    ctx_release(c);
+    if (rc) die("FSTSemi");
 }
 
 static void run_inv(int variant, double* rcoeffs, double* icoeffs, double* rdata, double* idata, int bw, int fmt) {
-    s2kit_cuda_plan* p = plan_for(bw, variant);
     long gs = 4L * bw * bw, cs = (long)bw * bw;
-    if (s2kit_cuda_inv_fst(p, rcoeffs, icoeffs, rdata, idata, 1, cs, gs, fmt, S2KIT_CUDA_HOST)) die("InvFSTSemi");
+    if (variant == S2KIT_CUDA_MEMO) {
+        pthread_mutex_lock(&g_multi_lock);
+        s2kit_cuda_multi* mp = multi_for(bw, fmt);
+        if (mp) {
+            int rc = s2kit_cuda_multi_inv_fst(mp, rcoeffs, icoeffs, rdata, idata);
+            pthread_mutex_unlock(&g_multi_lock);
+            if (rc) die("InvFSTSemiMemo (multi-GPU)");
+            return;
+        }
+        pthread_mutex_unlock(&g_multi_lock);
+    }
+    Checkout c = ctx_acquire(bw, variant);
+    int rc = s2kit_cuda_inv_fst(c.plan, rcoeffs, icoeffs, rdata, idata, 1, cs, gs, fmt, S2KIT_CUDA_HOST);
+    ctx_release(c);
+    if (rc) die("InvFSTSemi");
 }
 
 static void run_fzt(int variant, double* rdata, double* idata, double* rres, double* ires, int bw, int fmt) {
-    s2kit_cuda_plan* p = plan_for(bw, variant);
-    if (s2kit_cuda_fzt(p, rdata, idata, rres, ires, 1, 4L * bw * bw, bw, fmt, S2KIT_CUDA_HOST)) die("FZTSemi");
+    Checkout c = ctx_acquire(bw, variant);
+    int rc = s2kit_cuda_fzt(c.plan, rdata, idata, rres, ires, 1, 4L * bw * bw, bw, fmt, S2KIT_CUDA_HOST);
+    ctx_release(c);
+    if (rc) die("FZTSemi");
 }
 
 static void run_conv(int variant, double* rdata, double* idata, double* rfilter, double* ifilter, double* rres,
                      double* ires, int bw) {
-    s2kit_cuda_plan* p = plan_for(bw, variant);
+    Checkout c = ctx_acquire(bw, variant);
     long gs = 4L * bw * bw;
-    if (s2kit_cuda_conv(p, rdata, idata, rfilter, ifilter, rres, ires, 1, gs, gs, S2KIT_CUDA_HOST))
-        die("ConvOn2SphereSemi");
+    int rc = s2kit_cuda_conv(c.plan, rdata, idata, rfilter, ifilter, rres, ires, 1, gs, gs, S2KIT_CUDA_HOST);
+    ctx_release(c);
+    if (rc) die("ConvOn2SphereSemi");
 }
 
 void FSTSemiMemo(double* rdata, double* idata, double* rcoeffs, double* icoeffs, const int bw,
@@ -370,14 +493,19 @@ void ConvOn2SphereSemiFly(double* rdata, double* idata, double* rfilter, double*
 void DLTSemi(double* data, const int bw, const int m, double* result, double* workspace, double* cos_pml_table,
              double* weights, fftw_plan* plan) {
     (void)workspace; (void)cos_pml_table; (void)weights; (void)plan;
-    if (s2kit_cuda_dlt_semi(plan_for(bw, S2KIT_CUDA_MEMO), data, m, result, 1, S2KIT_CUDA_HOST)) die("DLTSemi");
+    Checkout c = ctx_acquire(bw, S2KIT_CUDA_MEMO);
+    int rc = s2kit_cuda_dlt_semi(c.plan, data, m, result, 1, S2KIT_CUDA_HOST);
+    ctx_release(c);
+    if (rc) die("DLTSemi");
 }
 
 void InvDLTSemi(double* coeffs, const int bw, const int m, double* result, double* trans_cos_pml_table,
                 double* sin_values, double* workspace, fftw_plan* plan) {
     (void)trans_cos_pml_table; (void)sin_values; (void)workspace; (void)plan;
-    if (s2kit_cuda_inv_dlt_semi(plan_for(bw, S2KIT_CUDA_MEMO), coeffs, m, result, 1, S2KIT_CUDA_HOST))
-        die("InvDLTSemi");
+    Checkout c = ctx_acquire(bw, S2KIT_CUDA_MEMO);
+    int rc = s2kit_cuda_inv_dlt_semi(c.plan, coeffs, m, result, 1, S2KIT_CUDA_HOST);
+    ctx_release(c);
+    if (rc) die("InvDLTSemi");
 }
 
 /* naive.c:35-60 */
@@ -395,7 +523,9 @@ void InvDLTNaive(double* coeffs, const int bw, const int m, double* result, doub
 /* util.c:68-103 */
 void TransMult(double* rdatacoeffs, double* idatacoeffs, double* rfiltercoeffs, double* ifiltercoeffs, double* rres,
                double* ires, const int bw) {
-    if (s2kit_cuda_trans_mult(plan_for(bw, S2KIT_CUDA_MEMO), rdatacoeffs, idatacoeffs, rfiltercoeffs, ifiltercoeffs,
-                              rres, ires, 1, (long)bw * bw, S2KIT_CUDA_HOST))
-        die("TransMult");
+    Checkout c = ctx_acquire(bw, S2KIT_CUDA_MEMO);
+    int rc = s2kit_cuda_trans_mult(c.plan, rdatacoeffs, idatacoeffs, rfiltercoeffs, ifiltercoeffs, rres, ires, 1,
+                                   (long)bw * bw, S2KIT_CUDA_HOST);
+    ctx_release(c);
+    if (rc) die("TransMult");
 }

@@ -58,18 +58,8 @@ bool shard_ok(int bw, int nranks) {
 
 }  // namespace
 
-struct ShardState {
-    int nr = 0;           // rings per rank = rows per rank
-    int nrows_real = 0;   // rows of this rank that exist (one less on the rank that owns order 0)
-    long block = 0;       // doubles per (src, dst) block
-    long* d_rowbase = nullptr;
-    int* d_rowlist = nullptr;
-    int* d_orders = nullptr;
-    int norders = 0;
-    s2k::PlaneView ring_view, order_view;
-};
+#include "s2k_shard.cuh"
 
-static ShardState* shard_of(const s2kit_cuda_plan* p) { return reinterpret_cast<ShardState*>(p->shard); }
 
 extern "C" int s2kit_cuda_shard_layout(int bw, int nranks, int rank, int* orders_out, int* rows_out) {
     if (!shard_ok(bw, nranks) || rank < 0 || rank >= nranks) return -1;
@@ -112,6 +102,7 @@ extern "C" int s2kit_cuda_plan_create_sharded(s2kit_cuda_plan** out, int bw, int
     if (e == cudaSuccess) e = cudaMalloc((void**)&st->d_orders, sizeof(int) * orders.size());
     if (e == cudaSuccess)
         e = cudaMemcpy(st->d_orders, orders.data(), sizeof(int) * orders.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();  // pageable uploads have landed before any stream reads them
     if (e != cudaSuccess) {
         s2kit_cuda_plan_destroy(p);
         *out = nullptr;
@@ -166,6 +157,7 @@ extern "C" int s2kit_cuda_shard_info(const s2kit_cuda_plan* p, long* block_doubl
 // forward, stage 1: local rings (rdata/idata: [nr][2bw]) -> send blocks
 extern "C" int s2kit_cuda_fst_rings(s2kit_cuda_plan* p, const double* rdata, const double* idata, double* sendbuf) {
     if (!p || !shard_of(p)) return s2k_fail_msg("not a sharded plan");
+    std::lock_guard<std::mutex> lock(*p->mu);
     CKS(cudaSetDevice(p->device));
     ShardState* st = shard_of(p);
     CKS(s2k::launch_phi_fft_fwd(p, rdata, idata, 0, sendbuf, 1, S2KIT_COMPLEX, &st->ring_view));
@@ -175,6 +167,7 @@ extern "C" int s2kit_cuda_fst_rings(s2kit_cuda_plan* p, const double* rdata, con
 // forward, stage 2: receive blocks -> coefficients of this rank's orders (positions of the full bw*bw arrays)
 extern "C" int s2kit_cuda_fst_orders(s2kit_cuda_plan* p, const double* recvbuf, double* rcoeffs, double* icoeffs) {
     if (!p || !shard_of(p)) return s2k_fail_msg("not a sharded plan");
+    std::lock_guard<std::mutex> lock(*p->mu);
     CKS(cudaSetDevice(p->device));
     ShardState* st = shard_of(p);
     CKS(s2k::launch_dct_fwd(p, recvbuf, p->d_X, 1, 0, st->nrows_real, S2KIT_COMPLEX, &st->order_view));
@@ -187,6 +180,7 @@ extern "C" int s2kit_cuda_fst_orders(s2kit_cuda_plan* p, const double* recvbuf, 
 extern "C" int s2kit_cuda_inv_fst_orders(s2kit_cuda_plan* p, const double* rcoeffs, const double* icoeffs,
                                          double* sendbuf) {
     if (!p || !shard_of(p)) return s2k_fail_msg("not a sharded plan");
+    std::lock_guard<std::mutex> lock(*p->mu);
     CKS(cudaSetDevice(p->device));
     ShardState* st = shard_of(p);
     CKS(s2k::launch_legendre_inv(p, p->d_table_t, 0, rcoeffs, icoeffs, (long)p->bw * p->bw, p->d_X, 1, 0, st->norders,
@@ -198,6 +192,7 @@ extern "C" int s2kit_cuda_inv_fst_orders(s2kit_cuda_plan* p, const double* rcoef
 // inverse, stage 2: receive blocks -> local rings
 extern "C" int s2kit_cuda_inv_fst_rings(s2kit_cuda_plan* p, const double* recvbuf, double* rdata, double* idata) {
     if (!p || !shard_of(p)) return s2k_fail_msg("not a sharded plan");
+    std::lock_guard<std::mutex> lock(*p->mu);
     CKS(cudaSetDevice(p->device));
     ShardState* st = shard_of(p);
     CKS(s2k::launch_phi_fft_inv(p, recvbuf, rdata, idata, 0, 1, S2KIT_COMPLEX, &st->ring_view));
