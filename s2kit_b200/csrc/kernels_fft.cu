@@ -268,11 +268,11 @@ __global__ void __launch_bounds__(N) k_phi_fft_inv_tma(double* __restrict__ rdat
 __device__ __forceinline__ int ridx_to_row(int ridx, int bw) { return ridx < bw ? ridx : ridx + 1; }
 
 // One CTA handles FPB (function, order row) pairs; each pair = re and im column -> one complex FFT.
-template <int N, int FPB>
+template <int N, int FPB, bool PEER>
 __global__ void __launch_bounds__(N / 8 * FPB) k_dct_fwd(const double* __restrict__ S, double* __restrict__ X,
                                                          const double* __restrict__ weights, int ridx_lo, int ridx_hi,
                                                          const double2* __restrict__ tw,
-                                                         const double2* __restrict__ qtab, PlaneView pv) {
+                                                         const double2* __restrict__ qtab, PlaneView pv, PeerSegs peers) {
     constexpr int T8 = N / 8, B = N / 2, NP = fft_padded_len(N);
     extern __shared__ double2 smem2[];
     const int tid = threadIdx.x, g = tid / T8, t = tid % T8;
@@ -291,11 +291,11 @@ __global__ void __launch_bounds__(N / 8 * FPB) k_dct_fwd(const double* __restric
     for (int e = 0; e < 8; ++e) {
         int p = t + e * T8;
         double wj = __ldg(w + p);  // weights are stored in load order (s2k_host_reordered)
-        if (pv.use_segptr) {
+        if constexpr (PEER) {
             // single field over the GPUs of one process: the segment lives in a peer's memory -- the ring -> order
             // exchange IS these loads (NVLink reads of contiguous runs, overlapped with the transforms of other CTAs)
             const int j = (p < B) ? 2 * p : 2 * (N - 1 - p) + 1;
-            const double* src = pv.segptr[j >> pv.seg_shift] + rowoff + (j & pv.seg_mask);
+            const double* src = peers.ptr[j >> pv.seg_shift] + rowoff + (j & pv.seg_mask);
             xr[e] = src[0] * wj;
             xi[e] = src[pv.part_stride] * wj;
             continue;
@@ -352,11 +352,11 @@ __global__ void __launch_bounds__(N / 8 * FPB) k_dct_fwd(const double* __restric
 }
 
 // ------------------------------------------------------------------------------------------------ K5
-template <int N, int FPB>
+template <int N, int FPB, bool PEER>
 __global__ void __launch_bounds__(N / 8 * FPB) k_dct_inv(const double* __restrict__ V, double* __restrict__ G,
                                                          const double* __restrict__ sinv, int ridx_lo, int ridx_hi,
                                                          double out_scale, const double2* __restrict__ tw,
-                                                         const double2* __restrict__ qtab, PlaneView pv) {
+                                                         const double2* __restrict__ qtab, PlaneView pv, PeerSegs peers) {
     constexpr int T8 = N / 8, B = N / 2, NP = fft_padded_len(N);
     extern __shared__ double2 smem2[];
     const int tid = threadIdx.x, g = tid / T8, t = tid % T8;
@@ -402,10 +402,10 @@ __global__ void __launch_bounds__(N / 8 * FPB) k_dct_inv(const double* __restric
     for (int e = 0; e < 8; ++e) {
         int i = fft_out_index<N>(e, t);
         double s = (m & 1) ? __ldg(sinv + i) * sign : sign;  // sines stored in output order (s2k_host_reordered)
-        if (pv.use_segptr) {
+        if constexpr (PEER) {
             // order -> ring exchange as NVLink stores into the ring owner's receive block (multi.cu)
             const int j = (i < B) ? 2 * i : 2 * (N - 1 - i) + 1;
-            double* dst = const_cast<double*>(pv.segptr[j >> pv.seg_shift]) + rowoff + (j & pv.seg_mask);
+            double* dst = const_cast<double*>(peers.ptr[j >> pv.seg_shift]) + rowoff + (j & pv.seg_mask);
             dst[0] = xi[e] * s;
             dst[pv.part_stride] = xr[e] * s;
             continue;
@@ -569,10 +569,18 @@ static cudaError_t dct_fwd_n(s2kit_cuda_plan* p, const double* S, double* X, int
     constexpr int T8 = N / 8;
     constexpr int FPB = (256 / T8) < 1 ? 1 : ((256 / T8) > 8 ? 8 : (256 / T8));
     size_t smem = sizeof(double2) * FPB * fft_padded_len(N);
-    cudaError_t e = set_smem(k_dct_fwd<N, FPB>, smem);
+    const dim3 grid((hi - lo + FPB - 1) / FPB, nfun);
+    if (pv.peers) {
+        cudaError_t e = set_smem(k_dct_fwd<N, FPB, true>, smem);
+        if (e != cudaSuccess) return e;
+        k_dct_fwd<N, FPB, true><<<grid, T8 * FPB, smem, p->stream>>>(S, X, p->d_wv, lo, hi, p->d_tw_n, p->d_q_n, pv,
+                                                                     *pv.peers);
+        return cudaGetLastError();
+    }
+    cudaError_t e = set_smem(k_dct_fwd<N, FPB, false>, smem);
     if (e != cudaSuccess) return e;
-    k_dct_fwd<N, FPB><<<dim3((hi - lo + FPB - 1) / FPB, nfun), T8 * FPB, smem, p->stream>>>(
-        S, X, p->d_wv, lo, hi, p->d_tw_n, p->d_q_n, pv);
+    k_dct_fwd<N, FPB, false><<<grid, T8 * FPB, smem, p->stream>>>(S, X, p->d_wv, lo, hi, p->d_tw_n, p->d_q_n, pv,
+                                                                  PeerSegs());
     return cudaGetLastError();
 }
 
@@ -580,16 +588,24 @@ template <int N>
 static cudaError_t dct_inv_n(s2kit_cuda_plan* p, const double* V, double* G, int nfun, int lo, int hi,
                              const PlaneView& pv) {
     if constexpr (N == 512) {
-        if (fft16_enabled()) return launch_dct_inv16(p, V, G, nfun, lo, hi, pv);
+        if (fft16_enabled() && !pv.peers) return launch_dct_inv16(p, V, G, nfun, lo, hi, pv);
     }
     constexpr int T8 = N / 8;
     constexpr int FPB = (256 / T8) < 1 ? 1 : ((256 / T8) > 8 ? 8 : (256 / T8));
     size_t smem = sizeof(double2) * FPB * fft_padded_len(N);
-    cudaError_t e = set_smem(k_dct_inv<N, FPB>, smem);
-    if (e != cudaSuccess) return e;
     double out_scale = 1.0 / sqrt(2.0 * M_PI);  // FST_semi_memo.c:344
-    k_dct_inv<N, FPB><<<dim3((hi - lo + FPB - 1) / FPB, nfun), T8 * FPB, smem, p->stream>>>(
-        V, G, p->d_sv, lo, hi, out_scale, p->d_tw_n, p->d_q_n, pv);
+    const dim3 grid((hi - lo + FPB - 1) / FPB, nfun);
+    if (pv.peers) {
+        cudaError_t e = set_smem(k_dct_inv<N, FPB, true>, smem);
+        if (e != cudaSuccess) return e;
+        k_dct_inv<N, FPB, true><<<grid, T8 * FPB, smem, p->stream>>>(V, G, p->d_sv, lo, hi, out_scale, p->d_tw_n,
+                                                                     p->d_q_n, pv, *pv.peers);
+        return cudaGetLastError();
+    }
+    cudaError_t e = set_smem(k_dct_inv<N, FPB, false>, smem);
+    if (e != cudaSuccess) return e;
+    k_dct_inv<N, FPB, false><<<grid, T8 * FPB, smem, p->stream>>>(V, G, p->d_sv, lo, hi, out_scale, p->d_tw_n, p->d_q_n,
+                                                                  pv, PeerSegs());
     return cudaGetLastError();
 }
 

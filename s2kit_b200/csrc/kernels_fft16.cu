@@ -61,13 +61,6 @@ __global__ void __launch_bounds__(F16_WARPS * 32, 2) k_dct_inv16(const double* _
     for (int o = 0; o < 16; ++o) {
         const int i = f16_out_index(lane, o);
         const double s = (m & 1) ? __ldg(sinv + i) * sign : sign;  // sines stored in output order (s2k_host_reordered)
-        if (pv.use_segptr) {  // peer-mapped ring blocks (multi.cu)
-            const int j = (i < B) ? 2 * i : 2 * (N - 1 - i) + 1;
-            double* dst = const_cast<double*>(pv.segptr[j >> pv.seg_shift]) + rowoff + (j & pv.seg_mask);
-            dst[0] = xi[o] * s;
-            dst[pv.part_stride] = xr[o] * s;
-            continue;
-        }
         long at = i;  // lat_perm: the row is kept in output order
         if (!pv.lat_perm) {
             const int j = (i < B) ? 2 * i : 2 * (N - 1 - i) + 1;

@@ -146,8 +146,10 @@ void run_forward(s2kit_cuda_multi* mp, int g, unsigned gen, bool first, bool las
     for (int q = 0; q < mp->G; ++q)
         if (q != g) MCK(d, cudaStreamWaitEvent(s, mp->dev[q].ev_x[b], 0));
     s2k::PlaneView ov = st->order_view;
-    ov.use_segptr = 1;
-    for (int q = 0; q < mp->G; ++q) ov.segptr[q] = mp->dev[q].ringbuf[b] + (long)g * mp->block;
+    s2k::PeerSegs peers;
+    memset(&peers, 0, sizeof(peers));
+    for (int q = 0; q < mp->G; ++q) peers.ptr[q] = mp->dev[q].ringbuf[b] + (long)g * mp->block;
+    ov.peers = &peers;
     // K2 pulls its rows out of the peers' K1 output: the exchange rides on the kernel's own loads
     MCK(d, s2k::launch_dct_fwd(p, d.ringbuf[b], p->d_X, 1, 0, st->nrows_real, S2KIT_COMPLEX, &ov));
     MCK(d, s2k::launch_legendre_fwd(p, p->d_table, 0, p->d_X, d.coef_r, d.coef_i, (long)bw * bw, 1, 0, st->norders,
@@ -186,8 +188,10 @@ void run_inverse(s2kit_cuda_multi* mp, int g, unsigned gen, bool first, bool las
     MCK(d, s2k::launch_legendre_inv(p, p->d_table_t, 0, d.coef_r, d.coef_i, (long)bw * bw, p->d_X, 1, 0, st->norders,
                                     S2KIT_COMPLEX, st->d_orders));
     s2k::PlaneView ov = st->order_view;
-    ov.use_segptr = 1;
-    for (int q = 0; q < mp->G; ++q) ov.segptr[q] = mp->dev[q].ringbuf[b] + (long)g * mp->block;
+    s2k::PeerSegs peers;
+    memset(&peers, 0, sizeof(peers));
+    for (int q = 0; q < mp->G; ++q) peers.ptr[q] = mp->dev[q].ringbuf[b] + (long)g * mp->block;
+    ov.peers = &peers;
     MCK(d, s2k::launch_dct_inv(p, p->d_X, d.ringbuf[b], 1, 0, st->nrows_real, S2KIT_COMPLEX, &ov));
     MCK(d, cudaEventRecord(d.ev_x[b], s));
     mp->bar.wait();

@@ -50,9 +50,13 @@ struct PlaneView {
     // 8 even or 8 odd grid rows); it is private to one fst / inv_fst call.
     int lat_perm = 0;
     // K2/K5 on a single field split over the GPUs of one process (multi.cu): segment s of a row lives in the memory of
-    // peer s (peer-mapped pointers, NVLink loads / stores straight from the DCT kernels); null -> seg_stride addressing
-    const double* segptr[S2K_MAX_PEERS] = {nullptr};
-    int use_segptr = 0;
+    // peer s (PeerSegs below, passed to the PEER instantiations of the DCT kernels as a separate argument so that the
+    // ordinary instantiations keep their parameters in constant memory without dynamic indexing)
+    const struct PeerSegs* peers = nullptr;  // host-side only: the launchers pick the PEER kernels when set
+};
+
+struct PeerSegs {
+    const double* ptr[S2K_MAX_PEERS];  // peer-mapped base of segment s (this rank's block inside peer s's ring buffer)
 };
 
 // address (doubles from the plane base of the local row) of latitude j in a row cut into segments

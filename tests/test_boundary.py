@@ -107,11 +107,13 @@ def test_product_does_not_touch_the_oracle():
     assert "oracle" not in out and "fftw" not in out
 
 
-@pytest.mark.parametrize("check,expect", [("layout_check", "layout mismatches: 0"), ("fft16_check", "exactly once: 0")])
+@pytest.mark.parametrize("check,expect", [("layout_check", "layout mismatches: 0"), ("fft16_check", "exactly once: 0"),
+                                          ("dct16_check", "dct16 check: OK")])
 def test_host_side_checks_of_device_helpers(tmp_path, check, expect):
     """Host-only programs built from the same headers as the kernels: (1) the closed-form tile layout the persistent
     kernels use instead of dependent loads against the tabulated layout for bandwidths 2 .. 2048; (2) the register-level
-    pieces of the one-warp 512-point FFT (s2k_fft16.cuh) for 32 emulated lanes against a long-double DFT."""
+    pieces of the one-warp 512-point FFT (s2k_fft16.cuh) for 32 emulated lanes against a long-double DFT; (3) the forward
+    DCT pair on that FFT with its in-place shared-memory exchange and shuffle-based separation (s2k_dct16.cuh)."""
     import shutil
     import subprocess
 

@@ -66,7 +66,7 @@ def test_memo_large_bw_vs_reference_samples(s2, oracle_mod, large, bw):
     # REAL format agrees with COMPLEX on a real field (the reference's two code paths, FST_semi_memo.c:131-145)
     fr2, fi2 = P.forward(rd, np.zeros_like(rd), 1)
     fr3, fi3 = P.forward(rd, np.zeros_like(rd), 0)
-    assert relerr(cat((fr2, fi2)), cat((fr3, fi3))) < 1e-13
+    assert relerr(cat((fr2, fi2)), cat((fr3, fi3))) < 1e-11
     P.close()
 
 
