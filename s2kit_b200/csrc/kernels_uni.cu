@@ -1,0 +1,319 @@
+// kernels_uni.cu -- the batched forward path at bw = 256 as ONE persistent kernel of UNIFORM warps: K2 + K3 fused.
+//
+//   weights . DCT-II(2bw) . triangular contraction . coefficient placement
+//   (DLTSemi, src/legendre_transform/seminaive.c:153-198, inside the m-loops of FSTSemiMemo,
+//    src/FST_semi_memo.c:96-108,131-145,175-201)
+//
+// Successor of the warp-specialised k_fwd_pipe (kernels_pipe.cu), which ran the FP64 pipe at 50 % (DMMA 28.8 % + DFMA
+// 21.7 %, profiles/r1_ncu_pipe_summary.md): its 8 DCT warps and 8 DMMA warps share one pipe, the kernel cost the SUM of
+// the two halves, and whenever the consumers waited for a panel only the latency-bound FFT warps were left to feed it.
+// Here there are no roles.  Work items are still (order m, 32-column tile), dealt round-robin to one CTA per SM, but
+// inside the CTA every item is cut into TASKS that any of the 16 warps takes from a shared-memory counter:
+//   * 16 DCT tasks of the NEXT item: one warp turns the weighted real / imaginary spectral rows of one (function, +-m)
+//     into two panel columns with the one-warp 512-point FFT (s2k_fft16.cuh / s2k_dct16.cuh: 16 points per lane, one
+//     shared-memory exchange done in place inside the warp's own two panel columns, no named barriers, a third fewer
+//     FP64 instructions per point than the 8-points-per-thread block FFT);
+//   * the DMMA sub-items of the CURRENT item: single row tiles for the long rows, pairs of adjacent row tiles (which
+//     share every panel fragment) for the short ones, heaviest first (host-built list, plan.cu), table tiles through
+//     the lane-private cp.async ring that removed the table-latency stalls in k_leg_fwd_stream.
+// DCT and DMMA tasks alternate in the task order, so at any time about half of the warps issue DFMAs and half DMMAs:
+// the latency gaps of the FFT code are filled by DMMAs of other warps and the pipe stays busy.  One __syncthreads per
+// item separates the panel generations (two panel buffers).
+#include <stdlib.h>
+
+#include "s2k_dct16.cuh"
+#include "s2k_legendre.cuh"
+
+namespace s2k {
+
+constexpr int UNI_NC = 32;
+constexpr int UNI_WARPS = 16;
+constexpr int UNI_THREADS = UNI_WARPS * 32;
+constexpr int UNI_RING = 8;  // table tiles in flight per warp (8 x 512 B)
+
+struct UniArgs {
+    const double* table;
+    const uint64_t* order_start;
+    uint64_t table_shift;
+    const int* sub_off;    // [bw + 1] first sub-item of each order
+    const int* sub_list;   // packed sub-items: parity | row tile << 1 | pair << 12
+    const double* S;       // spectral planes [f][part][order row][latitude slot]
+    const double* weights; // 4bw, load order (s2k_host_reordered)
+    const double2* tw;
+    const double2* qtab;
+    double* rco;
+    double* ico;
+    long coef_stride;
+    int nfun, m_lo, norders, ncoltiles, real_fmt, lat_perm;
+};
+
+__device__ __forceinline__ void uni_item(const UniArgs& a, int t, int NF, int& m, int& f0) {
+    const int oi = t / a.ncoltiles, x = t - oi * a.ncoltiles;
+    m = a.m_lo + oi;
+    f0 = x * NF;
+}
+
+// One DMMA sub-item: row tile rt1 (and, PAIR, rt1 - 1 = rt0) of one parity block against the panel.
+// tp0 / tp1: this lane's 16 bytes of the first tile of row tile rt0 / rt1; skip0 / skip1: the second k-step of the last
+// column tile multiplies only padding.
+template <bool PAIR>
+__device__ __forceinline__ void uni_rows(const double* __restrict__ tp0, int ctn0, bool skip0,
+                                         const double* __restrict__ tp1, int ctn1, bool skip1, const double* xp,
+                                         double (&acc0)[UNI_NC / 8][2], double (&acc1)[UNI_NC / 8][2], double2* ring) {
+    constexpr int NC = UNI_NC, CS = 132;
+    constexpr int STEPS = PAIR ? UNI_RING / 2 : UNI_RING;  // column-tile steps in flight
+#pragma unroll
+    for (int u = 0; u < STEPS; ++u) {
+        if (u < ctn1) {
+            if (PAIR && u < ctn0) cp_async16(reinterpret_cast<double*>(ring + ((2 * u) & (UNI_RING - 1)) * 32), tp0 + u * 64);
+            cp_async16(reinterpret_cast<double*>(ring + ((PAIR ? 2 * u + 1 : u) & (UNI_RING - 1)) * 32), tp1 + u * 64);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+#pragma unroll 1
+    for (int ct = 0; ct < ctn1; ++ct) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(STEPS - 1) : "memory");
+        double2* s1 = ring + ((PAIR ? 2 * ct + 1 : ct) & (UNI_RING - 1)) * 32;
+        double2* s0 = ring + ((2 * ct) & (UNI_RING - 1)) * 32;
+        const double2 a1 = *s1;
+        double2 a0 = make_double2(0.0, 0.0);
+        const bool have0 = PAIR && ct < ctn0;
+        if (have0) a0 = *s0;
+        double b[NC / 8][2];
+#pragma unroll
+        for (int j = 0; j < NC / 8; ++j) {
+            b[j][0] = xp[j * 8 * CS + 8 * ct];
+            b[j][1] = xp[j * 8 * CS + 8 * ct + 4];
+        }
+        if (have0) {
+#pragma unroll
+            for (int j = 0; j < NC / 8; ++j) dmma(acc0[j], a0.x, b[j][0]);
+        }
+#pragma unroll
+        for (int j = 0; j < NC / 8; ++j) dmma(acc1[j], a1.x, b[j][0]);
+        if (have0 && !(skip0 && ct == ctn0 - 1)) {
+#pragma unroll
+            for (int j = 0; j < NC / 8; ++j) dmma(acc0[j], a0.y, b[j][1]);
+        }
+        if (!(skip1 && ct == ctn1 - 1)) {
+#pragma unroll
+            for (int j = 0; j < NC / 8; ++j) dmma(acc1[j], a1.y, b[j][1]);
+        }
+        // the DMMAs above have consumed the slots' registers: refill with the step STEPS ahead
+        const int nx = ct + STEPS;
+        if (nx < ctn1) {
+            if (PAIR && nx < ctn0) cp_async16(reinterpret_cast<double*>(s0), tp0 + nx * 64);
+            cp_async16(reinterpret_cast<double*>(s1), tp1 + nx * 64);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(UNI_THREADS, 1) k_fwd_uni(const UniArgs a) {
+    constexpr int N = 512, B = 256, NC = UNI_NC, CS = 132, PS = NC * CS + 8, PANEL = 2 * PS;
+    extern __shared__ __align__(16) double smem[];
+    double* panels = smem;                                                  // [2][PANEL]
+    double2* rings = reinterpret_cast<double2*>(smem + 2 * PANEL);          // [WARPS][RING][32]
+    int* ctr = reinterpret_cast<int*>(rings + UNI_WARPS * UNI_RING * 32);   // task counters of the two generations
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q4 = lane & 3;
+    const int cols_per_fn = a.real_fmt ? 2 : 4, NF = NC / cols_per_fn;
+    const int nitems = a.norders * a.ncoltiles;
+    const int nk = (nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    double2* ring = rings + warp * UNI_RING * 32 + lane;
+    const double s_all = 1.0 / sqrt(2.0 * (double)N);  // 1/sqrt(2*size), seminaive.c:174
+
+    if (tid < 2) ctr[tid] = 0;
+    __syncthreads();
+
+    // DCT task `q` of item `item`: panel columns 2q (real part) and 2q + 1 (imaginary part) of buffer `buf`
+    auto dct_task = [&](int item, int q, double* buf) {
+        int m, f0;
+        uni_item(a, item, NF, m, f0);
+        const int fl = a.real_fmt ? q : (q >> 1), sgn = a.real_fmt ? 0 : (q & 1);
+        const int f = f0 + fl;
+        double* col0 = buf + (2 * q) * CS;
+        if (f >= a.nfun || (sgn && m == 0)) {  // dead pair: the contraction still multiplies these columns
+            for (int i = lane; i < 2 * CS; i += 32) col0[i] = col0[PS + i] = 0.0;
+            return;
+        }
+        const int mp = sgn ? N - m : m;
+        const double* Sr = a.S + ((long)f * 2 * N + mp) * N;
+        const double* Si = Sr + (long)N * N;
+        const double* w = a.weights + ((m & 1) ? N : 0);
+        double xr[16], xi[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            const int p = lane + 32 * e;
+            const int at = a.lat_perm ? p : ((p < B) ? 2 * p : 2 * (N - 1 - p) + 1);
+            const double wj = __ldg(w + p);
+            xr[e] = __ldg(Sr + at) * wj;
+            xi[e] = __ldg(Si + at) * wj;
+        }
+        d16_dct2_pair_to_panel<CS>(xr, xi, col0, PS, lane, a.tw, a.qtab, s_all);
+    };
+
+    // DMMA sub-item `idx` of the item (m, f0) whose panel is `Xs`
+    auto dmma_task = [&](int m, int f0, int idx, const double* Xs) {
+        const int code = __ldg(a.sub_list + __ldg(a.sub_off + m) + idx);
+        const int p = code & 1, rt1 = (code >> 1) & 0x7ff, pair = code >> 12;
+        const BlockMeta mb0 = block_meta_of(m, 0, B);
+        const BlockMeta mb = p ? block_meta_of(m, 1, B) : mb0;
+        const double* tblk = a.table + (a.order_start[m] - a.table_shift + (p ? block_tiles_of(mb0) : 0u)) * 64 + lane * 2;
+        const double* xp = Xs + p * PS + g * CS + q4;
+        const int ctn1 = tiles_in_row(mb, rt1);
+        const bool skip1 = mb.len0 + min(8 * rt1 + 7, mb.rows - 1) - 8 * (ctn1 - 1) <= 4;
+        const double* tp1 = tblk + (uint64_t)row_tile_start_of(mb, rt1) * 64;
+        double acc0[NC / 8][2], acc1[NC / 8][2];
+#pragma unroll
+        for (int j = 0; j < NC / 8; ++j) acc0[j][0] = acc0[j][1] = acc1[j][0] = acc1[j][1] = 0.0;
+        const int rt0 = pair ? rt1 - 1 : -1;
+        if (pair) {
+            const int ctn0 = tiles_in_row(mb, rt0);
+            const bool skip0 = mb.len0 + 8 * rt0 + 7 - 8 * (ctn0 - 1) <= 4;  // rt0 < rt1: a full row tile
+            uni_rows<true>(tblk + (uint64_t)row_tile_start_of(mb, rt0) * 64, ctn0, skip0, tp1, ctn1, skip1, xp, acc0, acc1, ring);
+        } else {
+            uni_rows<false>(tp1, 0, false, tp1, ctn1, skip1, xp, acc0, acc1, ring);
+        }
+        // ---- epilogue (k_fwd_pipe / K3): the lane's columns 8j + 2 q4 + {0,1} = (function, sign, re / im) in closed form
+        const int sgn = a.real_fmt ? 0 : (q4 & 1);
+        const int fl0 = a.real_fmt ? q4 : (q4 >> 1), flstep = a.real_fmt ? 4 : 2;
+        const long run0 = (long)(f0 + fl0) * a.coef_stride + (sgn ? coef_base(-m, B) : coef_base(m, B));
+        const long mrun0 = (long)(f0 + fl0) * a.coef_stride + coef_base(-m, B);
+        const unsigned long long flip = (sgn && (m & 1)) ? 0x8000000000000000ull : 0ull;  // FST_semi_memo.c:181-186
+        const bool live_sign = !(sgn && m == 0);
+        const bool mirror = a.real_fmt && m > 0;  // FST_semi_memo.c:131-145
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = 8 * (h ? rt1 : rt0) + g;
+            if ((h == 0 && rt0 < 0) || r >= mb.rows || !live_sign) continue;
+            const int off = p + 2 * r;  // l - m
+#pragma unroll
+            for (int j = 0; j < NC / 8; ++j) {
+                if (f0 + fl0 + j * flstep >= a.nfun) continue;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const unsigned long long bits = (unsigned long long)__double_as_longlong(h ? acc1[j][e] : acc0[j][e]);
+                    double* arr = e ? a.ico : a.rco;
+                    arr[run0 + (long)j * flstep * a.coef_stride + off] = __longlong_as_double((long long)(bits ^ flip));
+                    if (mirror) {
+                        const unsigned long long mflip = ((m & 1) ^ e) ? 0x8000000000000000ull : 0ull;
+                        arr[mrun0 + (long)j * flstep * a.coef_stride + off] = __longlong_as_double((long long)(bits ^ mflip));
+                    }
+                }
+            }
+        }
+    };
+
+    // ---- prologue: the panel of this CTA's first item
+    if (nk > 0) {
+        int m, f0;
+        uni_item(a, blockIdx.x, NF, m, f0);
+        if (warp == 0)
+            prefetch_order_l2(a.table + (a.order_start[m] - a.table_shift) * 64, a.order_start[m + 1] - a.order_start[m], lane, 32,
+                              1u << 20);
+        for (;;) {
+            int t = 0;
+            if (lane == 0) t = atomicAdd(&ctr[1], 1);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            if (t >= NC / 2) break;
+            dct_task(blockIdx.x, t, panels);
+        }
+    }
+    __syncthreads();
+
+#pragma unroll 1
+    for (int k = 0; k < nk; ++k) {
+        const int item = blockIdx.x + k * gridDim.x, b = k & 1;
+        const bool has_next = k + 1 < nk;
+        int m, f0;
+        uni_item(a, item, NF, m, f0);
+        if (tid == 0) ctr[b ^ 1] = 0;  // counter of the next generation: idle since the barrier before last
+        if (warp == 1 && has_next) {    // the next item's table tiles into L2 ahead of its contraction
+            int m2, f2;
+            uni_item(a, item + gridDim.x, NF, m2, f2);
+            if (m2 != m)
+                prefetch_order_l2(a.table + (a.order_start[m2] - a.table_shift) * 64, a.order_start[m2 + 1] - a.order_start[m2],
+                                  lane, 32, 1u << 20);
+        }
+        const int nd = __ldg(a.sub_off + m + 1) - __ldg(a.sub_off + m), nf = has_next ? NC / 2 : 0;
+        const int mi = nf < nd ? nf : nd, ntask = nf + nd;
+        const double* Xs = panels + b * PANEL;
+        double* Xn = panels + (b ^ 1) * PANEL;
+        for (;;) {
+            int t = 0;
+            if (lane == 0) t = atomicAdd(&ctr[b], 1);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            if (t >= ntask) break;
+            // DCT and DMMA tasks alternate while both kinds last
+            bool is_dct;
+            int idx;
+            if (t < 2 * mi) {
+                is_dct = !(t & 1);
+                idx = t >> 1;
+            } else if (nf > nd) {
+                is_dct = true;
+                idx = t - nd;
+            } else {
+                is_dct = false;
+                idx = t - nf;
+            }
+            if (is_dct)
+                dct_task(item + gridDim.x, idx, Xn);
+            else
+                dmma_task(m, f0, idx, Xs);
+        }
+        __syncthreads();  // panel b is drained, panel b ^ 1 is complete
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ launcher
+static bool uni_enabled() {
+    static int on = [] {
+        const char* e = getenv("S2KIT_CUDA_UNI");
+        return (e && e[0] == '0') ? 0 : 1;
+    }();
+    return on != 0;
+}
+
+bool fwd_uni_supported(const s2kit_cuda_plan* p, int nfun, int data_format) {
+    if (!uni_enabled() || !p->fast || p->n != 512 || !p->d_sub_list) return false;
+    return nfun * (data_format == S2KIT_REAL ? 2 : 4) >= UNI_NC;
+}
+
+cudaError_t launch_fwd_uni(s2kit_cuda_plan* p, const double* table, uint64_t shift, const double* S, double* rco,
+                           double* ico, long coef_stride, int nfun, int m_lo, int m_hi, int data_format, int lat_perm) {
+    if (m_hi <= m_lo || nfun <= 0) return cudaSuccess;
+    UniArgs a;
+    a.table = table;
+    a.order_start = p->d_order_start;
+    a.table_shift = shift;
+    a.sub_off = p->d_sub_off;
+    a.sub_list = p->d_sub_list;
+    a.S = S;
+    a.weights = p->d_wv;
+    a.tw = p->d_tw_n;
+    a.qtab = p->d_q_n;
+    a.rco = rco;
+    a.ico = ico;
+    a.coef_stride = coef_stride;
+    a.nfun = nfun;
+    a.m_lo = m_lo;
+    a.norders = m_hi - m_lo;
+    a.real_fmt = data_format == S2KIT_REAL;
+    const int NF = UNI_NC / (a.real_fmt ? 2 : 4);
+    a.ncoltiles = (nfun + NF - 1) / NF;
+    a.lat_perm = lat_perm;
+    constexpr int PANEL = 2 * (UNI_NC * 132 + 8);
+    const size_t smem = sizeof(double) * 2 * PANEL + sizeof(double2) * UNI_WARPS * UNI_RING * 32 + 16;
+    cudaError_t e = ensure_smem(reinterpret_cast<const void*>(k_fwd_uni), smem);
+    if (e != cudaSuccess) return e;
+    const int nitems = a.norders * a.ncoltiles;
+    int slot = prof_begin(p, S2KIT_K_FUSED_FWD);
+    k_fwd_uni<<<nitems < p->sm_count ? nitems : p->sm_count, UNI_THREADS, smem, p->stream>>>(a);
+    e = cudaGetLastError();
+    prof_end(p, slot);
+    return e;
+}
+
+}  // namespace s2k

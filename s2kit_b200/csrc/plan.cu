@@ -165,6 +165,36 @@ static void build_layout(s2kit_cuda_plan* p, const std::vector<char>& owned) {
     p->h_unit_first[bw] = (int)p->h_units.size() / 2;
 }
 
+// Work list of the uniform-warp forward kernel (kernels_uni.cu): per order the (parity, row tile) units of the
+// contraction, long rows alone, short rows in adjacent pairs of at most `cap` column-tile steps, heaviest first.
+static void build_subitems(s2kit_cuda_plan* p, std::vector<int>& off, std::vector<int>& list) {
+    const int bw = p->bw;
+    int cap = 16;
+    if (const char* e = getenv("S2KIT_CUDA_UNI_CAP")) cap = std::max(0, atoi(e));
+    off.assign(bw + 1, 0);
+    list.clear();
+    for (int m = 0; m < bw; ++m) {
+        std::vector<std::pair<int, int>> items;  // (cost, code)
+        for (int par = 0; par < 2; ++par) {
+            const s2k::BlockMeta& mb = p->h_meta[2 * m + par];
+            auto tiles = [&](int rt) { return (mb.len0 + std::min(8 * rt + 7, mb.rows - 1) + 7) >> 3; };
+            int rt = mb.nrt - 1;
+            while (rt >= 0) {
+                if (rt >= 1 && tiles(rt) + tiles(rt - 1) <= cap) {
+                    items.push_back({tiles(rt) + tiles(rt - 1), par | (rt << 1) | (1 << 12)});
+                    rt -= 2;
+                } else {
+                    items.push_back({tiles(rt), par | (rt << 1)});
+                    rt -= 1;
+                }
+            }
+        }
+        std::stable_sort(items.begin(), items.end(), [](const std::pair<int, int>& x, const std::pair<int, int>& y) { return x.first > y.first; });
+        for (auto& it : items) list.push_back(it.second);
+        off[m + 1] = (int)list.size();
+    }
+}
+
 // Keep a Memo table that fits comfortably in L2 resident across launches: the batch streams hundreds of MB through
 // L2 between two uses of the same order's tiles (persisting-L2 access policy window on the plan's stream).
 static void apply_table_l2_policy(s2kit_cuda_plan* p) {
@@ -342,6 +372,12 @@ static int plan_build(s2kit_cuda_plan* p, int bw, int variant, int max_batch, in
     CK(upload(p->stream, &p->d_rt_start, p->h_rt_start.data(), p->h_rt_start.size()));
     CK(upload(p->stream, &p->d_order_start, p->h_order_start.data(), p->h_order_start.size()));
     CK(upload(p->stream, &p->d_units, p->h_units.data(), p->h_units.size()));
+    if (p->fast && p->n == 512 && nranks == 1) {
+        std::vector<int> off, list;
+        build_subitems(p, off, list);
+        CK(upload(p->stream, &p->d_sub_off, off.data(), off.size()));
+        CK(upload(p->stream, &p->d_sub_list, list.data(), list.size()));
+    }
     CK(s2k::launch_rec_coeffs(p));
 
     // ---- tables
@@ -413,7 +449,8 @@ extern "C" int s2kit_cuda_plan_destroy(s2kit_cuda_plan* p) {
     s2k_shard_destroy(p);
     // tables and constants of a clone belong to the plan it was cloned from
     void* shared[] = {p->d_wv, p->d_sv, p->d_weights, p->d_sin, p->d_tw_n, p->d_tw_b, p->d_q_n, p->d_q_b, p->d_nodes,
-                      p->d_seeds, p->d_rec, p->d_meta, p->d_rt_start, p->d_order_start, p->d_units};
+                      p->d_seeds, p->d_rec, p->d_meta, p->d_rt_start, p->d_order_start, p->d_units,
+                      p->d_sub_off,  p->d_sub_list};
     void* own[] = {p->d_S, p->d_X, p->d_coef, p->d_coef2, p->d_filt, p->d_stage};
     if (!p->shares_tables)
         for (void* q : shared)
@@ -547,13 +584,17 @@ static int fst_device(s2kit_cuda_plan* p, const double* rdata, const double* ida
         s2k::PlaneView pv = s2k::default_view(p->n);
         pv.lat_perm = s2k::tma_planes_ok(p, nf);
         CK(s2k::launch_phi_fft_fwd(p, rd, id, data_stride, p->d_S, nf, fmt, &pv));
-        // batched: one persistent kernel does the DCTs and the contraction (kernels_pipe.cu)
+        // batched: one persistent kernel does the DCTs and the contraction (kernels_uni.cu at bw = 256, kernels_pipe.cu)
         const bool pipe = s2k::fwd_pipe_supported(p, nf, fmt);
+        const bool uni = pipe && s2k::fwd_pipe_fused() && s2k::fwd_uni_supported(p, nf, fmt);
         const bool pipe_fused = pipe && s2k::fwd_pipe_fused();
         if (!pipe_fused) CK(s2k::launch_dct_fwd(p, p->d_S, p->d_X, nf, 0, nrows, fmt, &pv));
         for (const OrderGroup& g : order_groups(p, 0, bw)) {
             if (p->variant == S2KIT_CUDA_FLY) CK(s2k::launch_table_gen(p, p->d_table, g.shift, g.lo, g.hi));
-            if (pipe_fused)
+            if (uni)
+                CK(s2k::launch_fwd_uni(p, p->d_table, g.shift, p->d_S, rc, ic, coef_stride, nf, g.lo, g.hi, fmt,
+                                       pv.lat_perm));
+            else if (pipe_fused)
                 CK(s2k::launch_fwd_pipe(p, p->d_table, g.shift, p->d_S, rc, ic, coef_stride, nf, g.lo, g.hi, fmt,
                                         pv.lat_perm));
             else if (pipe)

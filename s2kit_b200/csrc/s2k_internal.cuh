@@ -114,6 +114,9 @@ struct s2kit_cuda_plan {
     uint64_t* d_order_start = nullptr;
     s2k::BlockMeta* d_meta = nullptr;
     uint32_t* d_rt_start = nullptr;
+    // DMMA sub-items of the uniform-warp forward kernel (kernels_uni.cu), heaviest first per order
+    int* d_sub_off = nullptr;   // [bw + 1]
+    int* d_sub_list = nullptr;  // parity | row tile << 1 | pair << 12
     // table-generator work units (order, first degree)
     int* d_units = nullptr;  // pairs (m, l0)
     std::vector<int> h_units;
@@ -199,6 +202,11 @@ int table_unit_rows(int bw);
 bool fwd_pipe_supported(const s2kit_cuda_plan* p, int nfun, int data_format);
 cudaError_t launch_fwd_pipe(s2kit_cuda_plan* p, const double* table, uint64_t table_shift, const double* S, double* rco,
                             double* ico, long coef_stride, int nfun, int m_lo, int m_hi, int data_format, int lat_perm);
+
+// uniform-warp successor of the persistent kernel at bw = 256 (kernels_uni.cu); S2KIT_CUDA_UNI=0 falls back to k_fwd_pipe
+bool fwd_uni_supported(const s2kit_cuda_plan* p, int nfun, int data_format);
+cudaError_t launch_fwd_uni(s2kit_cuda_plan* p, const double* table, uint64_t table_shift, const double* S, double* rco,
+                           double* ico, long coef_stride, int nfun, int m_lo, int m_hi, int data_format, int lat_perm);
 
 bool fwd_pipe_fused();  // default: the DCT runs inside the persistent kernel; S2KIT_CUDA_PIPE=1: K2 + streamed K3
 // K3 as a persistent kernel with cp.async-streamed table tiles (kernels_pipe.cu); X = K2's cosine planes
