@@ -316,4 +316,278 @@ cudaError_t launch_fwd_uni(s2kit_cuda_plan* p, const double* table, uint64_t shi
     return e;
 }
 
+// =====================================================================================================================
+// The batched INVERSE path at bw = 256 as one persistent kernel: K4 + K5 fused.
+//
+//   transposed triangular contraction . scaling . DCT-III(2bw) . sin(theta) . (-1)^m . 1/sqrt(2 pi)
+//   (InvDLTSemi, src/legendre_transform/seminaive.c:56-115, inside the m-loops of InvFSTSemiMemo,
+//    src/FST_semi_memo.c:262-342)
+//
+// The cosine planes V never go through HBM (4.3 of the 9.7 GB the two separate kernels move per 1024 functions).  Per
+// work item (order m, 32 columns) the CTA alternates between two phases, all 16 warps in each:
+//   A  contraction: V[col, k] = sum_l c[col, l] T_m[l, k] on DMMA -- coefficient panel (A fragments) in shared memory,
+//      table tiles (B-fragment order) through the lane-private cp.async rings, sub-items = column tiles of one parity,
+//      alone where many row tiles reach them, in adjacent pairs (which share every coefficient fragment) otherwise,
+//      taken heaviest first from a shared-memory counter; results land in the V panel in shared memory;
+//   B  DCT-III: warp w turns panel columns 2w, 2w + 1 (real / imaginary part of one (function, +-m)) into a spectral-plane
+//      row pair with the one-warp FFT (exchange in place in those two columns) and writes it to G; meanwhile the
+//      coefficient panel of the NEXT item streams in with cp.async (the panel is idle during this phase).
+// Shared memory: coefficient panel + V panel + rings = 199 KB; a second V panel (to overlap the phases as the forward
+// kernel does) does not fit beside the coefficient panel.
+struct UniInvArgs {
+    const double* table;  // B-fragment-ordered tiles
+    const uint64_t* order_start;
+    uint64_t table_shift;
+    const int* sub_off;   // [bw + 1]
+    const int* sub_list;  // parity | column tile << 1 | pair << 12
+    const double* rco;
+    const double* ico;
+    long coef_stride;
+    double* G;            // spectral planes [f][part][order row][latitude slot]
+    const double* sinv;   // sines in the DCT's output order (s2k_host_reordered)
+    const double2* tw;
+    const double2* qtab;
+    int nfun, m_lo, norders, ncoltiles, real_fmt, lat_perm;
+};
+
+// One contraction sub-item: column tile ct (and, PAIR, ct + 1) of parity block mb over the row tiles that reach it.
+template <bool PAIR>
+__device__ __forceinline__ void uni_cols(const double* __restrict__ tblk, const BlockMeta& mb, int ct, const double* cp,
+                                         double (&acc0)[UNI_NC / 8][2], double (&acc1)[UNI_NC / 8][2], double2* ring) {
+    constexpr int NC = UNI_NC, CS = 132;
+    constexpr int STEPS = PAIR ? UNI_RING / 2 : UNI_RING;
+    const int rt_min = first_row_tile_reaching(mb, ct);
+    const int rt_min1 = PAIR ? first_row_tile_reaching(mb, ct + 1) : 0;  // >= rt_min: rows only grow
+    const int cnt = mb.nrt - rt_min;
+    if (cnt <= 0) return;
+    auto tile = [&](int rt) { return tblk + ((uint64_t)row_tile_start_of(mb, rt) + ct) * 64; };
+#pragma unroll
+    for (int u = 0; u < STEPS; ++u) {
+        if (u < cnt) {
+            const int rt = rt_min + u;
+            const double* t = tile(rt);
+            cp_async16(reinterpret_cast<double*>(ring + ((PAIR ? 2 * u : u) & (UNI_RING - 1)) * 32), t);
+            if (PAIR && rt >= rt_min1) cp_async16(reinterpret_cast<double*>(ring + ((2 * u + 1) & (UNI_RING - 1)) * 32), t + 64);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+#pragma unroll 1
+    for (int i = 0; i < cnt; ++i) {
+        const int rt = rt_min + i;
+        asm volatile("cp.async.wait_group %0;" ::"n"(STEPS - 1) : "memory");
+        double2* s0 = ring + ((PAIR ? 2 * i : i) & (UNI_RING - 1)) * 32;
+        double2* s1 = ring + ((2 * i + 1) & (UNI_RING - 1)) * 32;
+        const bool two = PAIR && rt >= rt_min1;
+        const double2 b0 = *s0;
+        double2 b1 = make_double2(0.0, 0.0);
+        if (two) b1 = *s1;
+        double av[NC / 8][2];
+#pragma unroll
+        for (int j = 0; j < NC / 8; ++j) {
+            av[j][0] = cp[j * 8 * CS + 8 * rt];
+            av[j][1] = cp[j * 8 * CS + 8 * rt + 4];
+        }
+#pragma unroll
+        for (int j = 0; j < NC / 8; ++j) dmma(acc0[j], av[j][0], b0.x);
+        if (two) {
+#pragma unroll
+            for (int j = 0; j < NC / 8; ++j) dmma(acc1[j], av[j][0], b1.x);
+        }
+#pragma unroll
+        for (int j = 0; j < NC / 8; ++j) dmma(acc0[j], av[j][1], b0.y);
+        if (two) {
+#pragma unroll
+            for (int j = 0; j < NC / 8; ++j) dmma(acc1[j], av[j][1], b1.y);
+        }
+        const int nx = i + STEPS;
+        if (nx < cnt) {
+            const int rn = rt_min + nx;
+            const double* t = tile(rn);
+            cp_async16(reinterpret_cast<double*>(s0), t);
+            if (PAIR && rn >= rt_min1) cp_async16(reinterpret_cast<double*>(s1), t + 64);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(UNI_THREADS, 1) k_inv_uni(const UniInvArgs a) {
+    constexpr int N = 512, B = 256, NC = UNI_NC, CS = 132, PS = NC * CS + 8, PANEL = 2 * PS, HALF = B / 2;
+    extern __shared__ __align__(16) double smem[];
+    double* Cp = smem;                                                       // coefficient panel [2][NC][CS]
+    double* Vp = smem + PANEL;                                               // cosine panel      [2][NC][CS]
+    double2* rings = reinterpret_cast<double2*>(smem + 2 * PANEL);           // [WARPS][RING][32]
+    int* ctr = reinterpret_cast<int*>(rings + UNI_WARPS * UNI_RING * 32);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q4 = lane & 3;
+    const int cols_per_fn = a.real_fmt ? 2 : 4, NF = NC / cols_per_fn;
+    const int nitems = a.norders * a.ncoltiles;
+    const int nk = (nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    double2* ring = rings + warp * UNI_RING * 32 + lane;
+    const double c_rest = 1.0 / sqrt(2.0 * (double)N);  // 0.5/sqrt(bw), seminaive.c:72
+    const double c_zero = 1.0 / sqrt((double)N);        // fcos[0] / sqrt(2 bw), seminaive.c:98
+    const double out_scale = 0.39894228040143267794;    // 1/sqrt(2 pi), FST_semi_memo.c:344
+
+    if (tid < 2) ctr[tid] = 0;
+
+    // coefficient panel of item `item`: column c = (function, sign, re / im), de-interleaved by the parity of l - m; rows
+    // beyond the order's degrees and dead columns are zero (they meet table padding, which must not see NaN garbage)
+    auto stage_coeffs = [&](int item) {
+        const int oi = item / a.ncoltiles, x = item - oi * a.ncoltiles;
+        const int m = a.m_lo + oi, f0 = x * NF;
+        const int cnt = B - m, h0 = (cnt + 1) / 2, h1 = cnt / 2;
+        const int base_pos = coef_base(m, B), base_neg = coef_base(-m, B);
+        for (int col = warp; col < NC; col += UNI_WARPS) {
+            const int fl = col / cols_per_fn, sub = col % cols_per_fn;
+            const int sgn = a.real_fmt ? 0 : (sub >> 1), part = sub & 1, f = f0 + fl;
+            double* d0 = Cp + col * CS;
+            double* d1 = d0 + PS;
+            if (f >= a.nfun || (sgn && m == 0)) {
+                for (int c = lane; c < CS; c += 32) d0[c] = d1[c] = 0.0;
+                continue;
+            }
+            const double* src = (part ? a.ico : a.rco) + (long)f * a.coef_stride + (sgn ? base_neg : base_pos);
+            for (int o = lane; o < cnt; o += 32) cp_async8(((o & 1) ? d1 : d0) + (o >> 1), src + o);
+            for (int c = h0 + lane; c < CS; c += 32) d0[c] = 0.0;
+            for (int c = h1 + lane; c < CS; c += 32) d1[c] = 0.0;
+        }
+    };
+
+    if (nk > 0) stage_coeffs(blockIdx.x);
+    cp_async_wait_all();
+    __syncthreads();
+
+#pragma unroll 1
+    for (int k = 0; k < nk; ++k) {
+        const int item = blockIdx.x + k * gridDim.x;
+        const int oi = item / a.ncoltiles, x = item - oi * a.ncoltiles;
+        const int m = a.m_lo + oi, f0 = x * NF;
+        const BlockMeta mb0 = block_meta_of(m, 0, B), mb1 = block_meta_of(m, 1, B);
+        if (warp == 1 && k + 1 < nk) {  // the next item's table tiles into L2
+            const int m2 = a.m_lo + (item + (int)gridDim.x) / a.ncoltiles;
+            if (m2 != m)
+                prefetch_order_l2(a.table + (a.order_start[m2] - a.table_shift) * 64, a.order_start[m2 + 1] - a.order_start[m2],
+                                  lane, 32, 1u << 20);
+        }
+        // ---------------------------------------------------------------------------------- phase A: contraction
+        const int nd = __ldg(a.sub_off + m + 1) - __ldg(a.sub_off + m);
+        const double* tord = a.table + (a.order_start[m] - a.table_shift) * 64 + lane * 2;
+        for (;;) {
+            int t = 0;
+            if (lane == 0) t = atomicAdd(&ctr[k & 1], 1);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            if (t >= nd) break;
+            const int code = __ldg(a.sub_list + __ldg(a.sub_off + m) + t);
+            const int p = code & 1, ct = (code >> 1) & 0x7ff, pair = code >> 12;
+            const BlockMeta mb = p ? mb1 : mb0;
+            const double* tblk = tord + (uint64_t)(p ? block_tiles_of(mb0) : 0u) * 64;
+            double acc0[NC / 8][2], acc1[NC / 8][2];
+#pragma unroll
+            for (int j = 0; j < NC / 8; ++j) acc0[j][0] = acc0[j][1] = acc1[j][0] = acc1[j][1] = 0.0;
+            const double* cp = Cp + p * PS + g * CS + q4;
+            if (pair)
+                uni_cols<true>(tblk, mb, ct, cp, acc0, acc1, ring);
+            else
+                uni_cols<false>(tblk, mb, ct, cp, acc0, acc1, ring);
+            // lane holds column 8j + g, cosine slots 8 (ct + h) + 2 q4 + {0, 1} of parity p (adjacent in the panel)
+            double* vp = Vp + p * PS + g * CS + 8 * ct + 2 * q4;
+#pragma unroll
+            for (int j = 0; j < NC / 8; ++j) {
+                *reinterpret_cast<double2*>(vp + j * 8 * CS) = make_double2(acc0[j][0], acc0[j][1]);
+                if (pair) *reinterpret_cast<double2*>(vp + j * 8 * CS + 8) = make_double2(acc1[j][0], acc1[j][1]);
+            }
+        }
+        __syncthreads();  // V panel complete, coefficient panel drained
+        if (tid == 0) ctr[k & 1] = 0, ctr[(k & 1) ^ 1] = 0;
+        // ---------------------------------------------------------------------------------- phase B: DCT-III
+        if (k + 1 < nk) stage_coeffs(item + gridDim.x);  // streams in while the transforms run
+        {
+            const int q = warp;  // pair index: panel columns 2q (real part), 2q + 1 (imaginary part)
+            const int fl = a.real_fmt ? q : (q >> 1), sgn = a.real_fmt ? 0 : (q & 1);
+            const int f = f0 + fl;
+            if (f < a.nfun && !(sgn && m == 0)) {
+                double* col0 = Vp + (2 * q) * CS;
+                const double* Va = col0;
+                const double* Vb = col0 + CS;
+                const double2 qb = __ldg(a.qtab + lane);
+                double xr[16], xi[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const int kk = f16_in_index(lane, e);
+                    // W[k] = e^{i pi k/2n} (Xa[k] - i Xa[n-k]) + i (same for b), X[k >= bw] = 0   (k_dct_inv)
+                    double wr = 0.0, wi = 0.0;
+                    if (kk != B) {
+                        const int src = kk < B ? kk : N - kk;
+                        const double sc = (src == 0) ? c_zero : c_rest;
+                        const int slot = (src & 1) * PS + (src >> 1);
+                        const double va = Va[slot] * sc, vb = Vb[slot] * sc;
+                        double qr, qi;
+                        f16_quarter_rot(qb.x, qb.y, e, qr, qi);
+                        const double ur = (kk < B) ? va : vb, ui = (kk < B) ? vb : -va;  // (a + ib) or -i (a + ib)
+                        wr = qr * ur - qi * ui;
+                        wi = qr * ui + qi * ur;
+                    }
+                    xr[e] = wi;  // swapped: inverse DFT through the forward transform
+                    xi[e] = wr;
+                }
+                d16_fft512_inplace(xr, xi, col0, PS, lane, a.tw);
+                const int mp = sgn ? N - m : m;
+                const double sign = (sgn && (m & 1)) ? -out_scale : out_scale;  // (-1)^m for negative orders
+                double* Gr = a.G + ((long)f * 2 * N + mp) * N;
+                double* Gi = Gr + (long)N * N;
+#pragma unroll
+                for (int o = 0; o < 16; ++o) {
+                    const int i = f16_out_index(lane, o);
+                    const double s = (m & 1) ? __ldg(a.sinv + i) * sign : sign;
+                    const int at = a.lat_perm ? i : ((i < B) ? 2 * i : 2 * (N - 1 - i) + 1);
+                    Gr[at] = xi[o] * s;  // Re z -> column a (real part)
+                    Gi[at] = xr[o] * s;  // Im z -> column b (imaginary part)
+                }
+            }
+        }
+        cp_async_wait_all();
+        __syncthreads();  // next coefficient panel landed, V panel free
+    }
+    (void)HALF;
+}
+
+bool inv_uni_supported(const s2kit_cuda_plan* p, int nfun, int data_format) {
+    if (!uni_enabled() || !p->fast || p->n != 512 || !p->d_isub_list) return false;
+    return nfun * (data_format == S2KIT_REAL ? 2 : 4) >= UNI_NC;
+}
+
+cudaError_t launch_inv_uni(s2kit_cuda_plan* p, const double* table_t, uint64_t shift, const double* rco, const double* ico,
+                           long coef_stride, double* G, int nfun, int m_lo, int m_hi, int data_format, int lat_perm) {
+    if (m_hi <= m_lo || nfun <= 0) return cudaSuccess;
+    UniInvArgs a;
+    a.table = table_t;
+    a.order_start = p->d_order_start;
+    a.table_shift = shift;
+    a.sub_off = p->d_isub_off;
+    a.sub_list = p->d_isub_list;
+    a.rco = rco;
+    a.ico = ico;
+    a.coef_stride = coef_stride;
+    a.G = G;
+    a.sinv = p->d_sv;
+    a.tw = p->d_tw_n;
+    a.qtab = p->d_q_n;
+    a.nfun = nfun;
+    a.m_lo = m_lo;
+    a.norders = m_hi - m_lo;
+    a.real_fmt = data_format == S2KIT_REAL;
+    const int NF = UNI_NC / (a.real_fmt ? 2 : 4);
+    a.ncoltiles = (nfun + NF - 1) / NF;
+    a.lat_perm = lat_perm;
+    constexpr int PANEL = 2 * (UNI_NC * 132 + 8);
+    const size_t smem = sizeof(double) * 2 * PANEL + sizeof(double2) * UNI_WARPS * UNI_RING * 32 + 16;
+    cudaError_t e = ensure_smem(reinterpret_cast<const void*>(k_inv_uni), smem);
+    if (e != cudaSuccess) return e;
+    const int nitems = a.norders * a.ncoltiles;
+    int slot = prof_begin(p, S2KIT_K_FUSED_INV);
+    k_inv_uni<<<nitems < p->sm_count ? nitems : p->sm_count, UNI_THREADS, smem, p->stream>>>(a);
+    e = cudaGetLastError();
+    prof_end(p, slot);
+    return e;
+}
+
 }  // namespace s2k

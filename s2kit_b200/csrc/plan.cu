@@ -195,6 +195,42 @@ static void build_subitems(s2kit_cuda_plan* p, std::vector<int>& off, std::vecto
     }
 }
 
+// The inverse kernel's list: per order the (parity, column tile) units, every column tile of the panel included (a tile
+// no row reaches still has to be zeroed), tiles many rows reach alone, the others in adjacent pairs.
+static void build_inv_subitems(s2kit_cuda_plan* p, std::vector<int>& off, std::vector<int>& list) {
+    const int bw = p->bw, nct = (((bw + 1) / 2) + 7) >> 3;
+    int cap = 16;
+    if (const char* e = getenv("S2KIT_CUDA_UNI_CAP")) cap = std::max(0, atoi(e));
+    off.assign(bw + 1, 0);
+    list.clear();
+    for (int m = 0; m < bw; ++m) {
+        std::vector<std::pair<int, int>> items;
+        for (int par = 0; par < 2; ++par) {
+            const s2k::BlockMeta& mb = p->h_meta[2 * m + par];
+            auto tiles = [&](int rt) { return (mb.len0 + std::min(8 * rt + 7, mb.rows - 1) + 7) >> 3; };
+            auto reach = [&](int ct) {  // row tiles that reach column tile ct (first_row_tile_reaching, s2k_legendre.cuh)
+                int rt_min = 0;
+                if (8 * ct >= mb.len0 + 7) rt_min = (8 * ct - mb.len0 - 7) / 8 + 1;
+                while (rt_min < mb.nrt && ct >= tiles(rt_min)) ++rt_min;
+                return std::max(0, mb.nrt - rt_min);
+            };
+            int ct = 0;
+            while (ct < nct) {
+                if (ct + 1 < nct && reach(ct) + reach(ct + 1) <= cap) {
+                    items.push_back({reach(ct) + reach(ct + 1), par | (ct << 1) | (1 << 12)});
+                    ct += 2;
+                } else {
+                    items.push_back({reach(ct), par | (ct << 1)});
+                    ct += 1;
+                }
+            }
+        }
+        std::stable_sort(items.begin(), items.end(), [](const std::pair<int, int>& x, const std::pair<int, int>& y) { return x.first > y.first; });
+        for (auto& it : items) list.push_back(it.second);
+        off[m + 1] = (int)list.size();
+    }
+}
+
 // Keep a Memo table that fits comfortably in L2 resident across launches: the batch streams hundreds of MB through
 // L2 between two uses of the same order's tiles (persisting-L2 access policy window on the plan's stream).
 static void apply_table_l2_policy(s2kit_cuda_plan* p) {
@@ -377,6 +413,9 @@ static int plan_build(s2kit_cuda_plan* p, int bw, int variant, int max_batch, in
         build_subitems(p, off, list);
         CK(upload(p->stream, &p->d_sub_off, off.data(), off.size()));
         CK(upload(p->stream, &p->d_sub_list, list.data(), list.size()));
+        build_inv_subitems(p, off, list);
+        CK(upload(p->stream, &p->d_isub_off, off.data(), off.size()));
+        CK(upload(p->stream, &p->d_isub_list, list.data(), list.size()));
     }
     CK(s2k::launch_rec_coeffs(p));
 
@@ -450,7 +489,7 @@ extern "C" int s2kit_cuda_plan_destroy(s2kit_cuda_plan* p) {
     // tables and constants of a clone belong to the plan it was cloned from
     void* shared[] = {p->d_wv, p->d_sv, p->d_weights, p->d_sin, p->d_tw_n, p->d_tw_b, p->d_q_n, p->d_q_b, p->d_nodes,
                       p->d_seeds, p->d_rec, p->d_meta, p->d_rt_start, p->d_order_start, p->d_units,
-                      p->d_sub_off,  p->d_sub_list};
+                      p->d_sub_off,  p->d_sub_list, p->d_isub_off, p->d_isub_list};
     void* own[] = {p->d_S, p->d_X, p->d_coef, p->d_coef2, p->d_filt, p->d_stage};
     if (!p->shares_tables)
         for (void* q : shared)
@@ -618,12 +657,17 @@ static int inv_fst_device(s2kit_cuda_plan* p, const double* rco, const double* i
         double* id = idata + (long)c0 * data_stride;
         s2k::PlaneView pv = s2k::default_view(p->n);
         pv.lat_perm = s2k::tma_planes_ok(p, nf);
+        // batched at bw = 256: contraction and DCT-III in one persistent kernel, the cosine planes stay in shared memory
+        const bool uni = s2k::inv_uni_supported(p, nf, fmt);
         for (const OrderGroup& g : order_groups(p, 0, bw)) {
             const double* tt = p->variant == S2KIT_CUDA_FLY ? p->d_table : p->d_table_t;
             if (p->variant == S2KIT_CUDA_FLY) CK(s2k::launch_table_gen(p, p->d_table, g.shift, g.lo, g.hi, 1));
-            CK(s2k::launch_legendre_inv(p, tt, g.shift, rc, ic, coef_stride, p->d_X, nf, g.lo, g.hi, fmt));
+            if (uni)
+                CK(s2k::launch_inv_uni(p, tt, g.shift, rc, ic, coef_stride, p->d_S, nf, g.lo, g.hi, fmt, pv.lat_perm));
+            else
+                CK(s2k::launch_legendre_inv(p, tt, g.shift, rc, ic, coef_stride, p->d_X, nf, g.lo, g.hi, fmt));
         }
-        CK(s2k::launch_dct_inv(p, p->d_X, p->d_S, nf, 0, nrows, fmt, &pv));
+        if (!uni) CK(s2k::launch_dct_inv(p, p->d_X, p->d_S, nf, 0, nrows, fmt, &pv));
         CK(s2k::launch_phi_fft_inv(p, p->d_S, rd, id, data_stride, nf, fmt, &pv));
     }
     return 0;

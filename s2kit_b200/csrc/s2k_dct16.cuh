@@ -70,18 +70,14 @@ __host__ __device__ inline void d16_separate(double ar, double ai, double br, do
 __host__ __device__ constexpr int d16_panel_slot(int kk, int ps) { return (kk & 1) * ps + (kk >> 1); }
 
 #ifdef __CUDACC__
-// The whole forward DCT pair for the calling warp.  On entry xr/xi[e] = weighted samples at reordered position
-// p = lane + 32 e (real / imaginary column).  col0: the warp's first panel column, parity-0 copy (the second column is CS
-// doubles further, the parity-1 copies ps doubles further).  On exit the first 256 cosine coefficients of both columns
-// are in the panel and the pad slots [128, CS) of the four column copies are zero.  Only __syncwarp inside.
-template <int CS>
-__device__ __forceinline__ void d16_dct2_pair_to_panel(double (&xr)[16], double (&xi)[16], double* col0, int ps, int lane,
-                                                       const double2* __restrict__ tw, const double2* __restrict__ qtab,
-                                                       double s_all) {
-    static_assert(2 * CS == 8 * 33, "the exchange fills the column pair exactly");
+// 512-point FFT of the calling warp with the register <-> shared-memory exchange done IN PLACE in the warp's own column
+// pair (col0: parity-0 copy, the parity-1 copy ps doubles further), real parts first, then imaginary parts.  Same
+// contract as f16_fft512_warp: register e holds x[lane + 32 e] on entry, register o holds X[f16_out_index(lane, o)] on
+// exit.  The column pair's previous contents must already be in registers (or dead); its contents afterwards are garbage.
+__device__ __forceinline__ void d16_fft512_inplace(double (&xr)[16], double (&xi)[16], double* col0, int ps, int lane,
+                                                   const double2* __restrict__ tw) {
     const double2 w1 = __ldg(tw + lane);
     f16_phase1(xr, xi, w1.x, w1.y);
-    // exchange, real parts then imaginary parts
     __syncwarp();
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1) col0[d16_ex_write(lane, k1, ps)] = xr[k1];
@@ -95,19 +91,30 @@ __device__ __forceinline__ void d16_dct2_pair_to_panel(double (&xr)[16], double 
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < 16; ++j) xi[j] = rd[2 * j];
-    __syncwarp();  // the column pair is free again: outputs may land
+    __syncwarp();  // the column pair is free again
     f16_dft16(xr, xi);
-    const int h = lane >> 4, k1 = lane & 15;
-    {
-        double pr[8], pi_[8];
+    const int h = lane >> 4;
+    double pr[8], pi_[8];
 #pragma unroll
-        for (int qi = 0; qi < 8; ++qi) {
-            const double sr = h ? xr[qi] : xr[8 + qi], si = h ? xi[qi] : xi[8 + qi];
-            pr[qi] = __shfl_xor_sync(0xffffffffu, sr, 16);
-            pi_[qi] = __shfl_xor_sync(0xffffffffu, si, 16);
-        }
-        f16_phase3(xr, xi, pr, pi_, h);
+    for (int qi = 0; qi < 8; ++qi) {
+        const double sr = h ? xr[qi] : xr[8 + qi], si = h ? xi[qi] : xi[8 + qi];
+        pr[qi] = __shfl_xor_sync(0xffffffffu, sr, 16);
+        pi_[qi] = __shfl_xor_sync(0xffffffffu, si, 16);
     }
+    f16_phase3(xr, xi, pr, pi_, h);
+}
+
+// The whole forward DCT pair for the calling warp.  On entry xr/xi[e] = weighted samples at reordered position
+// p = lane + 32 e (real / imaginary column).  col0: the warp's first panel column, parity-0 copy (the second column is CS
+// doubles further, the parity-1 copies ps doubles further).  On exit the first 256 cosine coefficients of both columns
+// are in the panel and the pad slots [128, CS) of the four column copies are zero.  Only __syncwarp inside.
+template <int CS>
+__device__ __forceinline__ void d16_dct2_pair_to_panel(double (&xr)[16], double (&xi)[16], double* col0, int ps, int lane,
+                                                       const double2* __restrict__ tw, const double2* __restrict__ qtab,
+                                                       double s_all) {
+    static_assert(2 * CS == 8 * 33, "the exchange fills the column pair exactly");
+    d16_fft512_inplace(xr, xi, col0, ps, lane, tw);
+    const int h = lane >> 4, k1 = lane & 15;
     // separation + write: output kk = k1 + 16 (qi + 8h) -> parity kk & 1 = k1 & 1, slot (k1 >> 1) + 8 qi + 64 h
     const double2 q0 = __ldg(qtab + k1 + 128 * h);
     double* out = col0 + (k1 & 1) * ps + (k1 >> 1) + 64 * h;

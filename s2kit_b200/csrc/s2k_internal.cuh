@@ -117,6 +117,8 @@ struct s2kit_cuda_plan {
     // DMMA sub-items of the uniform-warp forward kernel (kernels_uni.cu), heaviest first per order
     int* d_sub_off = nullptr;   // [bw + 1]
     int* d_sub_list = nullptr;  // parity | row tile << 1 | pair << 12
+    int* d_isub_off = nullptr;  // the inverse kernel's list: parity | column tile << 1 | pair << 12
+    int* d_isub_list = nullptr;
     // table-generator work units (order, first degree)
     int* d_units = nullptr;  // pairs (m, l0)
     std::vector<int> h_units;
@@ -207,6 +209,11 @@ cudaError_t launch_fwd_pipe(s2kit_cuda_plan* p, const double* table, uint64_t ta
 bool fwd_uni_supported(const s2kit_cuda_plan* p, int nfun, int data_format);
 cudaError_t launch_fwd_uni(s2kit_cuda_plan* p, const double* table, uint64_t table_shift, const double* S, double* rco,
                            double* ico, long coef_stride, int nfun, int m_lo, int m_hi, int data_format, int lat_perm);
+
+bool inv_uni_supported(const s2kit_cuda_plan* p, int nfun, int data_format);
+cudaError_t launch_inv_uni(s2kit_cuda_plan* p, const double* table_t, uint64_t table_shift, const double* rco,
+                           const double* ico, long coef_stride, double* G, int nfun, int m_lo, int m_hi, int data_format,
+                           int lat_perm);
 
 bool fwd_pipe_fused();  // default: the DCT runs inside the persistent kernel; S2KIT_CUDA_PIPE=1: K2 + streamed K3
 // K3 as a persistent kernel with cp.async-streamed table tiles (kernels_pipe.cu); X = K2's cosine planes
