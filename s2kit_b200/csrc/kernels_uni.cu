@@ -19,6 +19,15 @@
 // DCT and DMMA tasks alternate in the task order, so at any time about half of the warps issue DFMAs and half DMMAs:
 // the latency gaps of the FFT code are filled by DMMAs of other warps and the pipe stays busy.  One __syncthreads per
 // item separates the panel generations (two panel buffers).
+// What the first version's profile showed (profiles/r2_ncu_uni_summary.md: FP64 + DMMA pipes 46 % busy, 14 % of the warp
+// samples on the task counter and the dependent metadata loads behind it, 14 % on the DCT's global loads, 11 % at the
+// barrier) and what this version does about it:
+//   * a warp never leaves its SM sub-partition and every sub-partition has its own FP64 / DMMA pipe: the units of an
+//     order are split on the host into four queues of equal cost, one per sub-partition (plan.cu, lpt_queues);
+//   * all per-order metadata (queue offsets, unit codes, table offsets) is copied into shared memory once per CTA;
+//   * a warp takes its NEXT task from the counter before it starts the current one (and the first task of the next
+//     item before the barrier), so the atomic's latency is never waited for;
+//   * the spectral rows the DCT tasks will read are pulled into L2 two items ahead (cp.async.bulk.prefetch.L2).
 #include <stdlib.h>
 
 #include "s2k_dct16.cuh"
@@ -35,8 +44,9 @@ struct UniArgs {
     const double* table;
     const uint64_t* order_start;
     uint64_t table_shift;
-    const int* sub_off;    // [bw + 1] first sub-item of each order
-    const int* sub_list;   // packed sub-items: parity | row tile << 1 | pair << 12
+    const int* sub_off;               // [4 bw + 1]: queue s of order m = sub_list[sub_off[4m+s] .. sub_off[4m+s+1])
+    const unsigned short* sub_list;   // packed units: parity | row tile << 1 | pair << 12
+    int nlist;
     const double* S;       // spectral planes [f][part][order row][latitude slot]
     const double* weights; // 4bw, load order (s2k_host_reordered)
     const double2* tw;
@@ -46,6 +56,32 @@ struct UniArgs {
     long coef_stride;
     int nfun, m_lo, norders, ncoltiles, real_fmt, lat_perm;
 };
+
+// per-CTA copy of the per-order metadata (shared memory): queue offsets, unit codes, first tile of every order
+struct UniMeta {
+    const int* qoff;
+    const unsigned short* qlist;
+    const unsigned* ost;
+};
+template <int B>
+__device__ __forceinline__ UniMeta uni_stage_meta(void* at, const int* sub_off, const unsigned short* sub_list, int nlist,
+                                                  const uint64_t* order_start, uint64_t shift, int m_lo, int m_hi) {
+    int* qoff = reinterpret_cast<int*>(at);
+    unsigned* ost = reinterpret_cast<unsigned*>(qoff + 4 * B + 4);
+    unsigned short* qlist = reinterpret_cast<unsigned short*>(ost + B + 4);
+    for (int i = threadIdx.x; i <= 4 * B; i += blockDim.x) qoff[i] = sub_off[i];
+    for (int i = threadIdx.x; i <= B; i += blockDim.x)  // only the launch's orders are resident (Fly groups): clamp the rest
+        ost[i] = (i >= m_lo && i <= m_hi) ? (unsigned)(order_start[i] - shift) : 0u;
+    for (int i = threadIdx.x; i < nlist; i += blockDim.x) qlist[i] = sub_list[i];
+    UniMeta mt;
+    mt.qoff = qoff;
+    mt.qlist = qlist;
+    mt.ost = ost;
+    return mt;
+}
+__host__ __device__ constexpr size_t uni_meta_bytes(int B, int nlist) {
+    return sizeof(int) * (4 * B + 4) + sizeof(unsigned) * (B + 4) + sizeof(unsigned short) * ((nlist + 7) & ~7);
+}
 
 __device__ __forceinline__ void uni_item(const UniArgs& a, int t, int NF, int& m, int& f0) {
     const int oi = t / a.ncoltiles, x = t - oi * a.ncoltiles;
@@ -115,15 +151,18 @@ __global__ void __launch_bounds__(UNI_THREADS, 1) k_fwd_uni(const UniArgs a) {
     extern __shared__ __align__(16) double smem[];
     double* panels = smem;                                                  // [2][PANEL]
     double2* rings = reinterpret_cast<double2*>(smem + 2 * PANEL);          // [WARPS][RING][32]
-    int* ctr = reinterpret_cast<int*>(rings + UNI_WARPS * UNI_RING * 32);   // task counters of the two generations
+    int* ctr = reinterpret_cast<int*>(rings + UNI_WARPS * UNI_RING * 32);   // [3 generations][4 queues]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q4 = lane & 3;
+    const int sq = warp & 3;  // this warp's SM sub-partition = its task queue
     const int cols_per_fn = a.real_fmt ? 2 : 4, NF = NC / cols_per_fn;
     const int nitems = a.norders * a.ncoltiles;
     const int nk = (nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     double2* ring = rings + warp * UNI_RING * 32 + lane;
     const double s_all = 1.0 / sqrt(2.0 * (double)N);  // 1/sqrt(2*size), seminaive.c:174
 
-    if (tid < 2) ctr[tid] = 0;
+    if (tid < 12) ctr[tid] = 0;
+    const UniMeta mt = uni_stage_meta<B>(ctr + 16, a.sub_off, a.sub_list, a.nlist, a.order_start, a.table_shift, a.m_lo,
+                                         a.m_lo + a.norders);
     __syncthreads();
 
     // DCT task `q` of item `item`: panel columns 2q (real part) and 2q + 1 (imaginary part) of buffer `buf`
@@ -153,13 +192,24 @@ __global__ void __launch_bounds__(UNI_THREADS, 1) k_fwd_uni(const UniArgs a) {
         d16_dct2_pair_to_panel<CS>(xr, xi, col0, PS, lane, a.tw, a.qtab, s_all);
     };
 
-    // DMMA sub-item `idx` of the item (m, f0) whose panel is `Xs`
-    auto dmma_task = [&](int m, int f0, int idx, const double* Xs) {
-        const int code = __ldg(a.sub_list + __ldg(a.sub_off + m) + idx);
+    // the 32 spectral rows (16 pairs x re / im, 4 KiB each) the DCT tasks of `item` will read: into L2, one row per lane
+    auto prefetch_rows = [&](int item) {
+        int m, f0;
+        uni_item(a, item, NF, m, f0);
+        const int q = lane >> 1, part = lane & 1;
+        const int fl = a.real_fmt ? q : (q >> 1), sgn = a.real_fmt ? 0 : (q & 1);
+        const int f = f0 + fl;
+        if (f >= a.nfun || (sgn && m == 0)) return;
+        const double* row = a.S + (((long)f * 2 + part) * N + (sgn ? N - m : m)) * N;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(row), "r"(N * 8) : "memory");
+    };
+
+    // DMMA unit `code` of the item (m, f0) whose panel is `Xs`
+    auto dmma_task = [&](int m, int f0, int code, const double* Xs) {
         const int p = code & 1, rt1 = (code >> 1) & 0x7ff, pair = code >> 12;
         const BlockMeta mb0 = block_meta_of(m, 0, B);
         const BlockMeta mb = p ? block_meta_of(m, 1, B) : mb0;
-        const double* tblk = a.table + (a.order_start[m] - a.table_shift + (p ? block_tiles_of(mb0) : 0u)) * 64 + lane * 2;
+        const double* tblk = a.table + ((uint64_t)mt.ost[m] + (p ? block_tiles_of(mb0) : 0u)) * 64 + lane * 2;
         const double* xp = Xs + p * PS + g * CS + q4;
         const int ctn1 = tiles_in_row(mb, rt1);
         const bool skip1 = mb.len0 + min(8 * rt1 + 7, mb.rows - 1) - 8 * (ctn1 - 1) <= 4;
@@ -205,46 +255,40 @@ __global__ void __launch_bounds__(UNI_THREADS, 1) k_fwd_uni(const UniArgs a) {
         }
     };
 
-    // ---- prologue: the panel of this CTA's first item
+    // ---- prologue: the panel of this CTA's first item, one pair per warp; first task of item 0 taken ahead
+    int tn = 0;
     if (nk > 0) {
-        int m, f0;
-        uni_item(a, blockIdx.x, NF, m, f0);
-        if (warp == 0)
-            prefetch_order_l2(a.table + (a.order_start[m] - a.table_shift) * 64, a.order_start[m + 1] - a.order_start[m], lane, 32,
-                              1u << 20);
-        for (;;) {
-            int t = 0;
-            if (lane == 0) t = atomicAdd(&ctr[1], 1);
-            t = __shfl_sync(0xffffffffu, t, 0);
-            if (t >= NC / 2) break;
-            dct_task(blockIdx.x, t, panels);
+        if (warp == 0) {
+            const int m0 = a.m_lo + (int)blockIdx.x / a.ncoltiles;
+            prefetch_order_l2(a.table + (uint64_t)mt.ost[m0] * 64, a.order_start[m0 + 1] - a.order_start[m0], lane, 32, 1u << 20);
         }
+        if (warp == 2 && nk > 1) prefetch_rows(blockIdx.x + gridDim.x);
+        dct_task(blockIdx.x, 4 * sq + (warp >> 2), panels);
+        if (lane == 0) tn = atomicAdd(&ctr[sq], 1);
     }
     __syncthreads();
 
 #pragma unroll 1
     for (int k = 0; k < nk; ++k) {
-        const int item = blockIdx.x + k * gridDim.x, b = k & 1;
+        const int item = blockIdx.x + k * gridDim.x, b = k & 1, gen = k % 3;
         const bool has_next = k + 1 < nk;
         int m, f0;
         uni_item(a, item, NF, m, f0);
-        if (tid == 0) ctr[b ^ 1] = 0;  // counter of the next generation: idle since the barrier before last
-        if (warp == 1 && has_next) {    // the next item's table tiles into L2 ahead of its contraction
-            int m2, f2;
-            uni_item(a, item + gridDim.x, NF, m2, f2);
+        if (tid < 4) ctr[((k + 2) % 3) * 4 + tid] = 0;  // the generation after next: idle since the barrier before last
+        if (warp == 1 && has_next) {  // the next item's table tiles into L2 ahead of its contraction
+            const int m2 = a.m_lo + (item + (int)gridDim.x) / a.ncoltiles;
             if (m2 != m)
-                prefetch_order_l2(a.table + (a.order_start[m2] - a.table_shift) * 64, a.order_start[m2 + 1] - a.order_start[m2],
-                                  lane, 32, 1u << 20);
+                prefetch_order_l2(a.table + (uint64_t)mt.ost[m2] * 64, a.order_start[m2 + 1] - a.order_start[m2], lane, 32,
+                                  1u << 20);
         }
-        const int nd = __ldg(a.sub_off + m + 1) - __ldg(a.sub_off + m), nf = has_next ? NC / 2 : 0;
+        if (warp == 2 && k + 2 < nk) prefetch_rows(item + 2 * gridDim.x);  // read by the DCT tasks of the next iteration
+        const int qb = mt.qoff[4 * m + sq], nd = mt.qoff[4 * m + sq + 1] - qb, nf = has_next ? 4 : 0;
         const int mi = nf < nd ? nf : nd, ntask = nf + nd;
         const double* Xs = panels + b * PANEL;
         double* Xn = panels + (b ^ 1) * PANEL;
-        for (;;) {
-            int t = 0;
-            if (lane == 0) t = atomicAdd(&ctr[b], 1);
-            t = __shfl_sync(0xffffffffu, t, 0);
-            if (t >= ntask) break;
+        int t = __shfl_sync(0xffffffffu, tn, 0);
+        while (t < ntask) {
+            if (lane == 0) tn = atomicAdd(&ctr[gen * 4 + sq], 1);  // the task after this one: latency hidden behind it
             // DCT and DMMA tasks alternate while both kinds last
             bool is_dct;
             int idx;
@@ -259,10 +303,12 @@ __global__ void __launch_bounds__(UNI_THREADS, 1) k_fwd_uni(const UniArgs a) {
                 idx = t - nf;
             }
             if (is_dct)
-                dct_task(item + gridDim.x, idx, Xn);
+                dct_task(item + gridDim.x, 4 * sq + idx, Xn);
             else
-                dmma_task(m, f0, idx, Xs);
+                dmma_task(m, f0, mt.qlist[qb + idx], Xs);
+            t = __shfl_sync(0xffffffffu, tn, 0);
         }
+        if (has_next && lane == 0) tn = atomicAdd(&ctr[((k + 1) % 3) * 4 + sq], 1);  // first task of the next item
         __syncthreads();  // panel b is drained, panel b ^ 1 is complete
     }
 }
@@ -290,6 +336,7 @@ cudaError_t launch_fwd_uni(s2kit_cuda_plan* p, const double* table, uint64_t shi
     a.table_shift = shift;
     a.sub_off = p->d_sub_off;
     a.sub_list = p->d_sub_list;
+    a.nlist = p->n_sub_list;
     a.S = S;
     a.weights = p->d_wv;
     a.tw = p->d_tw_n;
@@ -305,7 +352,8 @@ cudaError_t launch_fwd_uni(s2kit_cuda_plan* p, const double* table, uint64_t shi
     a.ncoltiles = (nfun + NF - 1) / NF;
     a.lat_perm = lat_perm;
     constexpr int PANEL = 2 * (UNI_NC * 132 + 8);
-    const size_t smem = sizeof(double) * 2 * PANEL + sizeof(double2) * UNI_WARPS * UNI_RING * 32 + 16;
+    const size_t smem = sizeof(double) * 2 * PANEL + sizeof(double2) * UNI_WARPS * UNI_RING * 32 + 64 +
+                        uni_meta_bytes(256, p->n_sub_list);
     cudaError_t e = ensure_smem(reinterpret_cast<const void*>(k_fwd_uni), smem);
     if (e != cudaSuccess) return e;
     const int nitems = a.norders * a.ncoltiles;
@@ -338,8 +386,9 @@ struct UniInvArgs {
     const double* table;  // B-fragment-ordered tiles
     const uint64_t* order_start;
     uint64_t table_shift;
-    const int* sub_off;   // [bw + 1]
-    const int* sub_list;  // parity | column tile << 1 | pair << 12
+    const int* sub_off;              // [4 bw + 1], four queues per order
+    const unsigned short* sub_list;  // parity | column tile << 1 | pair << 12
+    int nlist;
     const double* rco;
     const double* ico;
     long coef_stride;
@@ -412,13 +461,14 @@ __device__ __forceinline__ void uni_cols(const double* __restrict__ tblk, const 
 }
 
 __global__ void __launch_bounds__(UNI_THREADS, 1) k_inv_uni(const UniInvArgs a) {
-    constexpr int N = 512, B = 256, NC = UNI_NC, CS = 132, PS = NC * CS + 8, PANEL = 2 * PS, HALF = B / 2;
+    constexpr int N = 512, B = 256, NC = UNI_NC, CS = 132, PS = NC * CS + 8, PANEL = 2 * PS;
     extern __shared__ __align__(16) double smem[];
     double* Cp = smem;                                                       // coefficient panel [2][NC][CS]
     double* Vp = smem + PANEL;                                               // cosine panel      [2][NC][CS]
     double2* rings = reinterpret_cast<double2*>(smem + 2 * PANEL);           // [WARPS][RING][32]
-    int* ctr = reinterpret_cast<int*>(rings + UNI_WARPS * UNI_RING * 32);
+    int* ctr = reinterpret_cast<int*>(rings + UNI_WARPS * UNI_RING * 32);    // [3 generations][4 queues]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q4 = lane & 3;
+    const int sq = warp & 3;
     const int cols_per_fn = a.real_fmt ? 2 : 4, NF = NC / cols_per_fn;
     const int nitems = a.norders * a.ncoltiles;
     const int nk = (nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -427,7 +477,9 @@ __global__ void __launch_bounds__(UNI_THREADS, 1) k_inv_uni(const UniInvArgs a) 
     const double c_zero = 1.0 / sqrt((double)N);        // fcos[0] / sqrt(2 bw), seminaive.c:98
     const double out_scale = 0.39894228040143267794;    // 1/sqrt(2 pi), FST_semi_memo.c:344
 
-    if (tid < 2) ctr[tid] = 0;
+    if (tid < 12) ctr[tid] = 0;
+    const UniMeta mt = uni_stage_meta<B>(ctr + 16, a.sub_off, a.sub_list, a.nlist, a.order_start, a.table_shift, a.m_lo,
+                                         a.m_lo + a.norders);
 
     // coefficient panel of item `item`: column c = (function, sign, re / im), de-interleaved by the parity of l - m; rows
     // beyond the order's degrees and dead columns are zero (they meet table padding, which must not see NaN garbage)
@@ -452,31 +504,40 @@ __global__ void __launch_bounds__(UNI_THREADS, 1) k_inv_uni(const UniInvArgs a) 
         }
     };
 
-    if (nk > 0) stage_coeffs(blockIdx.x);
+    int tn = 0;
+    if (nk > 0) {
+        stage_coeffs(blockIdx.x);
+        if (warp == 0) {
+            const int m0 = a.m_lo + (int)blockIdx.x / a.ncoltiles;
+            prefetch_order_l2(a.table + (a.order_start[m0] - a.table_shift) * 64, a.order_start[m0 + 1] - a.order_start[m0], lane,
+                              32, 1u << 20);
+        }
+    }
     cp_async_wait_all();
     __syncthreads();
+    if (nk > 0 && lane == 0) tn = atomicAdd(&ctr[sq], 1);
 
 #pragma unroll 1
     for (int k = 0; k < nk; ++k) {
-        const int item = blockIdx.x + k * gridDim.x;
+        const int item = blockIdx.x + k * gridDim.x, gen = k % 3;
+        const bool has_next = k + 1 < nk;
         const int oi = item / a.ncoltiles, x = item - oi * a.ncoltiles;
         const int m = a.m_lo + oi, f0 = x * NF;
         const BlockMeta mb0 = block_meta_of(m, 0, B), mb1 = block_meta_of(m, 1, B);
-        if (warp == 1 && k + 1 < nk) {  // the next item's table tiles into L2
+        if (tid < 4) ctr[((k + 2) % 3) * 4 + tid] = 0;
+        if (warp == 1 && has_next) {  // the next item's table tiles into L2
             const int m2 = a.m_lo + (item + (int)gridDim.x) / a.ncoltiles;
             if (m2 != m)
-                prefetch_order_l2(a.table + (a.order_start[m2] - a.table_shift) * 64, a.order_start[m2 + 1] - a.order_start[m2],
-                                  lane, 32, 1u << 20);
+                prefetch_order_l2(a.table + (uint64_t)mt.ost[m2] * 64, a.order_start[m2 + 1] - a.order_start[m2], lane, 32,
+                                  1u << 20);
         }
         // ---------------------------------------------------------------------------------- phase A: contraction
-        const int nd = __ldg(a.sub_off + m + 1) - __ldg(a.sub_off + m);
-        const double* tord = a.table + (a.order_start[m] - a.table_shift) * 64 + lane * 2;
-        for (;;) {
-            int t = 0;
-            if (lane == 0) t = atomicAdd(&ctr[k & 1], 1);
-            t = __shfl_sync(0xffffffffu, t, 0);
-            if (t >= nd) break;
-            const int code = __ldg(a.sub_list + __ldg(a.sub_off + m) + t);
+        const int qb = mt.qoff[4 * m + sq], nd = mt.qoff[4 * m + sq + 1] - qb;
+        const double* tord = a.table + (uint64_t)mt.ost[m] * 64 + lane * 2;
+        int t = __shfl_sync(0xffffffffu, tn, 0);
+        while (t < nd) {
+            if (lane == 0) tn = atomicAdd(&ctr[gen * 4 + sq], 1);
+            const int code = mt.qlist[qb + t];
             const int p = code & 1, ct = (code >> 1) & 0x7ff, pair = code >> 12;
             const BlockMeta mb = p ? mb1 : mb0;
             const double* tblk = tord + (uint64_t)(p ? block_tiles_of(mb0) : 0u) * 64;
@@ -495,11 +556,12 @@ __global__ void __launch_bounds__(UNI_THREADS, 1) k_inv_uni(const UniInvArgs a) 
                 *reinterpret_cast<double2*>(vp + j * 8 * CS) = make_double2(acc0[j][0], acc0[j][1]);
                 if (pair) *reinterpret_cast<double2*>(vp + j * 8 * CS + 8) = make_double2(acc1[j][0], acc1[j][1]);
             }
+            t = __shfl_sync(0xffffffffu, tn, 0);
         }
+        if (has_next && lane == 0) tn = atomicAdd(&ctr[((k + 1) % 3) * 4 + sq], 1);
         __syncthreads();  // V panel complete, coefficient panel drained
-        if (tid == 0) ctr[k & 1] = 0, ctr[(k & 1) ^ 1] = 0;
         // ---------------------------------------------------------------------------------- phase B: DCT-III
-        if (k + 1 < nk) stage_coeffs(item + gridDim.x);  // streams in while the transforms run
+        if (has_next) stage_coeffs(item + gridDim.x);  // streams in while the transforms run
         {
             const int q = warp;  // pair index: panel columns 2q (real part), 2q + 1 (imaginary part)
             const int fl = a.real_fmt ? q : (q >> 1), sgn = a.real_fmt ? 0 : (q & 1);
@@ -508,7 +570,7 @@ __global__ void __launch_bounds__(UNI_THREADS, 1) k_inv_uni(const UniInvArgs a) 
                 double* col0 = Vp + (2 * q) * CS;
                 const double* Va = col0;
                 const double* Vb = col0 + CS;
-                const double2 qb = __ldg(a.qtab + lane);
+                const double2 qb2 = __ldg(a.qtab + lane);
                 double xr[16], xi[16];
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
@@ -521,7 +583,7 @@ __global__ void __launch_bounds__(UNI_THREADS, 1) k_inv_uni(const UniInvArgs a) 
                         const int slot = (src & 1) * PS + (src >> 1);
                         const double va = Va[slot] * sc, vb = Vb[slot] * sc;
                         double qr, qi;
-                        f16_quarter_rot(qb.x, qb.y, e, qr, qi);
+                        f16_quarter_rot(qb2.x, qb2.y, e, qr, qi);
                         const double ur = (kk < B) ? va : vb, ui = (kk < B) ? vb : -va;  // (a + ib) or -i (a + ib)
                         wr = qr * ur - qi * ui;
                         wi = qr * ui + qi * ur;
@@ -547,7 +609,6 @@ __global__ void __launch_bounds__(UNI_THREADS, 1) k_inv_uni(const UniInvArgs a) 
         cp_async_wait_all();
         __syncthreads();  // next coefficient panel landed, V panel free
     }
-    (void)HALF;
 }
 
 bool inv_uni_supported(const s2kit_cuda_plan* p, int nfun, int data_format) {
@@ -564,6 +625,7 @@ cudaError_t launch_inv_uni(s2kit_cuda_plan* p, const double* table_t, uint64_t s
     a.table_shift = shift;
     a.sub_off = p->d_isub_off;
     a.sub_list = p->d_isub_list;
+    a.nlist = p->n_isub_list;
     a.rco = rco;
     a.ico = ico;
     a.coef_stride = coef_stride;
@@ -579,7 +641,8 @@ cudaError_t launch_inv_uni(s2kit_cuda_plan* p, const double* table_t, uint64_t s
     a.ncoltiles = (nfun + NF - 1) / NF;
     a.lat_perm = lat_perm;
     constexpr int PANEL = 2 * (UNI_NC * 132 + 8);
-    const size_t smem = sizeof(double) * 2 * PANEL + sizeof(double2) * UNI_WARPS * UNI_RING * 32 + 16;
+    const size_t smem = sizeof(double) * 2 * PANEL + sizeof(double2) * UNI_WARPS * UNI_RING * 32 + 64 +
+                        uni_meta_bytes(256, p->n_isub_list);
     cudaError_t e = ensure_smem(reinterpret_cast<const void*>(k_inv_uni), smem);
     if (e != cudaSuccess) return e;
     const int nitems = a.norders * a.ncoltiles;

@@ -165,16 +165,41 @@ static void build_layout(s2kit_cuda_plan* p, const std::vector<char>& owned) {
     p->h_unit_first[bw] = (int)p->h_units.size() / 2;
 }
 
-// Work list of the uniform-warp forward kernel (kernels_uni.cu): per order the (parity, row tile) units of the
-// contraction, long rows alone, short rows in adjacent pairs of at most `cap` column-tile steps, heaviest first.
-static void build_subitems(s2kit_cuda_plan* p, std::vector<int>& off, std::vector<int>& list) {
-    const int bw = p->bw;
+// Work lists of the uniform-warp kernels (kernels_uni.cu).  An SM sub-partition has its own FP64 / DMMA pipe and a warp
+// never leaves its sub-partition, so the units of one order are split into FOUR queues of equal cost (longest
+// processing time first into the lightest queue), one per sub-partition; the four warps of a sub-partition take their
+// queue's units heaviest first.  off[4 m + s] .. off[4 m + s + 1]: queue s of order m inside `list`.
+static void lpt_queues(std::vector<std::pair<int, int>>& items, std::vector<int>& off, std::vector<unsigned short>& list) {
+    std::stable_sort(items.begin(), items.end(),
+                     [](const std::pair<int, int>& x, const std::pair<int, int>& y) { return x.first > y.first; });
+    std::vector<unsigned short> q[4];
+    long load[4] = {0, 0, 0, 0};
+    for (auto& it : items) {
+        int best = 0;
+        for (int s = 1; s < 4; ++s)
+            if (load[s] < load[best]) best = s;
+        q[best].push_back((unsigned short)it.second);
+        load[best] += it.first + 1;  // + 1: a unit costs its set-up even when it has no tiles
+    }
+    for (int s = 0; s < 4; ++s) {
+        list.insert(list.end(), q[s].begin(), q[s].end());
+        off.push_back((int)list.size());
+    }
+}
+
+static int uni_cap() {
     int cap = 16;
     if (const char* e = getenv("S2KIT_CUDA_UNI_CAP")) cap = std::max(0, atoi(e));
-    off.assign(bw + 1, 0);
+    return cap;
+}
+
+// forward: (parity, row tile) units, long rows alone, short rows in adjacent pairs of at most `cap` column-tile steps
+static void build_subitems(s2kit_cuda_plan* p, std::vector<int>& off, std::vector<unsigned short>& list) {
+    const int bw = p->bw, cap = uni_cap();
+    off.assign(1, 0);
     list.clear();
     for (int m = 0; m < bw; ++m) {
-        std::vector<std::pair<int, int>> items;  // (cost, code)
+        std::vector<std::pair<int, int>> items;  // (cost, code = parity | row tile << 1 | pair << 12)
         for (int par = 0; par < 2; ++par) {
             const s2k::BlockMeta& mb = p->h_meta[2 * m + par];
             auto tiles = [&](int rt) { return (mb.len0 + std::min(8 * rt + 7, mb.rows - 1) + 7) >> 3; };
@@ -189,22 +214,18 @@ static void build_subitems(s2kit_cuda_plan* p, std::vector<int>& off, std::vecto
                 }
             }
         }
-        std::stable_sort(items.begin(), items.end(), [](const std::pair<int, int>& x, const std::pair<int, int>& y) { return x.first > y.first; });
-        for (auto& it : items) list.push_back(it.second);
-        off[m + 1] = (int)list.size();
+        lpt_queues(items, off, list);
     }
 }
 
-// The inverse kernel's list: per order the (parity, column tile) units, every column tile of the panel included (a tile
-// no row reaches still has to be zeroed), tiles many rows reach alone, the others in adjacent pairs.
-static void build_inv_subitems(s2kit_cuda_plan* p, std::vector<int>& off, std::vector<int>& list) {
-    const int bw = p->bw, nct = (((bw + 1) / 2) + 7) >> 3;
-    int cap = 16;
-    if (const char* e = getenv("S2KIT_CUDA_UNI_CAP")) cap = std::max(0, atoi(e));
-    off.assign(bw + 1, 0);
+// inverse: (parity, column tile) units, every column tile of the panel included (a tile no row reaches still has to be
+// zeroed), tiles many rows reach alone, the others in adjacent pairs
+static void build_inv_subitems(s2kit_cuda_plan* p, std::vector<int>& off, std::vector<unsigned short>& list) {
+    const int bw = p->bw, nct = (((bw + 1) / 2) + 7) >> 3, cap = uni_cap();
+    off.assign(1, 0);
     list.clear();
     for (int m = 0; m < bw; ++m) {
-        std::vector<std::pair<int, int>> items;
+        std::vector<std::pair<int, int>> items;  // code = parity | column tile << 1 | pair << 12
         for (int par = 0; par < 2; ++par) {
             const s2k::BlockMeta& mb = p->h_meta[2 * m + par];
             auto tiles = [&](int rt) { return (mb.len0 + std::min(8 * rt + 7, mb.rows - 1) + 7) >> 3; };
@@ -225,9 +246,7 @@ static void build_inv_subitems(s2kit_cuda_plan* p, std::vector<int>& off, std::v
                 }
             }
         }
-        std::stable_sort(items.begin(), items.end(), [](const std::pair<int, int>& x, const std::pair<int, int>& y) { return x.first > y.first; });
-        for (auto& it : items) list.push_back(it.second);
-        off[m + 1] = (int)list.size();
+        lpt_queues(items, off, list);
     }
 }
 
@@ -409,11 +428,14 @@ static int plan_build(s2kit_cuda_plan* p, int bw, int variant, int max_batch, in
     CK(upload(p->stream, &p->d_order_start, p->h_order_start.data(), p->h_order_start.size()));
     CK(upload(p->stream, &p->d_units, p->h_units.data(), p->h_units.size()));
     if (p->fast && p->n == 512 && nranks == 1) {
-        std::vector<int> off, list;
+        std::vector<int> off;
+        std::vector<unsigned short> list;
         build_subitems(p, off, list);
+        p->n_sub_list = (int)list.size();
         CK(upload(p->stream, &p->d_sub_off, off.data(), off.size()));
         CK(upload(p->stream, &p->d_sub_list, list.data(), list.size()));
         build_inv_subitems(p, off, list);
+        p->n_isub_list = (int)list.size();
         CK(upload(p->stream, &p->d_isub_off, off.data(), off.size()));
         CK(upload(p->stream, &p->d_isub_list, list.data(), list.size()));
     }

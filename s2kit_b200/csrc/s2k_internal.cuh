@@ -114,11 +114,13 @@ struct s2kit_cuda_plan {
     uint64_t* d_order_start = nullptr;
     s2k::BlockMeta* d_meta = nullptr;
     uint32_t* d_rt_start = nullptr;
-    // DMMA sub-items of the uniform-warp forward kernel (kernels_uni.cu), heaviest first per order
-    int* d_sub_off = nullptr;   // [bw + 1]
-    int* d_sub_list = nullptr;  // parity | row tile << 1 | pair << 12
-    int* d_isub_off = nullptr;  // the inverse kernel's list: parity | column tile << 1 | pair << 12
-    int* d_isub_list = nullptr;
+    // work lists of the uniform-warp kernels (kernels_uni.cu): four queues per order, heaviest unit first
+    int* d_sub_off = nullptr;              // [4 bw + 1]
+    unsigned short* d_sub_list = nullptr;  // forward: parity | row tile << 1 | pair << 12
+    int n_sub_list = 0;
+    int* d_isub_off = nullptr;
+    unsigned short* d_isub_list = nullptr;  // inverse: parity | column tile << 1 | pair << 12
+    int n_isub_list = 0;
     // table-generator work units (order, first degree)
     int* d_units = nullptr;  // pairs (m, l0)
     std::vector<int> h_units;
