@@ -83,6 +83,25 @@ __host__ __device__ constexpr size_t uni_meta_bytes(int B, int nlist) {
     return sizeof(int) * (4 * B + 4) + sizeof(unsigned) * (B + 4) + sizeof(unsigned short) * ((nlist + 7) & ~7);
 }
 
+// dependency counters in shared memory: release-increment by one lane after its warp's work (ordered by __syncwarp),
+// acquire-poll by every lane of a waiting warp
+__device__ __forceinline__ void uni_signal(int* ctr) {
+    asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(ctr)))
+                 : "memory");
+}
+__device__ __forceinline__ void uni_wait_ge(const int* ctr, int need) {
+    if (need <= 0) return;
+    const unsigned addr = static_cast<unsigned>(__cvta_generic_to_shared(ctr));
+    unsigned spins = 0;
+    for (;;) {
+        int v;
+        asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+        if (v >= need) return;
+        __nanosleep(32);
+        if (++spins > (1u << 24)) __trap();  // a lost signal must not hang the device
+    }
+}
+
 __device__ __forceinline__ void uni_item(const UniArgs& a, int t, int NF, int& m, int& f0) {
     const int oi = t / a.ncoltiles, x = t - oi * a.ncoltiles;
     m = a.m_lo + oi;
@@ -151,7 +170,8 @@ __global__ void __launch_bounds__(UNI_THREADS, 1) k_fwd_uni(const UniArgs a) {
     extern __shared__ __align__(16) double smem[];
     double* panels = smem;                                                  // [2][PANEL]
     double2* rings = reinterpret_cast<double2*>(smem + 2 * PANEL);          // [WARPS][RING][32]
-    int* ctr = reinterpret_cast<int*>(rings + UNI_WARPS * UNI_RING * 32);   // [3 generations][4 queues]
+    int* tick = reinterpret_cast<int*>(rings + UNI_WARPS * UNI_RING * 32);  // [4] ticket counters of the task queues
+    int* done = tick + 4;  // [0..1] dct_done, [2..3] dmma_done, per panel-buffer parity
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q4 = lane & 3;
     const int sq = warp & 3;  // this warp's SM sub-partition = its task queue
     const int cols_per_fn = a.real_fmt ? 2 : 4, NF = NC / cols_per_fn;
@@ -160,10 +180,14 @@ __global__ void __launch_bounds__(UNI_THREADS, 1) k_fwd_uni(const UniArgs a) {
     double2* ring = rings + warp * UNI_RING * 32 + lane;
     const double s_all = 1.0 / sqrt(2.0 * (double)N);  // 1/sqrt(2*size), seminaive.c:174
 
-    if (tid < 12) ctr[tid] = 0;
-    const UniMeta mt = uni_stage_meta<B>(ctr + 16, a.sub_off, a.sub_list, a.nlist, a.order_start, a.table_shift, a.m_lo,
+    if (tid < 8) tick[tid] = 0;
+    const UniMeta mt = uni_stage_meta<B>(tick + 16, a.sub_off, a.sub_list, a.nlist, a.order_start, a.table_shift, a.m_lo,
                                          a.m_lo + a.norders);
-    __syncthreads();
+    __syncthreads();  // the only CTA-wide barrier
+    if (warp == 0 && nk > 0) {
+        const int m0 = a.m_lo + (int)blockIdx.x / a.ncoltiles;
+        prefetch_order_l2(a.table + (uint64_t)mt.ost[m0] * 64, a.order_start[m0 + 1] - a.order_start[m0], lane, 32, 1u << 20);
+    }
 
     // DCT task `q` of item `item`: panel columns 2q (real part) and 2q + 1 (imaginary part) of buffer `buf`
     auto dct_task = [&](int item, int q, double* buf) {
@@ -255,61 +279,69 @@ __global__ void __launch_bounds__(UNI_THREADS, 1) k_fwd_uni(const UniArgs a) {
         }
     };
 
-    // ---- prologue: the panel of this CTA's first item, one pair per warp; first task of item 0 taken ahead
+    // ---- the task streams.  Queue sq hands out tickets; ticket numbers map to (stream, task): stream -1 = the four DCT
+    // tasks of item 0, stream k >= 0 = the DCT tasks of item k + 1 interleaved with the DMMA units of item k.  There is no
+    // CTA-wide barrier: a task waits only for what it depends on --
+    //   DMMA unit of item k      : the 16 DCT tasks of item k          (dct_done[k & 1] >= 16 (k / 2 + 1))
+    //   DCT task of item k + 1   : every DMMA unit of item k - 1, the last reader of that panel buffer
+    //                                                                   (dmma_done[(k - 1) & 1] >= units of its parity so far)
+    // -- so warps flow from item to item and a slow task delays only its dependants.  Counters are per buffer parity:
+    // items of one parity are strictly ordered by these two rules, items of different parity may overlap.
+    int k = -1, base = 0, nd = 0, nf = nk > 0 ? 4 : 0, ntask = nf, mi = 0, qb = 0, m = 0, f0 = 0;
+    int cum[2] = {0, 0};  // DMMA units of the items of each parity up to the current stream
     int tn = 0;
-    if (nk > 0) {
-        if (warp == 0) {
-            const int m0 = a.m_lo + (int)blockIdx.x / a.ncoltiles;
-            prefetch_order_l2(a.table + (uint64_t)mt.ost[m0] * 64, a.order_start[m0 + 1] - a.order_start[m0], lane, 32, 1u << 20);
-        }
-        if (warp == 2 && nk > 1) prefetch_rows(blockIdx.x + gridDim.x);
-        dct_task(blockIdx.x, 4 * sq + (warp >> 2), panels);
-        if (lane == 0) tn = atomicAdd(&ctr[sq], 1);
-    }
-    __syncthreads();
-
+    if (lane == 0) tn = atomicAdd(&tick[sq], 1);
 #pragma unroll 1
-    for (int k = 0; k < nk; ++k) {
-        const int item = blockIdx.x + k * gridDim.x, b = k & 1, gen = k % 3;
-        const bool has_next = k + 1 < nk;
-        int m, f0;
-        uni_item(a, item, NF, m, f0);
-        if (tid < 4) ctr[((k + 2) % 3) * 4 + tid] = 0;  // the generation after next: idle since the barrier before last
-        if (warp == 1 && has_next) {  // the next item's table tiles into L2 ahead of its contraction
-            const int m2 = a.m_lo + (item + (int)gridDim.x) / a.ncoltiles;
-            if (m2 != m)
-                prefetch_order_l2(a.table + (uint64_t)mt.ost[m2] * 64, a.order_start[m2 + 1] - a.order_start[m2], lane, 32,
-                                  1u << 20);
+    for (;;) {
+        const int t_abs = __shfl_sync(0xffffffffu, tn, 0);
+        while (t_abs >= base + ntask) {  // the ticket belongs to a later stream
+            base += ntask;
+            if (++k >= nk) break;
+            uni_item(a, (int)blockIdx.x + k * (int)gridDim.x, NF, m, f0);
+            qb = mt.qoff[4 * m + sq];
+            nd = mt.qoff[4 * m + sq + 1] - qb;
+            nf = (k + 1 < nk) ? 4 : 0;
+            ntask = nd + nf;
+            mi = nf < nd ? nf : nd;
+            cum[k & 1] += mt.qoff[4 * m + 4] - mt.qoff[4 * m];
         }
-        if (warp == 2 && k + 2 < nk) prefetch_rows(item + 2 * gridDim.x);  // read by the DCT tasks of the next iteration
-        const int qb = mt.qoff[4 * m + sq], nd = mt.qoff[4 * m + sq + 1] - qb, nf = has_next ? 4 : 0;
-        const int mi = nf < nd ? nf : nd, ntask = nf + nd;
-        const double* Xs = panels + b * PANEL;
-        double* Xn = panels + (b ^ 1) * PANEL;
-        int t = __shfl_sync(0xffffffffu, tn, 0);
-        while (t < ntask) {
-            if (lane == 0) tn = atomicAdd(&ctr[gen * 4 + sq], 1);  // the task after this one: latency hidden behind it
-            // DCT and DMMA tasks alternate while both kinds last
-            bool is_dct;
-            int idx;
-            if (t < 2 * mi) {
-                is_dct = !(t & 1);
-                idx = t >> 1;
-            } else if (nf > nd) {
-                is_dct = true;
-                idx = t - nd;
-            } else {
-                is_dct = false;
-                idx = t - nf;
+        if (k >= nk) break;
+        if (lane == 0) tn = atomicAdd(&tick[sq], 1);  // the task after this one: its latency hides behind this task
+        const int t = t_abs - base;
+        bool is_dct;
+        int idx;
+        if (t < 2 * mi) {  // DCT and DMMA tasks alternate while both kinds last
+            is_dct = !(t & 1);
+            idx = t >> 1;
+        } else if (nf > nd) {
+            is_dct = true;
+            idx = t - nd;
+        } else {
+            is_dct = false;
+            idx = t - nf;
+        }
+        const int item = (int)blockIdx.x + k * (int)gridDim.x;  // (k = -1: only DCT tasks, of item 0)
+        if (sq == 0 && t == 0 && k >= 0) {  // once per item: pull what the coming streams read into L2
+            if (k + 1 < nk) {
+                const int m2 = a.m_lo + (item + (int)gridDim.x) / a.ncoltiles;
+                if (m2 != m)
+                    prefetch_order_l2(a.table + (uint64_t)mt.ost[m2] * 64, a.order_start[m2 + 1] - a.order_start[m2], lane, 32,
+                                      1u << 20);
             }
-            if (is_dct)
-                dct_task(item + gridDim.x, 4 * sq + idx, Xn);
-            else
-                dmma_task(m, f0, mt.qlist[qb + idx], Xs);
-            t = __shfl_sync(0xffffffffu, tn, 0);
+            if (k + 2 < nk) prefetch_rows(item + 2 * (int)gridDim.x);
         }
-        if (has_next && lane == 0) tn = atomicAdd(&ctr[((k + 1) % 3) * 4 + sq], 1);  // first task of the next item
-        __syncthreads();  // panel b is drained, panel b ^ 1 is complete
+        if (is_dct) {
+            uni_wait_ge(&done[2 + ((k + 1) & 1)], cum[(k + 1) & 1]);  // dmma_done of the buffer's previous readers
+            dct_task(item + (int)gridDim.x, 4 * sq + idx, panels + ((k + 1) & 1) * PANEL);
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) uni_signal(&done[(k + 1) & 1]);
+        } else {
+            uni_wait_ge(&done[k & 1], 16 * (k / 2 + 1));  // dct_done: the item's panel is complete
+            dmma_task(m, f0, mt.qlist[qb + idx], panels + (k & 1) * PANEL);
+            __syncwarp();
+            if (lane == 0) uni_signal(&done[2 + (k & 1)]);
+        }
     }
 }
 
