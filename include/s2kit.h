@@ -1,11 +1,23 @@
 /*
  * s2kit.h -- S2kit's public C API, as exported by libs2kit_cuda.so (drop-in boundary).
  *
- * One header for the prototypes the reference spreads over include/s2kit/*.h; each block cites the
+ * One header for the prototypes the reference spreads over the files of include/s2kit/ (the same file names exist
+ * here as forwarding headers); each block cites the
  * declaration it replaces.  Names, argument order and meaning are the reference's; the parameters are named
  * here (the reference leaves them anonymous) and extern "C" guards are added.  Where FFTW's header is not
  * available, `fftw_plan` is declared as an opaque pointer: the GPU engine accepts and ignores the plan
  * arguments.
+ *
+ * Differences from the reference a caller can observe:
+ *  - bandwidths 2 .. 2048 (any value; powers of two >= 16 run on the radix-FFT kernels, others on direct O(n^2)
+ *    kernels); bw > 2048 is refused: the void entry points print the reason and abort(), there is no CPU fallback;
+ *  - every order uses the seminaive algorithm, `cutoff` is accepted and ignored;
+ *  - Transpose_RowSize / TransposeCosPmlTable agree with the reference for every even bw; for odd bw the reference's
+ *    row sizes do not add up to TableSize (its odd-bw inverse is wrong, cospml.c:270-288) -- here they do, and the
+ *    inverse transform is the exact transpose of the forward one;
+ *  - at bw = 2048 the orders |m| >= 2044, where the reference returns NaN (pmm.c:22-30), are finite;
+ *  - the entry points may be called from several host threads at once (each call checks a private context out of a
+ *    per-bandwidth cache); FSTSemiMemo / InvFSTSemiMemo use several GPUs for one field when S2KIT_CUDA_NGPU > 1.
  */
 #ifndef S2KIT_H
 #define S2KIT_H

@@ -1,0 +1,3 @@
+/* s2kit/pmm.h -- forwarding header: callers of the reference include "s2kit/pmm.h" (reference
+ * include/s2kit/pmm.h); every prototype of the drop-in library lives in ../s2kit.h. */
+#include "../s2kit.h"

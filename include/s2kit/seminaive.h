@@ -1,0 +1,3 @@
+/* s2kit/seminaive.h -- forwarding header: callers of the reference include "s2kit/seminaive.h" (reference
+ * include/s2kit/seminaive.h); every prototype of the drop-in library lives in ../s2kit.h. */
+#include "../s2kit.h"

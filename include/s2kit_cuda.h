@@ -72,8 +72,11 @@ void* s2kit_cuda_plan_stream(s2kit_cuda_plan* plan);
 int s2kit_cuda_synchronize(s2kit_cuda_plan* plan);
 
 int s2kit_cuda_plan_bw(const s2kit_cuda_plan* plan);
-/* bytes of device memory held by the cosine tables (tile-padded private layout) */
+/* bytes of device memory held by the cosine tables (tile-padded private layout): one copy at bw >= 512, a second,
+ * tile-transposed copy for the wide batched inverse kernels below that */
 size_t s2kit_cuda_plan_table_bytes(const s2kit_cuda_plan* plan);
+/* table bytes ONE transform of a Memo plan reads (a single copy of the plan's tiles) */
+size_t s2kit_cuda_plan_table_stream_bytes(const s2kit_cuda_plan* plan);
 
 /* ---- transforms (replace FSTSemiMemo/Fly, InvFSTSemiMemo/Fly, FZTSemiMemo/Fly, ConvOn2SphereSemiMemo/Fly) */
 

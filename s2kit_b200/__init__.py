@@ -68,6 +68,8 @@ def lib():
     L.s2kit_cuda_plan_bw.argtypes = [vp]
     L.s2kit_cuda_plan_table_bytes.restype = cs
     L.s2kit_cuda_plan_table_bytes.argtypes = [vp]
+    L.s2kit_cuda_plan_table_stream_bytes.restype = cs
+    L.s2kit_cuda_plan_table_stream_bytes.argtypes = [vp]
     L.s2kit_cuda_fst.argtypes = [vp, vp, vp, vp, vp, ci, cl, cl, ci, ci]
     L.s2kit_cuda_inv_fst.argtypes = [vp, vp, vp, vp, vp, ci, cl, cl, ci, ci]
     L.s2kit_cuda_fzt.argtypes = [vp, vp, vp, vp, vp, ci, cl, cl, ci, ci]
@@ -177,6 +179,10 @@ class Plan:
 
     def table_bytes(self):
         return lib().s2kit_cuda_plan_table_bytes(self.h)
+
+    def table_stream_bytes(self):
+        """Table bytes one transform reads (one copy of the tiles)."""
+        return lib().s2kit_cuda_plan_table_stream_bytes(self.h)
 
     def profile(self, on=True):
         _check(lib().s2kit_cuda_profile_enable(self.h, 1 if on else 0), "profile_enable")
@@ -314,6 +320,9 @@ class ShardedPlan:
 
     def table_bytes(self):
         return lib().s2kit_cuda_plan_table_bytes(self.h)
+
+    def table_stream_bytes(self):
+        return lib().s2kit_cuda_plan_table_stream_bytes(self.h)
 
     def fst_rings(self, rdata, idata, sendbuf):
         _check(lib().s2kit_cuda_fst_rings(self.h, rdata.data_ptr(), idata.data_ptr(), sendbuf.data_ptr()), "fst_rings")

@@ -11,7 +11,9 @@
 // from L2/HBM straight into mma.sync.m8n8k4.f64 A fragments with one coalesced 128-bit load per lane and
 // tile, never touching shared memory; the X (or coefficient) panel of the CTA's columns sits in shared
 // memory for the whole order.  The inverse reads the SAME tiles as B fragments (4 rows x 8 columns), so
-// no transposed table is stored (the reference keeps one: cospml.c:301-362).
+// Memo plans at bw >= 512 store ONE table copy (the inverse gathers its B fragments from the A-order tiles with two 8-byte
+// copies per lane); smaller bandwidths also keep a tile-transposed copy for the wide batched kernels, 26 MB at bw = 256
+// (the reference always keeps a transposed table: cospml.c:301-362).
 #include <stdlib.h>
 
 #include "s2k_legendre.cuh"
@@ -57,7 +59,7 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, NC >= 32 ? 2 : 3) k_legendre_f
     const double* __restrict__ table, const uint64_t* __restrict__ order_start, uint64_t table_shift,
     const BlockMeta* __restrict__ meta, const uint32_t* __restrict__ rt_start, const double* __restrict__ X,
     double* __restrict__ rco, double* __restrict__ ico, long coef_stride, int bw, int nfun, int m_lo, int real_fmt,
-    const int* __restrict__ order_list, unsigned l2pf_cap) {
+    const int* __restrict__ order_list, unsigned l2pf_cap, int tma_tables) {
     extern __shared__ double smem[];
     const int n = 2 * bw, CS = panel_stride(bw);
     const int m = order_list ? order_list[blockIdx.y] : m_lo + blockIdx.y;
@@ -107,6 +109,15 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, NC >= 32 ? 2 : 3) k_legendre_f
     ColOut* cinfo = reinterpret_cast<ColOut*>(srt + ((bw / 8 + 8 + 3) & ~3));
     // narrow panels: lane-private table-tile ring [LEG_WARPS][LEG_RING][32] behind the column table (s2k_legendre.cuh)
     double2* ring = reinterpret_cast<double2*>(cinfo + NC) + (warp * LEG_RING * 32 + lane);
+    // TMA-staged tiles (narrow panels): BULK_NS mbarriers per warp behind the rings
+    const unsigned bar = static_cast<unsigned>(__cvta_generic_to_shared(reinterpret_cast<double2*>(cinfo + NC) +
+                                                                        LEG_WARPS * LEG_RING * 32)) + warp * BULK_NS * 8;
+    unsigned phases = 0;
+    if (NC < 32 && tma_tables && lane == 0) {
+        for (int s = 0; s < BULK_NS; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar + 8 * s) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     if (NC < 32 && tid < NC) {
         // where column `tid` of the panel lands: f^(+-m, l) of function f, re or im array, with its sign
         ColOut co = {nullptr, nullptr, 1.0, 1.0};
@@ -206,11 +217,20 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, NC >= 32 ? 2 : 3) k_legendre_f
             double acc0[NC / 8][2], acc1[NC / 8][2];
     #pragma unroll
             for (int j = 0; j < NC / 8; ++j) acc0[j][0] = acc0[j][1] = acc1[j][0] = acc1[j][1] = 0.0;
-            fwd_row_tile_async<NC>(tbase + (uint64_t)srt[rt] * 64, Xs + gsel * CS + q4, CS, tiles_in_row(mb0, rt), acc0,
-                                   PC < NC && g >= PC, ring);
-            if (rt < mb1.nrt)
-                fwd_row_tile_async<NC>(tbase + (uint64_t)srt[mb0.nrt + rt] * 64, Xs + (PC + gsel) * CS + q4, CS,
-                                       tiles_in_row(mb1, rt), acc1, PC < NC && g >= PC, ring);
+            if (tma_tables) {
+                double2* wring = ring - lane;
+                fwd_row_tile_bulk<NC>(tbase - lane * 2 + (uint64_t)srt[rt] * 64, Xs + gsel * CS + q4, CS, tiles_in_row(mb0, rt),
+                                      acc0, PC < NC && g >= PC, wring, bar, phases, lane);
+                if (rt < mb1.nrt)
+                    fwd_row_tile_bulk<NC>(tbase - lane * 2 + (uint64_t)srt[mb0.nrt + rt] * 64, Xs + (PC + gsel) * CS + q4, CS,
+                                          tiles_in_row(mb1, rt), acc1, PC < NC && g >= PC, wring, bar, phases, lane);
+            } else {
+                fwd_row_tile_async<NC>(tbase + (uint64_t)srt[rt] * 64, Xs + gsel * CS + q4, CS, tiles_in_row(mb0, rt), acc0,
+                                       PC < NC && g >= PC, ring);
+                if (rt < mb1.nrt)
+                    fwd_row_tile_async<NC>(tbase + (uint64_t)srt[mb0.nrt + rt] * 64, Xs + (PC + gsel) * CS + q4, CS,
+                                           tiles_in_row(mb1, rt), acc1, PC < NC && g >= PC, ring);
+            }
 
             // ---- epilogue: lane holds row r = 8rt + g of both parities = degrees l - m = 2r, 2r+1, columns 8j + 2 q4 + {0,1}
             const int r = 8 * rt + g;
@@ -239,7 +259,7 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_inv(
     const double* __restrict__ table, const uint64_t* __restrict__ order_start, uint64_t table_shift,
     const BlockMeta* __restrict__ meta, const uint32_t* __restrict__ rt_start, const double* __restrict__ rco,
     const double* __restrict__ ico, long coef_stride, double* __restrict__ V, int bw, int nfun, int m_lo,
-    int real_fmt, const int* __restrict__ order_list, unsigned l2pf_cap) {
+    int real_fmt, const int* __restrict__ order_list, unsigned l2pf_cap, int a_order) {
     extern __shared__ double smem[];
     const int n = 2 * bw, CS = panel_stride(bw);
     const int m = order_list ? order_list[blockIdx.y] : m_lo + blockIdx.y;
@@ -335,8 +355,9 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_inv(
         double acc[NC / 8][2];
 #pragma unroll
         for (int j = 0; j < NC / 8; ++j) acc[j][0] = acc[j][1] = 0.0;
-        inv_col_tile_async<NC>(tbase, srt + (p ? mb0.nrt : 0), mb, ct,
-                               Cs + (p * PC + (PC < NC ? (g & (PC - 1)) : g)) * CS + q4, CS, acc, PC < NC && g >= PC, ring);
+        inv_col_tile_async<NC>(tbase - lane * 2, srt + (p ? mb0.nrt : 0), mb, ct,
+                               Cs + (p * PC + (PC < NC ? (g & (PC - 1)) : g)) * CS + q4, CS, acc, PC < NC && g >= PC, ring,
+                               a_order, lane);
         // ---- epilogue: lane holds column 8j + g, cosine slots c = 8ct + 2 q4 + {0,1}
         // slots c0, c0+1 of parity p are adjacent in the parity-split plane
         const int c0 = 8 * ct + 2 * q4, hp = p ? bw / 2 : (bw + 1) / 2;
@@ -377,15 +398,22 @@ static cudaError_t leg_fwd_nc(s2kit_cuda_plan* p, const double* table, uint64_t 
     int cols_per_fn = real_fmt ? 2 : 4;
     int NF = PC / cols_per_fn;
     size_t smem = sizeof(double) * 2 * PC * panel_stride(p->bw) + sizeof(uint32_t) * ((p->bw / 8 + 8 + 3) & ~3) +
-                  sizeof(ColOut) * NC + (NC < 32 ? sizeof(double2) * LEG_WARPS * LEG_RING * 32 : 0);
+                  sizeof(ColOut) * NC + (NC < 32 ? sizeof(double2) * LEG_WARPS * LEG_RING * 32 + 8 * LEG_WARPS * BULK_NS : 0);
     if (smem > 48 * 1024) {
         cudaError_t e = ensure_smem(reinterpret_cast<const void*>(k_legendre_fwd<NC, PC>), smem);
         if (e != cudaSuccess) return e;
     }
+    // narrow panels (single fields stream every tile once): table tiles staged by the TMA; S2KIT_CUDA_TMA_TABLES=0 keeps
+    // the lane-private cp.async ring
+    static const int tma_tables = [] {
+        const char* e = getenv("S2KIT_CUDA_TMA_TABLES");
+        return (e && e[0] == '0') ? 0 : 1;
+    }();
     dim3 grid((nfun + NF - 1) / NF, m_hi - m_lo, rowsplit);
     k_legendre_fwd<NC, PC><<<grid, LEG_WARPS * 32, smem, p->stream>>>(table, p->d_order_start, shift, p->d_meta,
                                                                   p->d_rt_start, X, rco, ico, coef_stride, p->bw, nfun,
-                                                                  m_lo, real_fmt, order_list, l2_prefetch_cap(PC));
+                                                                  m_lo, real_fmt, order_list, l2_prefetch_cap(PC),
+                                                                  NC < 32 ? tma_tables : 0);
     return cudaGetLastError();
 }
 
@@ -404,7 +432,8 @@ static cudaError_t leg_inv_nc(s2kit_cuda_plan* p, const double* table, uint64_t 
     dim3 grid((nfun + NF - 1) / NF, m_hi - m_lo, rowsplit);
     k_legendre_inv<NC, PC><<<grid, LEG_WARPS * 32, smem, p->stream>>>(table, p->d_order_start, shift, p->d_meta,
                                                                   p->d_rt_start, rco, ico, coef_stride, V, p->bw, nfun,
-                                                                  m_lo, real_fmt, order_list, l2_prefetch_cap(PC));
+                                                                  m_lo, real_fmt, order_list, l2_prefetch_cap(PC),
+                                                                  (NC < 32 && p->table_single && table == p->d_table) ? 1 : 0);
     return cudaGetLastError();
 }
 
@@ -462,6 +491,7 @@ cudaError_t launch_legendre_inv(s2kit_cuda_plan* p, const double* table, uint64_
     int real_fmt = data_format == S2KIT_REAL;
     int nc = pick_nc(p->bw, nfun, real_fmt);
     if (nc == 8 && nfun * (real_fmt ? 2 : 4) <= 4) nc = 4;  // single field: half-width panel
+    if (nc >= 32 && p->table_single && table == p->d_table) nc = 16;  // one table copy: the A-order reader is the narrow path
     int NF = nc / (real_fmt ? 2 : 4);
     int rs = pick_rowsplit(p->bw, (nfun + NF - 1) / NF, m_hi - m_lo);
     int slot = prof_begin(p, S2KIT_K_LEGENDRE_INV);

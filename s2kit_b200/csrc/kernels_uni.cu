@@ -55,6 +55,9 @@ struct UniArgs {
     double* ico;
     long coef_stride;
     int nfun, m_lo, norders, ncoltiles, real_fmt, lat_perm;
+    int debug_skip;  // measurement only (S2KIT_CUDA_UNI_SKIP): 1 = DCT tasks do nothing, 2 = DMMA units do nothing
+    int lead;        // DMMA units at the head of a stream before the DCT tasks start to alternate with them
+    int sleep_ns;    // back-off of the dependency polls (0 = plain polling)
 };
 
 // per-CTA copy of the per-order metadata (shared memory): queue offsets, unit codes, first tile of every order
@@ -89,7 +92,7 @@ __device__ __forceinline__ void uni_signal(int* ctr) {
     asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(ctr)))
                  : "memory");
 }
-__device__ __forceinline__ void uni_wait_ge(const int* ctr, int need) {
+__device__ __forceinline__ void uni_wait_ge(const int* ctr, int need, int sleep_ns) {
     if (need <= 0) return;
     const unsigned addr = static_cast<unsigned>(__cvta_generic_to_shared(ctr));
     unsigned spins = 0;
@@ -97,8 +100,8 @@ __device__ __forceinline__ void uni_wait_ge(const int* ctr, int need) {
         int v;
         asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
         if (v >= need) return;
-        __nanosleep(32);
-        if (++spins > (1u << 24)) __trap();  // a lost signal must not hang the device
+        if (sleep_ns) __nanosleep(sleep_ns);
+        if (++spins > (1u << 26)) __trap();  // a lost signal must not hang the device
     }
 }
 
@@ -154,7 +157,9 @@ __device__ __forceinline__ void uni_rows(const double* __restrict__ tp0, int ctn
 #pragma unroll
             for (int j = 0; j < NC / 8; ++j) dmma(acc1[j], a1.y, b[j][1]);
         }
-        // the DMMAs above have consumed the slots' registers: refill with the step STEPS ahead
+        // the DMMAs above have consumed the slots' registers: refill with the step STEPS ahead.  (Loading the next step's
+        // fragments before this step's DMMAs -- a software pipeline -- was measured SLOWER: 2.64 vs 2.37 ms per 1024
+        // functions; the extra live registers and moves cost more than the exposed shared-memory latency.)
         const int nx = ct + STEPS;
         if (nx < ctn1) {
             if (PAIR && nx < ctn0) cp_async16(reinterpret_cast<double*>(s0), tp0 + nx * 64);
@@ -308,17 +313,25 @@ __global__ void __launch_bounds__(UNI_THREADS, 1) k_fwd_uni(const UniArgs a) {
         if (k >= nk) break;
         if (lane == 0) tn = atomicAdd(&tick[sq], 1);  // the task after this one: its latency hides behind this task
         const int t = t_abs - base;
+        // stream order: `lead` DMMA units first (the heaviest; by the time the DCT tasks come up, the previous readers of
+        // their panel buffer are done), then DCT and DMMA tasks alternate while both kinds last, then the rest
         bool is_dct;
         int idx;
-        if (t < 2 * mi) {  // DCT and DMMA tasks alternate while both kinds last
-            is_dct = !(t & 1);
-            idx = t >> 1;
-        } else if (nf > nd) {
-            is_dct = true;
-            idx = t - nd;
-        } else {
-            is_dct = false;
-            idx = t - nf;
+        {
+            const int ld = nf ? (a.lead < nd ? a.lead : nd) : 0, t2 = t - ld, nd2 = nd - ld, mi2 = nf < nd2 ? nf : nd2;
+            if (t2 < 0) {
+                is_dct = false;
+                idx = t;
+            } else if (t2 < 2 * mi2) {
+                is_dct = !(t2 & 1);
+                idx = is_dct ? (t2 >> 1) : ld + (t2 >> 1);
+            } else if (nf > nd2) {
+                is_dct = true;
+                idx = t2 - nd2;
+            } else {
+                is_dct = false;
+                idx = ld + t2 - nf;
+            }
         }
         const int item = (int)blockIdx.x + k * (int)gridDim.x;  // (k = -1: only DCT tasks, of item 0)
         if (sq == 0 && t == 0 && k >= 0) {  // once per item: pull what the coming streams read into L2
@@ -331,14 +344,14 @@ __global__ void __launch_bounds__(UNI_THREADS, 1) k_fwd_uni(const UniArgs a) {
             if (k + 2 < nk) prefetch_rows(item + 2 * (int)gridDim.x);
         }
         if (is_dct) {
-            uni_wait_ge(&done[2 + ((k + 1) & 1)], cum[(k + 1) & 1]);  // dmma_done of the buffer's previous readers
-            dct_task(item + (int)gridDim.x, 4 * sq + idx, panels + ((k + 1) & 1) * PANEL);
+            uni_wait_ge(&done[2 + ((k + 1) & 1)], cum[(k + 1) & 1], a.sleep_ns);  // dmma_done of the buffer's previous readers
+            if (a.debug_skip != 1) dct_task(item + (int)gridDim.x, 4 * sq + idx, panels + ((k + 1) & 1) * PANEL);
             __threadfence_block();
             __syncwarp();
             if (lane == 0) uni_signal(&done[(k + 1) & 1]);
         } else {
-            uni_wait_ge(&done[k & 1], 16 * (k / 2 + 1));  // dct_done: the item's panel is complete
-            dmma_task(m, f0, mt.qlist[qb + idx], panels + (k & 1) * PANEL);
+            uni_wait_ge(&done[k & 1], 16 * (k / 2 + 1), a.sleep_ns);  // dct_done: the item's panel is complete
+            if (a.debug_skip != 2) dmma_task(m, f0, mt.qlist[qb + idx], panels + (k & 1) * PANEL);
             __syncwarp();
             if (lane == 0) uni_signal(&done[2 + (k & 1)]);
         }
@@ -383,6 +396,21 @@ cudaError_t launch_fwd_uni(s2kit_cuda_plan* p, const double* table, uint64_t shi
     const int NF = UNI_NC / (a.real_fmt ? 2 : 4);
     a.ncoltiles = (nfun + NF - 1) / NF;
     a.lat_perm = lat_perm;
+    static const int skip = [] {
+        const char* e = getenv("S2KIT_CUDA_UNI_SKIP");
+        return e ? atoi(e) : 0;
+    }();
+    a.debug_skip = skip;
+    static const int lead = [] {
+        const char* e = getenv("S2KIT_CUDA_UNI_LEAD");
+        return e ? atoi(e) : 0;
+    }();
+    static const int sleep_ns = [] {
+        const char* e = getenv("S2KIT_CUDA_UNI_SLEEP");
+        return e ? atoi(e) : 32;
+    }();
+    a.lead = lead;
+    a.sleep_ns = sleep_ns;
     constexpr int PANEL = 2 * (UNI_NC * 132 + 8);
     const size_t smem = sizeof(double) * 2 * PANEL + sizeof(double2) * UNI_WARPS * UNI_RING * 32 + 64 +
                         uni_meta_bytes(256, p->n_sub_list);

@@ -444,12 +444,17 @@ static int plan_build(s2kit_cuda_plan* p, int bw, int variant, int max_batch, in
     // ---- tables
     const uint64_t total_tiles = p->h_order_start[bw];
     if (variant == S2KIT_CUDA_MEMO) {
-        // two copies of the tiles in one allocation: A-fragment order for the forward contraction, B-fragment
-        // (tile-transposed) order for the inverse
+        // bw < 512: two copies of the tiles in one allocation, A-fragment order for the forward contraction and
+        // B-fragment (tile-transposed) order for the wide batched inverse kernels (26 MB at bw = 256).  bw >= 512 (where
+        // the table is what fills the memory: 11.7 GB at bw = 2048): ONE copy, the inverse gathers its fragments from it
         p->table_tiles = total_tiles;
-        p->table_bytes = 2 * total_tiles * 64 * sizeof(double);
+        {
+            const char* tc = getenv("S2KIT_CUDA_TABLE_COPIES");
+            p->table_single = bw >= 512 && !(tc && tc[0] == '2');
+        }
+        p->table_bytes = (p->table_single ? 1 : 2) * total_tiles * 64 * sizeof(double);
         CK(cudaMalloc((void**)&p->d_table, p->table_bytes));
-        p->d_table_t = p->d_table + total_tiles * 64;
+        p->d_table_t = p->table_single ? p->d_table : p->d_table + total_tiles * 64;
         // generate every run of consecutive owned orders
         int m = 0;
         while (m < bw) {
@@ -460,7 +465,7 @@ static int plan_build(s2kit_cuda_plan* p, int bw, int variant, int max_batch, in
             int hi = m;
             while (hi < bw && owned[hi]) ++hi;
             CK(s2k::launch_table_gen(p, p->d_table, 0, m, hi, 0));
-            CK(s2k::launch_table_gen(p, p->d_table_t, 0, m, hi, 1));
+            if (!p->table_single) CK(s2k::launch_table_gen(p, p->d_table_t, 0, m, hi, 1));
             m = hi;
         }
     } else {
@@ -599,6 +604,10 @@ extern "C" int s2kit_cuda_synchronize(s2kit_cuda_plan* p) {
 }
 extern "C" int s2kit_cuda_plan_bw(const s2kit_cuda_plan* p) { return p ? p->bw : 0; }
 extern "C" size_t s2kit_cuda_plan_table_bytes(const s2kit_cuda_plan* p) { return p ? p->table_bytes : 0; }
+extern "C" size_t s2kit_cuda_plan_table_stream_bytes(const s2kit_cuda_plan* p) {
+    if (!p) return 0;
+    return p->variant == S2KIT_CUDA_MEMO ? p->table_tiles * 64 * sizeof(double) : 0;
+}
 
 // ------------------------------------------------------------------------------------------------ order groups
 // Memo: one group covering [0, bw) on the resident table.  Fly: groups that fit the scratch ring; the table

@@ -106,7 +106,9 @@ struct s2kit_cuda_plan {
 
     // table (private tiled layout)
     double* d_table = nullptr;    // tiles in A-fragment order (forward); Fly: the scratch ring, either order
-    double* d_table_t = nullptr;  // Memo: the same tiles in B-fragment order (inverse), second half of one allocation
+    double* d_table_t = nullptr;  // Memo: the same tiles in B-fragment order (inverse), second half of one allocation;
+                                  // == d_table when the plan keeps a single copy (table_single)
+    bool table_single = false;    // bw >= 512: one copy, the inverse reads A-order tiles (S2KIT_CUDA_TABLE_COPIES=2 forces two)
     size_t table_tiles = 0;             // tiles resident in d_table
     std::vector<uint64_t> h_order_start;  // [bw+1] tile offset of each order in a full table
     std::vector<s2k::BlockMeta> h_meta;   // [2*bw]

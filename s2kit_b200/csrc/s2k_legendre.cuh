@@ -333,17 +333,105 @@ __device__ __forceinline__ void fwd_row_tile_async(const double* __restrict__ tp
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+// ---- table tiles staged by the TMA (bulk async copies) -----------------------------------------------------------
+// The column tiles of one row tile are contiguous in memory, so instead of one 16-byte cp.async per lane and tile a single
+// elected lane issues cp.async.bulk copies of BULK_CH tiles (1 KiB) into the warp's ring; completion is counted in
+// bytes on one mbarrier per ring stage (mbarrier::complete_tx), the lanes then read their 16 bytes per tile from shared
+// memory as before.  The copies are written by the async proxy: no LSU instruction or wavefront per tile on the way in.
+// ring: the WARP's ring (BULK_NS * BULK_CH tiles of 32 double2); bar: shared-memory address of the warp's BULK_NS
+// mbarriers (initialised to one arrival each); phases: the warp's phase bits, kept across calls.
+constexpr int BULK_CH = 2;  // tiles per bulk copy
+constexpr int BULK_NS = 4;  // stages: BULK_NS * BULK_CH = LEG_RING tiles in flight
+
+__device__ __forceinline__ void bulk_tile_copy(double2* dst, const double* src, unsigned bytes, unsigned bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     static_cast<unsigned>(__cvta_generic_to_shared(dst))),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_wait(unsigned bar, unsigned parity) {
+    unsigned done = 0, spins = 0;
+    while (!done) {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (++spins > (1u << 26)) __trap();  // a lost completion must not hang the device
+    }
+}
+
+// tile0: first tile of the row tile, no lane offset
+template <int NC>
+__device__ __forceinline__ void fwd_row_tile_bulk(const double* __restrict__ tile0, const double* xp, int CS, int ctn,
+                                                  double (&acc)[NC / 8][2], bool dead_lane, double2* ring, unsigned bar,
+                                                  unsigned& phases, int lane) {
+    static_assert(BULK_CH * BULK_NS == LEG_RING, "the bulk stages fill the lane-private ring's memory");
+    const int nch = (ctn + BULK_CH - 1) / BULK_CH;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < BULK_NS; ++s)
+            if (s < nch)
+                bulk_tile_copy(ring + s * BULK_CH * 32, tile0 + s * BULK_CH * 64, 512u * min(BULK_CH, ctn - s * BULK_CH), bar + 8 * s);
+    }
+#pragma unroll 1
+    for (int c = 0; c < nch; ++c) {
+        const int s = c & (BULK_NS - 1);
+        bulk_wait(bar + 8 * s, (phases >> s) & 1u);
+        phases ^= 1u << s;
+#pragma unroll
+        for (int u = 0; u < BULK_CH; ++u) {
+            const int ct = c * BULK_CH + u;
+            if (ct < ctn) {
+                const double2 av = ring[(s * BULK_CH + u) * 32 + lane];
+                double b[NC / 8][2];
+#pragma unroll
+                for (int j = 0; j < NC / 8; ++j) {
+                    b[j][0] = xp[j * 8 * CS + 8 * ct];
+                    b[j][1] = xp[j * 8 * CS + 8 * ct + 4];
+                    if (dead_lane) b[j][0] = b[j][1] = 0.0;  // MMA columns beyond a half-width panel
+                }
+#pragma unroll
+                for (int j = 0; j < NC / 8; ++j) dmma(acc[j], av.x, b[j][0]);
+#pragma unroll
+                for (int j = 0; j < NC / 8; ++j) dmma(acc[j], av.y, b[j][1]);
+            }
+        }
+        __syncwarp();  // every lane has its values of this stage in registers: the stage may be overwritten
+        if (lane == 0 && c + BULK_NS < nch) {
+            const int cn = c + BULK_NS;
+            bulk_tile_copy(ring + s * BULK_CH * 32, tile0 + cn * BULK_CH * 64, 512u * min(BULK_CH, ctn - cn * BULK_CH), bar + 8 * s);
+        }
+    }
+}
+
+// a_order: the tiles are stored in A-fragment order only (large-bandwidth Memo plans keep ONE table copy, plan.cu): the
+// lane's two B-fragment values -- tile elements (q4, g) and (q4 + 4, g) -- are then two 8-byte copies from the
+// transposed positions instead of one 16-byte copy; both still touch every sector of the tile exactly once per warp.
+// tbase: first tile of the order WITHOUT any lane offset.
 template <int NC>
 __device__ __forceinline__ void inv_col_tile_async(const double* __restrict__ tbase, const uint32_t* srt,
                                                    const BlockMeta& mb, int ct, const double* cp, int CS,
-                                                   double (&acc)[NC / 8][2], bool dead_lane, double2* ring) {
+                                                   double (&acc)[NC / 8][2], bool dead_lane, double2* ring, int a_order,
+                                                   int lane) {
     const int rt_min = first_row_tile_reaching(mb, ct);
     const int cnt = mb.nrt - rt_min;
     if (cnt <= 0) return;
+    const int g = lane >> 2, q4 = lane & 3;
+    const int o1 = a_order ? tile_elem_offset(q4, g) : 2 * lane;
+    auto copy_tile = [&](double2* slot, int rt) {
+        const double* t = tbase + ((uint64_t)srt[rt] + ct) * 64 + o1;
+        if (a_order) {
+            cp_async8(reinterpret_cast<double*>(slot), t);
+            cp_async8(reinterpret_cast<double*>(slot) + 1, t + 32);  // tile_elem_offset(q4 + 4, g)
+        } else {
+            cp_async16(reinterpret_cast<double*>(slot), t);
+        }
+    };
 #pragma unroll
     for (int u = 0; u < LEG_RING; ++u) {
-        if (u < cnt)
-            cp_async16(reinterpret_cast<double*>(ring + u * 32), tbase + ((uint64_t)srt[rt_min + u] + ct) * 64);
+        if (u < cnt) copy_tile(ring + u * 32, rt_min + u);
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
 #pragma unroll 1
@@ -363,8 +451,7 @@ __device__ __forceinline__ void inv_col_tile_async(const double* __restrict__ tb
         for (int j = 0; j < NC / 8; ++j) dmma(acc[j], a[j][0], bv.x);
 #pragma unroll
         for (int j = 0; j < NC / 8; ++j) dmma(acc[j], a[j][1], bv.y);
-        if (i + LEG_RING < cnt)
-            cp_async16(reinterpret_cast<double*>(slot), tbase + ((uint64_t)srt[rt + LEG_RING] + ct) * 64);
+        if (i + LEG_RING < cnt) copy_tile(slot, rt + LEG_RING);
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");

@@ -126,3 +126,20 @@ def test_host_side_checks_of_device_helpers(tmp_path, check, expect):
     assert r.returncode == 0, r.stderr[-2000:]
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and expect in r.stdout, r.stdout + r.stderr
+
+
+def test_per_file_headers_forward_to_the_api(tmp_path):
+    """A caller of the reference includes "s2kit/FST_semi_memo.h" etc. (reference include/s2kit/*.h): the drop-in tree
+    ships those file names, each forwarding to include/s2kit.h; every one compiles alone and declares the entry points
+    of the reference header of the same name."""
+    import subprocess
+
+    expect = {"FST_semi_memo": "FSTSemiMemo", "FST_semi_fly": "InvFSTSemiFly", "cospml": "Spharmonic_Pml_Table",
+              "pml": "GeneratePmlTable", "pmm": "Pmm_L2", "seminaive": "InvDLTSemi", "naive": "DLTNaive",
+              "weights": "GenerateWeightsForDLT", "util": "TransMult", "chebyshev_nodes": "ChebyshevNodes"}
+    for name, symbol in expect.items():
+        src = tmp_path / f"use_{name}.c"
+        src.write_text(f'#include "s2kit/{name}.h"\nvoid* probe(void) {{ return (void*){symbol}; }}\nDataFormat fmt = REAL;\n')
+        r = subprocess.run(["gcc", "-std=gnu11", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr

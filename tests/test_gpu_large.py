@@ -91,6 +91,8 @@ def test_c5_bw2048_forward_vs_reference(s2, large, plan2048):
         wr, wi = large[f"bw2048_fwd_order_{tag}_r"], large[f"bw2048_fwd_order_{tag}_i"]
         e = max(np.abs(fr[a0:a0 + bw - abs(m)] - wr).max(), np.abs(fi[a0:a0 + bw - abs(m)] - wi).max()) / scale
         assert e < TOL, (m, e)
+    # one copy of the tiled table is resident (the reference needs two packed tables: 2 x 11.46 GB)
+    assert plan2048.table_bytes() == plan2048.table_stream_bytes() < 12.0e9
     nan_orders = set(int(m) for m in large["bw2048_ref_nan_orders"])
     assert nan_orders == {m for m in range(-(bw - 1), bw) if abs(m) >= 2044}
 

@@ -102,10 +102,8 @@ def main():
     inverse()
     proj_err = float((out_r - a1_r).abs().max() / a1_r.abs().max())  # projection is idempotent
     res = {"bw": bw, "n_gpus": world, "ms_forward": ms_fwd, "ms_inverse": ms_inv, "ms_exchange_only": ms_x,
-           # a Memo plan keeps the table twice (A-fragment order for the forward, B-fragment order for the inverse
-           # contraction): one direction streams half of table_bytes
            "table_bytes_per_gpu": P.table_bytes(),
-           "table_stream_gbs_per_gpu_fwd": 0.5 * P.table_bytes() / (ms_fwd * 1e-3) / 1e9,
+           "table_stream_gbs_per_gpu_fwd": P.table_stream_bytes() / (ms_fwd * 1e-3) / 1e9,
            "exchange_bytes_per_gpu": 8 * blk * (world - 1), "idempotence_rel_err": proj_err}
     if a.check:
         # gather the sharded coefficients and compare with the unsharded plan on rank 0
