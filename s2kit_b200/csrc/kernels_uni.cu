@@ -671,8 +671,19 @@ __global__ void __launch_bounds__(UNI_THREADS, 1) k_inv_uni(const UniInvArgs a) 
     }
 }
 
+// Opt-in (S2KIT_CUDA_UNI_INV=1): measured at bw = 256, 1024 functions, the fused kernel takes 2.83 ms against 1.17 + 1.19 ms
+// for K4 + K5 as separate kernels -- with one V panel its two phases cannot overlap, so it pays both halves in full plus
+// two CTA-wide barriers per item, while the separate kernels run at 24 warps per SM (profiles/r2_ncu_uni_summary.md).
+static bool uni_inv_enabled() {
+    static int on = [] {
+        const char* e = getenv("S2KIT_CUDA_UNI_INV");
+        return (e && e[0] == '1') ? 1 : 0;
+    }();
+    return on != 0;
+}
+
 bool inv_uni_supported(const s2kit_cuda_plan* p, int nfun, int data_format) {
-    if (!uni_enabled() || !p->fast || p->n != 512 || !p->d_isub_list) return false;
+    if (!uni_enabled() || !uni_inv_enabled() || !p->fast || p->n != 512 || !p->d_isub_list) return false;
     return nfun * (data_format == S2KIT_REAL ? 2 : 4) >= UNI_NC;
 }
 
