@@ -111,10 +111,10 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, NC >= 32 ? 2 : 3) k_legendre_f
     double2* ring = reinterpret_cast<double2*>(cinfo + NC) + (warp * LEG_RING * 32 + lane);
     // TMA-staged tiles (narrow panels): BULK_NS mbarriers per warp behind the rings
     const unsigned bar = static_cast<unsigned>(__cvta_generic_to_shared(reinterpret_cast<double2*>(cinfo + NC) +
-                                                                        LEG_WARPS * LEG_RING * 32)) + warp * BULK_NS * 8;
+                                                                        LEG_WARPS * LEG_RING * 32)) + warp * BULK_NS_MAX * 8;
     unsigned phases = 0;
     if (NC < 32 && tma_tables && lane == 0) {
-        for (int s = 0; s < BULK_NS; ++s)
+        for (int s = 0; s < BULK_NS_MAX; ++s)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar + 8 * s) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -219,11 +219,23 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, NC >= 32 ? 2 : 3) k_legendre_f
             for (int j = 0; j < NC / 8; ++j) acc0[j][0] = acc0[j][1] = acc1[j][0] = acc1[j][1] = 0.0;
             if (tma_tables) {
                 double2* wring = ring - lane;
-                fwd_row_tile_bulk<NC>(tbase - lane * 2 + (uint64_t)srt[rt] * 64, Xs + gsel * CS + q4, CS, tiles_in_row(mb0, rt),
-                                      acc0, PC < NC && g >= PC, wring, bar, phases, lane);
-                if (rt < mb1.nrt)
-                    fwd_row_tile_bulk<NC>(tbase - lane * 2 + (uint64_t)srt[mb0.nrt + rt] * 64, Xs + (PC + gsel) * CS + q4, CS,
-                                          tiles_in_row(mb1, rt), acc1, PC < NC && g >= PC, wring, bar, phases, lane);
+                const double* t0 = tbase - lane * 2 + (uint64_t)srt[rt] * 64;
+                const double* t1 = tbase - lane * 2 + (uint64_t)srt[mb0.nrt + (rt < mb1.nrt ? rt : 0)] * 64;
+                const double* x0 = Xs + gsel * CS + q4;
+                const double* x1 = Xs + (PC + gsel) * CS + q4;
+                const bool dead = PC < NC && g >= PC;
+                const int c0 = tiles_in_row(mb0, rt), c1 = rt < mb1.nrt ? tiles_in_row(mb1, rt) : 0;
+                // copies of 1, 2 or 4 tiles (S2KIT_CUDA_TMA_TABLES = 3, 1, 2), always 8 tiles in flight per warp
+                if (tma_tables == 2) {
+                    fwd_row_tile_bulk<NC, 4, 2>(t0, x0, CS, c0, acc0, dead, wring, bar, phases, lane);
+                    if (c1) fwd_row_tile_bulk<NC, 4, 2>(t1, x1, CS, c1, acc1, dead, wring, bar, phases, lane);
+                } else if (tma_tables == 3) {
+                    fwd_row_tile_bulk<NC, 1, 8>(t0, x0, CS, c0, acc0, dead, wring, bar, phases, lane);
+                    if (c1) fwd_row_tile_bulk<NC, 1, 8>(t1, x1, CS, c1, acc1, dead, wring, bar, phases, lane);
+                } else {
+                    fwd_row_tile_bulk<NC, 2, 4>(t0, x0, CS, c0, acc0, dead, wring, bar, phases, lane);
+                    if (c1) fwd_row_tile_bulk<NC, 2, 4>(t1, x1, CS, c1, acc1, dead, wring, bar, phases, lane);
+                }
             } else {
                 fwd_row_tile_async<NC>(tbase + (uint64_t)srt[rt] * 64, Xs + gsel * CS + q4, CS, tiles_in_row(mb0, rt), acc0,
                                        PC < NC && g >= PC, ring);
@@ -398,16 +410,19 @@ static cudaError_t leg_fwd_nc(s2kit_cuda_plan* p, const double* table, uint64_t 
     int cols_per_fn = real_fmt ? 2 : 4;
     int NF = PC / cols_per_fn;
     size_t smem = sizeof(double) * 2 * PC * panel_stride(p->bw) + sizeof(uint32_t) * ((p->bw / 8 + 8 + 3) & ~3) +
-                  sizeof(ColOut) * NC + (NC < 32 ? sizeof(double2) * LEG_WARPS * LEG_RING * 32 + 8 * LEG_WARPS * BULK_NS : 0);
+                  sizeof(ColOut) * NC + (NC < 32 ? sizeof(double2) * LEG_WARPS * LEG_RING * 32 + 8 * LEG_WARPS * BULK_NS_MAX : 0);
     if (smem > 48 * 1024) {
         cudaError_t e = ensure_smem(reinterpret_cast<const void*>(k_legendre_fwd<NC, PC>), smem);
         if (e != cudaSuccess) return e;
     }
-    // narrow panels (single fields stream every tile once): table tiles staged by the TMA; S2KIT_CUDA_TMA_TABLES=0 keeps
-    // the lane-private cp.async ring
+    // Narrow panels (single fields stream every tile once).  Default: the lane-private cp.async ring.  S2KIT_CUDA_TMA_TABLES
+    // = 1 / 2 / 3 stages the tiles with TMA bulk copies of 2 / 4 / 1 tiles instead (fwd_row_tile_bulk): measured slower --
+    // bw = 2048 forward 2.27 ms (cp.async) vs 2.34 / 2.30 / 2.94 ms, bw = 1024 0.36 vs 0.47 ms (profiles/r2_single_field_variants.json):
+    // the ring already runs the table stream at the HBM roofline (6.6 TB/s), and one elected lane issuing the copies and
+    // arming the mbarriers per chunk costs more than 32 lanes each issuing their own 16-byte copy.
     static const int tma_tables = [] {
         const char* e = getenv("S2KIT_CUDA_TMA_TABLES");
-        return (e && e[0] == '0') ? 0 : 1;
+        return e ? atoi(e) : 0;
     }();
     dim3 grid((nfun + NF - 1) / NF, m_hi - m_lo, rowsplit);
     k_legendre_fwd<NC, PC><<<grid, LEG_WARPS * 32, smem, p->stream>>>(table, p->d_order_start, shift, p->d_meta,

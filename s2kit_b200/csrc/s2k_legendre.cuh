@@ -340,8 +340,7 @@ __device__ __forceinline__ void fwd_row_tile_async(const double* __restrict__ tp
 // memory as before.  The copies are written by the async proxy: no LSU instruction or wavefront per tile on the way in.
 // ring: the WARP's ring (BULK_NS * BULK_CH tiles of 32 double2); bar: shared-memory address of the warp's BULK_NS
 // mbarriers (initialised to one arrival each); phases: the warp's phase bits, kept across calls.
-constexpr int BULK_CH = 2;  // tiles per bulk copy
-constexpr int BULK_NS = 4;  // stages: BULK_NS * BULK_CH = LEG_RING tiles in flight
+constexpr int BULK_NS_MAX = 8;  // mbarriers reserved per warp
 
 __device__ __forceinline__ void bulk_tile_copy(double2* dst, const double* src, unsigned bytes, unsigned bar) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -362,12 +361,12 @@ __device__ __forceinline__ void bulk_wait(unsigned bar, unsigned parity) {
     }
 }
 
-// tile0: first tile of the row tile, no lane offset
-template <int NC>
+// tile0: first tile of the row tile, no lane offset.  BULK_CH tiles per bulk copy, BULK_NS stages.
+template <int NC, int BULK_CH, int BULK_NS>
 __device__ __forceinline__ void fwd_row_tile_bulk(const double* __restrict__ tile0, const double* xp, int CS, int ctn,
                                                   double (&acc)[NC / 8][2], bool dead_lane, double2* ring, unsigned bar,
                                                   unsigned& phases, int lane) {
-    static_assert(BULK_CH * BULK_NS == LEG_RING, "the bulk stages fill the lane-private ring's memory");
+    static_assert(BULK_CH * BULK_NS == LEG_RING && BULK_NS <= BULK_NS_MAX, "the bulk stages fill the lane-private ring's memory");
     const int nch = (ctn + BULK_CH - 1) / BULK_CH;
     if (lane == 0) {
 #pragma unroll
@@ -406,9 +405,12 @@ __device__ __forceinline__ void fwd_row_tile_bulk(const double* __restrict__ til
     }
 }
 
-// a_order: the tiles are stored in A-fragment order only (large-bandwidth Memo plans keep ONE table copy, plan.cu): the
-// lane's two B-fragment values -- tile elements (q4, g) and (q4 + 4, g) -- are then two 8-byte copies from the
-// transposed positions instead of one 16-byte copy; both still touch every sector of the tile exactly once per warp.
+// a_order: the tiles are stored in A-fragment order only (large-bandwidth Memo plans keep ONE table copy, plan.cu).  The
+// copy into the ring is the same coalesced 16 bytes per lane as in the forward direction; the lane's two B-fragment
+// values -- tile elements (q4, g) and (q4 + 4, g) -- are then READ from the other lanes' slots (two conflict-free 64-bit
+// loads at the transposed positions), which makes the ring slot warp-shared: a __syncwarp after the lane's own copy has
+// landed (then every lane's has) and one before the slot is refilled.  (Gathering with two 8-byte cp.async per lane
+// instead was 34 % slower at bw = 2048: 2.44 vs 1.83 ms.)
 // tbase: first tile of the order WITHOUT any lane offset.
 template <int NC>
 __device__ __forceinline__ void inv_col_tile_async(const double* __restrict__ tbase, const uint32_t* srt,
@@ -419,15 +421,9 @@ __device__ __forceinline__ void inv_col_tile_async(const double* __restrict__ tb
     const int cnt = mb.nrt - rt_min;
     if (cnt <= 0) return;
     const int g = lane >> 2, q4 = lane & 3;
-    const int o1 = a_order ? tile_elem_offset(q4, g) : 2 * lane;
+    const int o1 = tile_elem_offset(q4, g);  // element (q4, g) inside an A-order tile; (q4 + 4, g) is 32 doubles further
     auto copy_tile = [&](double2* slot, int rt) {
-        const double* t = tbase + ((uint64_t)srt[rt] + ct) * 64 + o1;
-        if (a_order) {
-            cp_async8(reinterpret_cast<double*>(slot), t);
-            cp_async8(reinterpret_cast<double*>(slot) + 1, t + 32);  // tile_elem_offset(q4 + 4, g)
-        } else {
-            cp_async16(reinterpret_cast<double*>(slot), t);
-        }
+        cp_async16(reinterpret_cast<double*>(slot), tbase + ((uint64_t)srt[rt] + ct) * 64 + 2 * lane);
     };
 #pragma unroll
     for (int u = 0; u < LEG_RING; ++u) {
@@ -439,7 +435,14 @@ __device__ __forceinline__ void inv_col_tile_async(const double* __restrict__ tb
         const int rt = rt_min + i;
         double2* slot = ring + (i & (LEG_RING - 1)) * 32;
         asm volatile("cp.async.wait_group %0;" ::"n"(LEG_RING - 1) : "memory");
-        const double2 bv = *slot;
+        double2 bv;
+        if (a_order) {
+            __syncwarp();  // every lane's 16 bytes of this tile have landed
+            const double* tile = reinterpret_cast<const double*>(slot - lane);
+            bv = make_double2(tile[o1], tile[o1 + 32]);
+        } else {
+            bv = *slot;
+        }
         double a[NC / 8][2];
 #pragma unroll
         for (int j = 0; j < NC / 8; ++j) {
@@ -451,6 +454,7 @@ __device__ __forceinline__ void inv_col_tile_async(const double* __restrict__ tb
         for (int j = 0; j < NC / 8; ++j) dmma(acc[j], a[j][0], bv.x);
 #pragma unroll
         for (int j = 0; j < NC / 8; ++j) dmma(acc[j], a[j][1], bv.y);
+        if (a_order) __syncwarp();  // every lane has read the slot: it may be overwritten
         if (i + LEG_RING < cnt) copy_tile(slot, rt + LEG_RING);
         asm volatile("cp.async.commit_group;" ::: "memory");
     }

@@ -275,7 +275,7 @@ def test_table_builders_match_reference_layout(s2, oracle_mod):
 @pytest.mark.parametrize("env", [{"S2KIT_CUDA_NO_TMA": "1"}, {"S2KIT_CUDA_FFT16": "0"}, {"S2KIT_CUDA_L2PERSIST": "1"},
                                  {"S2KIT_CUDA_NC": "16"}, {"S2KIT_CUDA_L2PF_MAX": "0"}, {"S2KIT_CUDA_UNI": "0"},
                                  {"S2KIT_CUDA_UNI_INV": "1"}, {"S2KIT_CUDA_UNI_LEAD": "2", "S2KIT_CUDA_UNI_SLEEP": "0", "S2KIT_CUDA_UNI_CAP": "8"},
-                                 {"S2KIT_CUDA_TMA_TABLES": "0"},
+                                 {"S2KIT_CUDA_TMA_TABLES": "1"},
                                  {"S2KIT_CUDA_TABLE_LCH": "64", "S2KIT_CUDA_FLY_RING_MB": "8"}])
 def test_tuning_switches_keep_parity(env):
     """Every environment switch the library reads selects code that must still match the oracle: the wide-panel batch
@@ -288,9 +288,9 @@ def test_tuning_switches_keep_parity(env):
     assert "4 passed" in r.stdout, r.stdout[-500:]
 
 
-@pytest.mark.parametrize("env", [{"S2KIT_CUDA_TABLE_COPIES": "2"}, {"S2KIT_CUDA_TMA_TABLES": "0"}])
+@pytest.mark.parametrize("env", [{"S2KIT_CUDA_TABLE_COPIES": "2"}, {"S2KIT_CUDA_TMA_TABLES": "1"}, {"S2KIT_CUDA_TMA_TABLES": "2"}])
 def test_large_bandwidth_switches_keep_parity(env):
-    """Switches that only matter at bw >= 512 (second table copy, cp.async instead of TMA-staged table tiles): the bw = 512
+    """Switches that only matter at bw >= 512 (second table copy, TMA-staged table tiles instead of cp.async): the bw = 512
     reference-sample test in a child process."""
     e = dict(os.environ, **env)
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_large.py"), "-q", "-x", "-m", "gpu",
