@@ -287,26 +287,43 @@ __global__ void __launch_bounds__(N / 8 * FPB) k_dct_fwd(const double* __restric
     const double* Sr = S + (long)f * 2 * N * N + rowoff;
     const double* Si = Sr + pv.part_stride;
     double xr[8], xi[8];
+    if constexpr (PEER) {
+        // Single field over the GPUs of one process: segment s of the row lives in peer s's memory -- the ring -> order
+        // exchange IS these loads.  The row (2 x N doubles) is pulled into the transform's exchange buffer with coalesced
+        // 16-byte cp.async copies (512 contiguous bytes per warp and instruction: NVLink-friendly requests, all of a
+        // thread's copies in flight at once), then read from there in the DCT's even/odd order.  (Loading the reordered
+        // 8-byte elements straight from peer memory made the 2-GPU transform slower than one GPU: 2.7 vs 2.3 ms.)
+        double* st = reinterpret_cast<double*>(sx);
+        for (int q = t; q < N; q += T8) {
+            const int part = q / (N / 2), j = (q % (N / 2)) * 2;
+            const double* src = peers.ptr[j >> pv.seg_shift] + rowoff + (j & pv.seg_mask) + (long)part * pv.part_stride;
+            unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(st + part * N + j));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
+        }
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+        fft_sync<N>(g);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        int p = t + e * T8;
-        double wj = __ldg(w + p);  // weights are stored in load order (s2k_host_reordered)
-        if constexpr (PEER) {
-            // single field over the GPUs of one process: the segment lives in a peer's memory -- the ring -> order
-            // exchange IS these loads (NVLink reads of contiguous runs, overlapped with the transforms of other CTAs)
+        for (int e = 0; e < 8; ++e) {
+            const int p = t + e * T8;
+            const double wj = __ldg(w + p);
             const int j = (p < B) ? 2 * p : 2 * (N - 1 - p) + 1;
-            const double* src = peers.ptr[j >> pv.seg_shift] + rowoff + (j & pv.seg_mask);
-            xr[e] = src[0] * wj;
-            xi[e] = src[pv.part_stride] * wj;
-            continue;
+            xr[e] = st[j] * wj;
+            xi[e] = st[N + j] * wj;
         }
-        long at = p;               // lat_perm: the row already is in load order
-        if (!pv.lat_perm) {
-            int j = (p < B) ? 2 * p : 2 * (N - 1 - p) + 1;
-            at = seg_offset(pv, j);
+        fft_sync<N>(g);  // the staging area becomes the exchange buffer
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            int p = t + e * T8;
+            double wj = __ldg(w + p);  // weights are stored in load order (s2k_host_reordered)
+            long at = p;               // lat_perm: the row already is in load order
+            if (!pv.lat_perm) {
+                int j = (p < B) ? 2 * p : 2 * (N - 1 - p) + 1;
+                at = seg_offset(pv, j);
+            }
+            xr[e] = __ldg(Sr + at) * wj;
+            xi[e] = __ldg(Si + at) * wj;
         }
-        xr[e] = __ldg(Sr + at) * wj;
-        xi[e] = __ldg(Si + at) * wj;
     }
     fft_block<N>(xr, xi, sx, t, g, tw);
     // Separation of the two real spectra needs Z[k] and Z[n-k], k < bw: Z[k] is still in this thread's registers, so
@@ -393,23 +410,39 @@ __global__ void __launch_bounds__(N / 8 * FPB) k_dct_inv(const double* __restric
         xi[e] = wr;
     }
     fft_block<N>(xr, xi, sx, t, g, tw);
-    if (!live) return;
     double sign = ((mp > B) && (m & 1)) ? -out_scale : out_scale;  // (-1)^m for negative orders
     const long rowoff = (long)(pv.rowlist ? rsel : mp) * pv.lrow_stride;
+    if constexpr (PEER) {
+        // order -> ring exchange as NVLink stores into the ring owners' receive blocks (multi.cu): the row is put into
+        // natural latitude order in the exchange buffer first, so the stores are coalesced 16-byte pieces of each peer's
+        // contiguous run instead of scattered 8-byte elements
+        double* st = reinterpret_cast<double*>(sx);
+        fft_sync<N>(g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int i = fft_out_index<N>(e, t);
+            const double sc = (m & 1) ? __ldg(sinv + i) * sign : sign;
+            const int j = (i < B) ? 2 * i : 2 * (N - 1 - i) + 1;
+            st[j] = xi[e] * sc;      // Re z -> column a (real part)
+            st[N + j] = xr[e] * sc;  // Im z -> column b (imaginary part)
+        }
+        fft_sync<N>(g);
+        if (live)
+            for (int q = t; q < N; q += T8) {
+                const int part = q / (N / 2), j = (q % (N / 2)) * 2;
+                double* dst = const_cast<double*>(peers.ptr[j >> pv.seg_shift]) + rowoff + (j & pv.seg_mask) +
+                              (long)part * pv.part_stride;
+                *reinterpret_cast<double2*>(dst) = *reinterpret_cast<const double2*>(st + part * N + j);
+            }
+        return;
+    }
+    if (!live) return;
     double* Gr = G + (long)f * 2 * N * N + rowoff;
     double* Gi = Gr + pv.part_stride;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         int i = fft_out_index<N>(e, t);
         double s = (m & 1) ? __ldg(sinv + i) * sign : sign;  // sines stored in output order (s2k_host_reordered)
-        if constexpr (PEER) {
-            // order -> ring exchange as NVLink stores into the ring owner's receive block (multi.cu)
-            const int j = (i < B) ? 2 * i : 2 * (N - 1 - i) + 1;
-            double* dst = const_cast<double*>(peers.ptr[j >> pv.seg_shift]) + rowoff + (j & pv.seg_mask);
-            dst[0] = xi[e] * s;
-            dst[pv.part_stride] = xr[e] * s;
-            continue;
-        }
         long at = i;  // lat_perm: the row is kept in output order
         if (!pv.lat_perm) {
             int j = (i < B) ? 2 * i : 2 * (N - 1 - i) + 1;

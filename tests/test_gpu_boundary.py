@@ -128,7 +128,7 @@ def test_plan_clone_shares_tables_and_runs_concurrently(s2, oracle_mod):
 
 
 # ------------------------------------------------------------------------------------------------ multi-GPU, one process
-@pytest.mark.parametrize("bw,ngpu", [(64, 1), (256, 1), (128, 2), (256, 4), (256, 8)])
+@pytest.mark.parametrize("bw,ngpu", [(64, 1), (256, 1), (512, 1), (128, 2), (512, 2), (256, 4), (256, 8)])
 def test_multi_gpu_single_process_transform(s2, oracle_mod, bw, ngpu):
     """s2kit_cuda_multi_*: rings and orders split over the GPUs, the exchange done by the DCT kernels on peer-mapped
     memory.  ngpu = 1 runs the same code path (peer pointers = own buffers) on the driver's single-GPU box."""
