@@ -85,7 +85,7 @@ __device__ __forceinline__ int lat_row(int pos, int n, int lat_perm) {
 template <int N>
 __global__ void __launch_bounds__(N) k_phi_fft_fwd_tma(const double* __restrict__ rdata, const double* __restrict__ idata,
                                                         long stride, double scale, int rows_kept, int lat_perm,
-                                                        const double2* __restrict__ tw,
+                                                        const double2* __restrict__ tw, int f_plane0,
                                                         const __grid_constant__ CUtensorMap tmap) {
     constexpr int LT = 8, T8 = N / 8;
     constexpr int RS = phi_row_stride(N, LT);
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(N) k_phi_fft_fwd_tma(const double* __restrict_
             for (int h = 0; h < nbox; ++h)
                 asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(
                                  reinterpret_cast<uint64_t>(&tmap)),
-                             "r"(j0), "r"(h * ROWS), "r"(f * 2 + part),
+                             "r"(j0), "r"(h * ROWS), "r"((f_plane0 + f) * 2 + part),
                              "r"(sbase + (unsigned)((part * (N / ROWS) + h) * BOX_BYTES))
                              : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -202,7 +202,7 @@ __device__ __forceinline__ void mbar_wait(unsigned mbar_addr, unsigned phase) {
 
 template <int N>
 __global__ void __launch_bounds__(N) k_phi_fft_inv_tma(double* __restrict__ rdata, double* __restrict__ idata, long stride,
-                                                        int real_fmt, int lat_perm, const double2* __restrict__ tw,
+                                                        int real_fmt, int lat_perm, const double2* __restrict__ tw, int f_plane0,
                                                         const __grid_constant__ CUtensorMap tmap) {
     constexpr int LT = 8, T8 = N / 8;
     constexpr int RS = phi_row_stride(N, LT);
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(N) k_phi_fft_inv_tma(double* __restrict__ rdat
                 asm volatile(
                     "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::
                         "r"(sbase + (unsigned)((part * NBOX + h) * BOX_BYTES)),
-                    "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(j0), "r"(h * ROWS), "r"(f * 2 + part), "r"(mbar)
+                    "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(j0), "r"(h * ROWS), "r"((f_plane0 + f) * 2 + part), "r"(mbar)
                     : "memory");
     }
     mbar_wait(mbar, 0);
@@ -547,14 +547,17 @@ static cudaError_t phi_fwd_n(s2kit_cuda_plan* p, const double* rdata, const doub
     constexpr int LT = (4096 / N) < 8 ? (4096 / N) : 8;
     if constexpr (N <= 512) {
         // ordinary plane in the plan's own workspace: transposed write through the TMA
-        if (tma_planes_ok(p, nfun) && S == p->d_S && !pv.rowbase && nrings == N) {
+        const long plane2 = 2L * N * N, offS = S - p->d_S;
+        if (tma_planes_ok(p, nfun) && offS >= 0 && offS % plane2 == 0 && offS / plane2 + nfun <= p->chunk && !pv.rowbase &&
+            nrings == N) {
             constexpr int RSX = phi_row_stride(N, 8);
             size_t smem = std::max(sizeof(double2) * 8 * RSX, (size_t)2 * N * 8 * 8);
             cudaError_t e = set_smem(k_phi_fft_fwd_tma<N>, smem);
             if (e != cudaSuccess) return e;
             double scale = sqrt(2.0 * M_PI) / (double)N;
             k_phi_fft_fwd_tma<N><<<dim3(N / 8, nfun), N, smem, p->stream>>>(rdata, idata, stride, scale, rows_kept,
-                                                                              pv.lat_perm, p->d_tw_n, p->tma_S);
+                                                                              pv.lat_perm, p->d_tw_n, (int)(offS / plane2),
+                                                                              p->tma_S);
             return cudaGetLastError();
         }
     }
@@ -575,13 +578,15 @@ static cudaError_t phi_inv_n(s2kit_cuda_plan* p, const double* G, double* rdata,
                              int real_fmt, const PlaneView& pv, int nrings) {
     constexpr int LT = (4096 / N) < 8 ? (4096 / N) : 8;
     if constexpr (N <= 512) {
-        if (tma_planes_ok(p, nfun) && G == p->d_S && !pv.rowbase && nrings == N) {
+        const long plane2 = 2L * N * N, offG = G - p->d_S;
+        if (tma_planes_ok(p, nfun) && offG >= 0 && offG % plane2 == 0 && offG / plane2 + nfun <= p->chunk && !pv.rowbase &&
+            nrings == N) {
             constexpr int RSX = phi_row_stride(N, 8);
             size_t smem = std::max(sizeof(double2) * 8 * RSX, (size_t)2 * N * 8 * 8) + 16;
             cudaError_t e = set_smem(k_phi_fft_inv_tma<N>, smem);
             if (e != cudaSuccess) return e;
             k_phi_fft_inv_tma<N><<<dim3(N / 8, nfun), N, smem, p->stream>>>(rdata, idata, stride, real_fmt, pv.lat_perm,
-                                                                              p->d_tw_n, p->tma_S);
+                                                                              p->d_tw_n, (int)(offG / plane2), p->tma_S);
             return cudaGetLastError();
         }
     }

@@ -36,7 +36,7 @@
 namespace s2k {
 
 constexpr int UNI_NC = 32;
-constexpr int UNI_WARPS = 16;
+constexpr int UNI_WARPS = 16;  // 128 registers per thread.  20 warps at 96 registers (spills, 6-tile rings) were measured slower: 2.67 vs 2.37 ms
 constexpr int UNI_THREADS = UNI_WARPS * 32;
 constexpr int UNI_RING = 8;  // table tiles in flight per warp (8 x 512 B)
 
@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(UNI_THREADS, 1) k_inv_uni(const UniInvArgs a) 
             const int q = warp;  // pair index: panel columns 2q (real part), 2q + 1 (imaginary part)
             const int fl = a.real_fmt ? q : (q >> 1), sgn = a.real_fmt ? 0 : (q & 1);
             const int f = f0 + fl;
-            if (f < a.nfun && !(sgn && m == 0)) {
+            if (q < NC / 2 && f < a.nfun && !(sgn && m == 0)) {
                 double* col0 = Vp + (2 * q) * CS;
                 const double* Va = col0;
                 const double* Vb = col0 + CS;

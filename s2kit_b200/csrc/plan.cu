@@ -372,6 +372,8 @@ static int plan_build(s2kit_cuda_plan* p, int bw, int variant, int max_batch, in
         // L2 away from the streaming kernels), the per-CTA bulk prefetch already does the job -- opt-in
         const char* np = getenv("S2KIT_CUDA_L2PERSIST");
         p->l2_persist = (np && np[0] == '1');
+        const char* sp = getenv("S2KIT_CUDA_SPLIT");
+        p->nsplit = sp ? std::max(1, std::min(16, atoi(sp))) : 1;
     }
     {
         cudaDeviceProp prop;
@@ -529,6 +531,9 @@ extern "C" int s2kit_cuda_plan_destroy(s2kit_cuda_plan* p) {
         cudaEventDestroy(s.b);
     }
     host_pipe_destroy(p->host_pipe);
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    if (p->ev_join) cudaEventDestroy(p->ev_join);
+    if (p->aux_stream) cudaStreamDestroy(p->aux_stream);
     if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
     delete p->mu;
     delete p;
@@ -552,6 +557,8 @@ extern "C" int s2kit_cuda_plan_clone(s2kit_cuda_plan** out, const s2kit_cuda_pla
     p->stream = nullptr;
     p->own_stream = true;
     p->host_pipe = nullptr;
+    p->aux_stream = nullptr;
+    p->ev_fork = p->ev_join = nullptr;
     p->d_S = p->d_X = p->d_coef = p->d_coef2 = p->d_filt = p->d_stage = nullptr;
     p->stage_doubles = 0;
     p->prof_slots.clear();
@@ -640,66 +647,117 @@ static int ensure(double** ptr, size_t doubles) {
 }
 
 // ------------------------------------------------------------------------------------------------ device paths
-static int fst_device(s2kit_cuda_plan* p, const double* rdata, const double* idata, double* rco, double* ico,
-                      int batch, long data_stride, long coef_stride, int fmt) {
-    const int bw = p->bw;
+// One sub-batch of nf functions through the forward kernels, on p->stream, in the workspace slice starting at function
+// slot w0 of d_S / d_X.
+static int fst_sub(s2kit_cuda_plan* p, const double* rd, const double* id, double* rc, double* ic, int nf,
+                   long data_stride, long coef_stride, int fmt, int w0) {
+    const int bw = p->bw, n = p->n;
     const int nrows = (fmt == S2KIT_REAL) ? bw : 2 * bw - 1;
-    for (int c0 = 0; c0 < batch; c0 += p->chunk) {
-        int nf = std::min(p->chunk, batch - c0);
-        const double* rd = rdata + (long)c0 * data_stride;
-        const double* id = idata + (long)c0 * data_stride;
-        double* rc = rco + (long)c0 * coef_stride;
-        double* ic = ico + (long)c0 * coef_stride;
+    double* dS = p->d_S + (size_t)w0 * 2 * n * n;
+    double* dX = p->d_X + (size_t)w0 * n * 2 * bw;
+    {
         // TMA variant of K1 available: keep the planes' latitudes in the DCT's own load order (PlaneView::lat_perm)
         s2k::PlaneView pv = s2k::default_view(p->n);
-        pv.lat_perm = s2k::tma_planes_ok(p, nf);
-        CK(s2k::launch_phi_fft_fwd(p, rd, id, data_stride, p->d_S, nf, fmt, &pv));
+        pv.lat_perm = s2k::tma_planes_ok(p, w0 + nf);
+        CK(s2k::launch_phi_fft_fwd(p, rd, id, data_stride, dS, nf, fmt, &pv));
         // batched: one persistent kernel does the DCTs and the contraction (kernels_uni.cu at bw = 256, kernels_pipe.cu)
         const bool pipe = s2k::fwd_pipe_supported(p, nf, fmt);
         const bool uni = pipe && s2k::fwd_pipe_fused() && s2k::fwd_uni_supported(p, nf, fmt);
         const bool pipe_fused = pipe && s2k::fwd_pipe_fused();
-        if (!pipe_fused) CK(s2k::launch_dct_fwd(p, p->d_S, p->d_X, nf, 0, nrows, fmt, &pv));
+        if (!pipe_fused) CK(s2k::launch_dct_fwd(p, dS, dX, nf, 0, nrows, fmt, &pv));
         for (const OrderGroup& g : order_groups(p, 0, bw)) {
             if (p->variant == S2KIT_CUDA_FLY) CK(s2k::launch_table_gen(p, p->d_table, g.shift, g.lo, g.hi));
             if (uni)
-                CK(s2k::launch_fwd_uni(p, p->d_table, g.shift, p->d_S, rc, ic, coef_stride, nf, g.lo, g.hi, fmt,
+                CK(s2k::launch_fwd_uni(p, p->d_table, g.shift, dS, rc, ic, coef_stride, nf, g.lo, g.hi, fmt,
                                        pv.lat_perm));
             else if (pipe_fused)
-                CK(s2k::launch_fwd_pipe(p, p->d_table, g.shift, p->d_S, rc, ic, coef_stride, nf, g.lo, g.hi, fmt,
+                CK(s2k::launch_fwd_pipe(p, p->d_table, g.shift, dS, rc, ic, coef_stride, nf, g.lo, g.hi, fmt,
                                         pv.lat_perm));
             else if (pipe)
-                CK(s2k::launch_leg_fwd_stream(p, p->d_table, g.shift, p->d_X, rc, ic, coef_stride, nf, g.lo, g.hi, fmt));
+                CK(s2k::launch_leg_fwd_stream(p, p->d_table, g.shift, dX, rc, ic, coef_stride, nf, g.lo, g.hi, fmt));
             else
-                CK(s2k::launch_legendre_fwd(p, p->d_table, g.shift, p->d_X, rc, ic, coef_stride, nf, g.lo, g.hi, fmt));
+                CK(s2k::launch_legendre_fwd(p, p->d_table, g.shift, dX, rc, ic, coef_stride, nf, g.lo, g.hi, fmt));
         }
+    }
+    return 0;
+}
+
+static int inv_fst_sub(s2kit_cuda_plan* p, const double* rc, const double* ic, double* rd, double* id, int nf,
+                       long coef_stride, long data_stride, int fmt, int w0) {
+    const int bw = p->bw, n = p->n;
+    const int nrows = (fmt == S2KIT_REAL) ? bw : 2 * bw - 1;
+    double* dS = p->d_S + (size_t)w0 * 2 * n * n;
+    double* dX = p->d_X + (size_t)w0 * n * 2 * bw;
+    s2k::PlaneView pv = s2k::default_view(p->n);
+    pv.lat_perm = s2k::tma_planes_ok(p, w0 + nf);
+    // batched at bw = 256 (opt-in): contraction and DCT-III in one persistent kernel, the cosine planes stay in shared memory
+    const bool uni = s2k::inv_uni_supported(p, nf, fmt);
+    for (const OrderGroup& g : order_groups(p, 0, bw)) {
+        const double* tt = p->variant == S2KIT_CUDA_FLY ? p->d_table : p->d_table_t;
+        if (p->variant == S2KIT_CUDA_FLY) CK(s2k::launch_table_gen(p, p->d_table, g.shift, g.lo, g.hi, 1));
+        if (uni)
+            CK(s2k::launch_inv_uni(p, tt, g.shift, rc, ic, coef_stride, dS, nf, g.lo, g.hi, fmt, pv.lat_perm));
+        else
+            CK(s2k::launch_legendre_inv(p, tt, g.shift, rc, ic, coef_stride, dX, nf, g.lo, g.hi, fmt));
+    }
+    if (!uni) CK(s2k::launch_dct_inv(p, dX, dS, nf, 0, nrows, fmt, &pv));
+    CK(s2k::launch_phi_fft_inv(p, dS, rd, id, data_stride, nf, fmt, &pv));
+    return 0;
+}
+
+// A chunk of a device call is cut into p->nsplit sub-batches that alternate between the plan's stream and an auxiliary
+// one (S2KIT_CUDA_SPLIT, Memo plans): the HBM-bound kernels (longitude FFTs, DCTs) of one sub-batch can then run beside
+// the FP64-bound contraction of another instead of each kernel having the machine to itself.
+template <typename F>
+static int run_split(s2kit_cuda_plan* p, int nf, F sub) {
+    int ns = (p->variant == S2KIT_CUDA_MEMO) ? p->nsplit : 1;
+    if (ns > 1 && nf < 64 * ns) ns = 1;
+    if (ns <= 1) return sub(0, nf);
+    if (!p->aux_stream) {
+        CK(cudaStreamCreateWithFlags(&p->aux_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+    }
+    const int per = ((nf + ns - 1) / ns + 7) / 8 * 8;  // whole 32-column panels in both data formats
+    cudaStream_t main_stream = p->stream;
+    CK(cudaEventRecord(p->ev_fork, main_stream));
+    CK(cudaStreamWaitEvent(p->aux_stream, p->ev_fork, 0));
+    int rc = 0, i = 0;
+    for (int f0 = 0; f0 < nf && !rc; f0 += per, ++i) {
+        p->stream = (i & 1) ? p->aux_stream : main_stream;
+        rc = sub(f0, std::min(per, nf - f0));
+    }
+    p->stream = main_stream;
+    if (rc) return rc;
+    CK(cudaEventRecord(p->ev_join, p->aux_stream));
+    CK(cudaStreamWaitEvent(main_stream, p->ev_join, 0));
+    return 0;
+}
+
+static int fst_device(s2kit_cuda_plan* p, const double* rdata, const double* idata, double* rco, double* ico,
+                      int batch, long data_stride, long coef_stride, int fmt) {
+    for (int c0 = 0; c0 < batch; c0 += p->chunk) {
+        const int nf = std::min(p->chunk, batch - c0);
+        const int rc = run_split(p, nf, [&](int f0, int n) {
+            const long f = c0 + f0;
+            return fst_sub(p, rdata + f * data_stride, idata + f * data_stride, rco + f * coef_stride, ico + f * coef_stride, n,
+                           data_stride, coef_stride, fmt, f0);
+        });
+        if (rc) return rc;
     }
     return 0;
 }
 
 static int inv_fst_device(s2kit_cuda_plan* p, const double* rco, const double* ico, double* rdata, double* idata,
                           int batch, long coef_stride, long data_stride, int fmt) {
-    const int bw = p->bw;
-    const int nrows = (fmt == S2KIT_REAL) ? bw : 2 * bw - 1;
     for (int c0 = 0; c0 < batch; c0 += p->chunk) {
-        int nf = std::min(p->chunk, batch - c0);
-        const double* rc = rco + (long)c0 * coef_stride;
-        const double* ic = ico + (long)c0 * coef_stride;
-        double* rd = rdata + (long)c0 * data_stride;
-        double* id = idata + (long)c0 * data_stride;
-        s2k::PlaneView pv = s2k::default_view(p->n);
-        pv.lat_perm = s2k::tma_planes_ok(p, nf);
-        // batched at bw = 256: contraction and DCT-III in one persistent kernel, the cosine planes stay in shared memory
-        const bool uni = s2k::inv_uni_supported(p, nf, fmt);
-        for (const OrderGroup& g : order_groups(p, 0, bw)) {
-            const double* tt = p->variant == S2KIT_CUDA_FLY ? p->d_table : p->d_table_t;
-            if (p->variant == S2KIT_CUDA_FLY) CK(s2k::launch_table_gen(p, p->d_table, g.shift, g.lo, g.hi, 1));
-            if (uni)
-                CK(s2k::launch_inv_uni(p, tt, g.shift, rc, ic, coef_stride, p->d_S, nf, g.lo, g.hi, fmt, pv.lat_perm));
-            else
-                CK(s2k::launch_legendre_inv(p, tt, g.shift, rc, ic, coef_stride, p->d_X, nf, g.lo, g.hi, fmt));
-        }
-        if (!uni) CK(s2k::launch_dct_inv(p, p->d_X, p->d_S, nf, 0, nrows, fmt, &pv));
-        CK(s2k::launch_phi_fft_inv(p, p->d_S, rd, id, data_stride, nf, fmt, &pv));
+        const int nf = std::min(p->chunk, batch - c0);
+        const int rc = run_split(p, nf, [&](int f0, int n) {
+            const long f = c0 + f0;
+            return inv_fst_sub(p, rco + f * coef_stride, ico + f * coef_stride, rdata + f * data_stride, idata + f * data_stride,
+                               n, coef_stride, data_stride, fmt, f0);
+        });
+        if (rc) return rc;
     }
     return 0;
 }

@@ -84,6 +84,11 @@ struct s2kit_cuda_plan {
     std::mutex* mu = nullptr;
     bool shares_tables = false;  // a clone: tables / constants belong to the plan it was cloned from
     bool own_table = true;       // d_table is this object's allocation (false for Memo clones)
+    // sub-batches of one device call on two streams (S2KIT_CUDA_SPLIT): HBM-bound and FP64-bound kernels of different
+    // sub-batches overlap
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int nsplit = 1;
     void* host_pipe = nullptr;   // HostPipe (plan.cu): copy streams + events of the host-pointer pipeline, created once
 
     // sharding (single-field multi-GPU); nranks == 1 for ordinary plans
