@@ -10,6 +10,7 @@ size), plus a launch list with durations and the pipe utilisations of every kern
   ncu -i gpurun_out/step.ncu-rep --page raw --csv > /tmp/step.csv; python tools/ncu_traffic.py /tmp/step.csv 256 1024
 """
 import csv
+import re
 import json
 import os
 import sys
@@ -34,13 +35,13 @@ def main():
     kernels, launches = {}, []
     for r in rows[2:]:
         name = r[col["Kernel Name"]]
-        kind = next((v for k, v in KIND.items() if name.startswith(k)), None)
+        kind = next((v for k, v in KIND.items() if re.search(r"(^|[\s:])" + k, name)), None)
         if kind is None:
             continue
         dram = val(r, "dram__bytes_read.sum", "bytes") + val(r, "dram__bytes_write.sum", "bytes")
-        ent = {"kernel": name.split("(")[0], "functions_per_launch": nfun, "dram_bytes_per_launch": dram,
+        ent = {"kernel": name.split("(")[0].replace("void ", ""), "functions_per_launch": nfun, "dram_bytes_per_launch": dram,
                "dram_read_bytes": val(r, "dram__bytes_read.sum", "bytes"), "dram_write_bytes": val(r, "dram__bytes_write.sum", "bytes"),
-               "duration_us_under_ncu": val(r, "gpu__time_duration.sum"),
+               "duration_under_ncu": val(r, "gpu__time_duration.sum"), "duration_unit": units[col["gpu__time_duration.sum"]],
                "fp64_pipe_pct": val(r, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
                "dmma_pipe_pct": val(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
                "lsu_wavefronts_pct": val(r, "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
