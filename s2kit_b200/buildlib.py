@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libs2kit_cuda.so")
 
-CU = ["kernels_fft.cu", "kernels_legendre.cu", "kernels_table.cu", "kernels_misc.cu", "kernels_pipe.cu", "kernels_uni.cu", "kernels_fft16.cu", "plan.cu", "shard.cu", "multi.cu"]
+CU = ["kernels_fft.cu", "kernels_legendre.cu", "kernels_table.cu", "kernels_misc.cu", "kernels_pipe.cu", "kernels_uni.cu", "kernels_flow.cu", "kernels_fft16.cu", "plan.cu", "shard.cu", "multi.cu"]
 C = ["host_setup.c", "s2kit_compat.c"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

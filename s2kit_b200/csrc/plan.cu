@@ -250,6 +250,32 @@ static void build_inv_subitems(s2kit_cuda_plan* p, std::vector<int>& off, std::v
     }
 }
 
+// inverse, persistent contraction kernel (kernels_flow.cu): units of FOUR adjacent column tiles of one parity block
+static void build_invq_subitems(s2kit_cuda_plan* p, std::vector<int>& off, std::vector<unsigned short>& list) {
+    const int bw = p->bw, nct = (((bw + 1) / 2) + 7) >> 3;
+    off.assign(1, 0);
+    list.clear();
+    for (int m = 0; m < bw; ++m) {
+        std::vector<std::pair<int, int>> items;  // code = parity | quad << 1
+        for (int par = 0; par < 2; ++par) {
+            const s2k::BlockMeta& mb = p->h_meta[2 * m + par];
+            auto tiles = [&](int rt) { return (mb.len0 + std::min(8 * rt + 7, mb.rows - 1) + 7) >> 3; };
+            auto reach = [&](int ct) {
+                int rt_min = 0;
+                if (8 * ct >= mb.len0 + 7) rt_min = (8 * ct - mb.len0 - 7) / 8 + 1;
+                while (rt_min < mb.nrt && ct >= tiles(rt_min)) ++rt_min;
+                return std::max(0, mb.nrt - rt_min);
+            };
+            for (int q = 0; 4 * q < nct; ++q) {
+                int cost = 0;  // DMMA column-tile steps of the quad
+                for (int c = 4 * q; c < std::min(nct, 4 * q + 4); ++c) cost += reach(c);
+                items.push_back({cost, par | (q << 1)});
+            }
+        }
+        lpt_queues(items, off, list);
+    }
+}
+
 // Keep a Memo table that fits comfortably in L2 resident across launches: the batch streams hundreds of MB through
 // L2 between two uses of the same order's tiles (persisting-L2 access policy window on the plan's stream).
 static void apply_table_l2_policy(s2kit_cuda_plan* p) {
@@ -440,6 +466,10 @@ static int plan_build(s2kit_cuda_plan* p, int bw, int variant, int max_batch, in
         p->n_isub_list = (int)list.size();
         CK(upload(p->stream, &p->d_isub_off, off.data(), off.size()));
         CK(upload(p->stream, &p->d_isub_list, list.data(), list.size()));
+        build_invq_subitems(p, off, list);
+        p->n_iq_list = (int)list.size();
+        CK(upload(p->stream, &p->d_iq_off, off.data(), off.size()));
+        CK(upload(p->stream, &p->d_iq_list, list.data(), list.size()));
     }
     CK(s2k::launch_rec_coeffs(p));
 
@@ -518,7 +548,7 @@ extern "C" int s2kit_cuda_plan_destroy(s2kit_cuda_plan* p) {
     // tables and constants of a clone belong to the plan it was cloned from
     void* shared[] = {p->d_wv, p->d_sv, p->d_weights, p->d_sin, p->d_tw_n, p->d_tw_b, p->d_q_n, p->d_q_b, p->d_nodes,
                       p->d_seeds, p->d_rec, p->d_meta, p->d_rt_start, p->d_order_start, p->d_units,
-                      p->d_sub_off,  p->d_sub_list, p->d_isub_off, p->d_isub_list};
+                      p->d_sub_off,  p->d_sub_list, p->d_isub_off, p->d_isub_list, p->d_iq_off, p->d_iq_list};
     void* own[] = {p->d_S, p->d_X, p->d_coef, p->d_coef2, p->d_filt, p->d_stage};
     if (!p->shares_tables)
         for (void* q : shared)
@@ -692,11 +722,15 @@ static int inv_fst_sub(s2kit_cuda_plan* p, const double* rc, const double* ic, d
     pv.lat_perm = s2k::tma_planes_ok(p, w0 + nf);
     // batched at bw = 256 (opt-in): contraction and DCT-III in one persistent kernel, the cosine planes stay in shared memory
     const bool uni = s2k::inv_uni_supported(p, nf, fmt);
+    // batched at bw = 256: the contraction as a persistent kernel (kernels_flow.cu)
+    const bool flow = !uni && s2k::inv_flow_supported(p, nf, fmt);
     for (const OrderGroup& g : order_groups(p, 0, bw)) {
         const double* tt = p->variant == S2KIT_CUDA_FLY ? p->d_table : p->d_table_t;
         if (p->variant == S2KIT_CUDA_FLY) CK(s2k::launch_table_gen(p, p->d_table, g.shift, g.lo, g.hi, 1));
         if (uni)
             CK(s2k::launch_inv_uni(p, tt, g.shift, rc, ic, coef_stride, dS, nf, g.lo, g.hi, fmt, pv.lat_perm));
+        else if (flow)
+            CK(s2k::launch_inv_flow(p, tt, g.shift, rc, ic, coef_stride, dX, nf, g.lo, g.hi, fmt));
         else
             CK(s2k::launch_legendre_inv(p, tt, g.shift, rc, ic, coef_stride, dX, nf, g.lo, g.hi, fmt));
     }

@@ -128,6 +128,9 @@ struct s2kit_cuda_plan {
     int* d_isub_off = nullptr;
     unsigned short* d_isub_list = nullptr;  // inverse: parity | column tile << 1 | pair << 12
     int n_isub_list = 0;
+    int* d_iq_off = nullptr;               // persistent inverse contraction (kernels_flow.cu)
+    unsigned short* d_iq_list = nullptr;   // parity | quad << 1 (four adjacent column tiles)
+    int n_iq_list = 0;
     // table-generator work units (order, first degree)
     int* d_units = nullptr;  // pairs (m, l0)
     std::vector<int> h_units;
@@ -223,6 +226,11 @@ bool inv_uni_supported(const s2kit_cuda_plan* p, int nfun, int data_format);
 cudaError_t launch_inv_uni(s2kit_cuda_plan* p, const double* table_t, uint64_t table_shift, const double* rco,
                            const double* ico, long coef_stride, double* G, int nfun, int m_lo, int m_hi, int data_format,
                            int lat_perm);
+
+// K4 as a persistent kernel at bw = 256, batched (kernels_flow.cu); S2KIT_CUDA_FLOW=0 falls back to k_legendre_inv
+bool inv_flow_supported(const s2kit_cuda_plan* p, int nfun, int data_format);
+cudaError_t launch_inv_flow(s2kit_cuda_plan* p, const double* table_t, uint64_t table_shift, const double* rco,
+                            const double* ico, long coef_stride, double* V, int nfun, int m_lo, int m_hi, int data_format);
 
 bool fwd_pipe_fused();  // default: the DCT runs inside the persistent kernel; S2KIT_CUDA_PIPE=1: K2 + streamed K3
 // K3 as a persistent kernel with cp.async-streamed table tiles (kernels_pipe.cu); X = K2's cosine planes
