@@ -315,10 +315,15 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) k_inv_flow(const FlowInvArgs 
 }
 
 // ------------------------------------------------------------------------------------------------ launcher
+// Opt-in (S2KIT_CUDA_FLOW=1).  Measured at bw = 256, 1024 functions: 1.80 ms against 1.19 ms for k_legendre_inv<32,32>.
+// The DMMA phase itself is lean (LSU data pipe 31 % busy against 70 %), but the pipe is only 43 % busy: an item has eight
+// units of very unequal length (16 / 12 / 8 / 4 row-tile steps at m = 0) for sixteen warps, its critical path is the longest
+// unit (16 steps x 32 DMMAs), and with two panel buffers the staging of item k + 1 cannot start before the last unit of
+// item k - 1 has finished -- 40 % of the warp samples sit in the dependency polls (profiles/r2_ncu_flow_summary.md).
 static bool flow_enabled() {
     static int on = [] {
         const char* e = getenv("S2KIT_CUDA_FLOW");
-        return (e && e[0] == '0') ? 0 : 1;
+        return (e && e[0] == '1') ? 1 : 0;
     }();
     return on != 0;
 }
