@@ -244,7 +244,7 @@ def _event_ms(torch, fn, warmup, steps, barrier):
     return e0.elapsed_time(e1) / steps
 
 
-def single_field_block(a, torch, dist, s2, world, rank, local, dev, hbm_peak):
+def single_field_block(a, torch, dist, s2, world, rank, local, dev, hbm_peak, cpu_group=None):
     """The second half of BASELINE.json's metric: ONE field at bw = 2048 (configs[4], FSTSemiMemo with m-sharded tables).
     N = 1: the whole 11.7 GB table streams through one GPU per transform.  N > 1 (torchrun): (a) every rank runs its
     share, ring -> order exchange by NCCL all_to_all; (b) rank 0 alone drives all N GPUs through the in-library
@@ -355,9 +355,13 @@ def single_field_block(a, torch, dist, s2, world, rank, local, dev, hbm_peak):
             "forward_rel_err_vs_reference_sample": sample_err(full_r.cpu().numpy(), full_i.cpu().numpy())}
     out["nccl_all_to_all"] = nccl
     P.close()
-    del send, recv
+    del send, recv, my_r, my_i, out_r, out_i
+    torch.cuda.empty_cache()
     barrier()
-    # ---- (b) rank 0 drives all GPUs through the C-ABI (s2kit_cuda_multi_*): no NCCL, the DCT kernels do the exchange
+    # ---- (b) rank 0 drives all GPUs through the C-ABI (s2kit_cuda_multi_*): no NCCL, the DCT kernels do the exchange.
+    # The other ranks must leave their GPUs idle meanwhile: they wait on a CPU (gloo) barrier -- an NCCL barrier would keep
+    # a spinning kernel of another process on every GPU, and the time-slicing between the two contexts doubled the measured
+    # time of this path (2.67 vs 1.22 ms forward on two GPUs, profiles/r2_multi_stage_times.txt)
     if rank == 0:
         try:
             M = s2.MultiPlan(bw, world)
@@ -384,6 +388,8 @@ def single_field_block(a, torch, dist, s2, world, rank, local, dev, hbm_peak):
             M.close()
         except Exception as ex:  # noqa: BLE001 -- e.g. no peer access on this box: report, do not lose the line
             out["in_library_p2p"] = {"unavailable": repr(ex)[:300]}
+    if cpu_group is not None:
+        dist.barrier(group=cpu_group)
     barrier()
     best = out["nccl_all_to_all"]
     if rank == 0 and "ms_forward" in out.get("in_library_p2p", {}):
@@ -419,6 +425,7 @@ def run_ours(a):
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
+    cpu_group = dist.new_group(backend="gloo") if world > 1 else None  # host-side barrier (single_field_block)
     fmt = s2.COMPLEX if a.format == "complex" else s2.REAL
     bw, n, batch = a.bw, 2 * a.bw, a.batch
 
@@ -606,7 +613,7 @@ def run_ours(a):
         del rd, idt, rc2, ic2
         torch.cuda.empty_cache()
         try:
-            single = single_field_block(a, torch, dist, s2, world, rank, local, dev, hbm_peak)
+            single = single_field_block(a, torch, dist, s2, world, rank, local, dev, hbm_peak, cpu_group)
         except Exception as ex:  # noqa: BLE001 -- never lose the headline line to the second block
             single = {"error": repr(ex)[:400]}
 

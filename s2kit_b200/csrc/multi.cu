@@ -15,6 +15,7 @@
 // the ring buffers are double-buffered so back-to-back transforms need no further synchronisation (see the comments
 // in run_forward / run_inverse).  One host thread per GPU enqueues its device's work, so launch overhead does not
 // serialise over the devices.
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -124,6 +125,36 @@ namespace {
         }                                                                 \
     } while (0)
 
+// S2KIT_CUDA_MULTI_PROF=1: CUDA events between the stages of the LAST transform of a job, printed per device (diagnostics)
+static bool multi_prof() {
+    static int on = [] {
+        const char* e = getenv("S2KIT_CUDA_MULTI_PROF");
+        return (e && e[0] == '1') ? 1 : 0;
+    }();
+    return on != 0;
+}
+struct StageProf {
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int n = 0;
+    void mark(cudaStream_t s) {
+        if (n >= 6) return;
+        if (!ev[n]) cudaEventCreate(&ev[n]);
+        cudaEventRecord(ev[n++], s);
+    }
+    void report(int g, const char* const* names) {
+        char line[256];
+        int at = snprintf(line, sizeof line, "[s2kit multi] gpu %d:", g);
+        for (int i = 0; i + 1 < n; ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+            at += snprintf(line + at, sizeof line - at, " %s %.3f ms", names[i], ms);
+        }
+        fprintf(stderr, "%s\n", line);
+        n = 0;
+    }
+};
+static StageProf g_prof[s2k::S2K_MAX_PEERS];
+
 // forward on device g, generation `gen` of the ring buffers.
 // Safety of reusing ringbuf[gen & 1] without extra events: K1_s(i+2) follows K2_s(i+1) in s's stream, K2_s(i+1) waited
 // for every K1_d(i+1), and K1_d(i+1) follows K2_d(i) -- the last reader of generation i on any device -- in d's stream.
@@ -140,11 +171,15 @@ void run_forward(s2kit_cuda_multi* mp, int g, unsigned gen, bool first, bool las
         }
         MCK(d, cudaEventRecord(d.ev_start, s));
     }
+    const bool prof = last && multi_prof();
+    if (prof) g_prof[g].mark(s);
     MCK(d, s2k::launch_phi_fft_fwd(p, d.ring_r, d.ring_i, 0, d.ringbuf[b], 1, S2KIT_COMPLEX, &st->ring_view));
     MCK(d, cudaEventRecord(d.ev_x[b], s));
+    if (prof) g_prof[g].mark(s);
     mp->bar.wait();  // every device has recorded its K1 event of this generation
     for (int q = 0; q < mp->G; ++q)
         if (q != g) MCK(d, cudaStreamWaitEvent(s, mp->dev[q].ev_x[b], 0));
+    if (prof) g_prof[g].mark(s);
     s2k::PlaneView ov = st->order_view;
     s2k::PeerSegs peers;
     memset(&peers, 0, sizeof(peers));
@@ -152,8 +187,10 @@ void run_forward(s2kit_cuda_multi* mp, int g, unsigned gen, bool first, bool las
     ov.peers = &peers;
     // K2 pulls its rows out of the peers' K1 output: the exchange rides on the kernel's own loads
     MCK(d, s2k::launch_dct_fwd(p, d.ringbuf[b], p->d_X, 1, 0, st->nrows_real, S2KIT_COMPLEX, &ov));
+    if (prof) g_prof[g].mark(s);
     MCK(d, s2k::launch_legendre_fwd(p, p->d_table, 0, p->d_X, d.coef_r, d.coef_i, (long)bw * bw, 1, 0, st->norders,
                                     S2KIT_COMPLEX, st->d_orders));
+    if (prof) g_prof[g].mark(s);
     // (ev_x[b] is recorded again two generations later; by then every peer has passed the barrier of the generation in
     // between, i.e. has long enqueued its wait on this record)
     if (last) {
@@ -185,8 +222,11 @@ void run_inverse(s2kit_cuda_multi* mp, int g, unsigned gen, bool first, bool las
         }
         MCK(d, cudaEventRecord(d.ev_start, s));
     }
+    const bool prof = last && multi_prof();
+    if (prof) g_prof[g].mark(s);
     MCK(d, s2k::launch_legendre_inv(p, p->d_table_t, 0, d.coef_r, d.coef_i, (long)bw * bw, p->d_X, 1, 0, st->norders,
                                     S2KIT_COMPLEX, st->d_orders));
+    if (prof) g_prof[g].mark(s);
     s2k::PlaneView ov = st->order_view;
     s2k::PeerSegs peers;
     memset(&peers, 0, sizeof(peers));
@@ -194,10 +234,13 @@ void run_inverse(s2kit_cuda_multi* mp, int g, unsigned gen, bool first, bool las
     ov.peers = &peers;
     MCK(d, s2k::launch_dct_inv(p, p->d_X, d.ringbuf[b], 1, 0, st->nrows_real, S2KIT_COMPLEX, &ov));
     MCK(d, cudaEventRecord(d.ev_x[b], s));
+    if (prof) g_prof[g].mark(s);
     mp->bar.wait();
     for (int q = 0; q < mp->G; ++q)
         if (q != g) MCK(d, cudaStreamWaitEvent(s, mp->dev[q].ev_x[b], 0));
+    if (prof) g_prof[g].mark(s);
     MCK(d, s2k::launch_phi_fft_inv(p, d.ringbuf[b], d.ring_r, d.ring_i, 0, 1, S2KIT_COMPLEX, &st->ring_view));
+    if (prof) g_prof[g].mark(s);
     if (last) {
         MCK(d, cudaEventRecord(d.ev_stop, s));
         if (job.host_io) {
@@ -230,6 +273,11 @@ void worker(s2kit_cuda_multi* mp, int g) {
                 run_inverse(mp, g, gen0 + it, it == 0, it == job.iters - 1, job);
         }
         MCK(d, cudaStreamSynchronize(d.plan->stream));
+        if (multi_prof() && g_prof[g].n) {
+            static const char* const fwd_names[] = {"K1", "peer wait", "K2 (pull)", "K3", ""};
+            static const char* const inv_names[] = {"K4", "K5 (push)", "peer wait", "K6", ""};
+            g_prof[g].report(g, job.kind == JOB_FWD ? fwd_names : inv_names);
+        }
         d.ms = 0.f;
         if (!d.status) cudaEventElapsedTime(&d.ms, d.ev_start, d.ev_stop);
         {
