@@ -73,7 +73,9 @@ void DLTNaive(double* data, const int bw, const int m, double* weights, double* 
               double* workspace);
 void InvDLTNaive(double* coeffs, const int bw, const int m, double* result, double* pml_table);
 
-/* include/s2kit/pmm.h:4 */
+/* include/s2kit/pmm.h:4.  Same libm expression as the reference (bit-identical) wherever the reference is finite; for
+ * m >= 2044 the reference's product overflows and it returns NaN -- here the 2^(-m/2) factor is folded into the product
+ * so the result is the finite value of the definition (checked against mpmath, tests/golden/mp_high_orders.npz). */
 void Pmm_L2(const int m, double* eval_points, const int n, double* result);
 
 /* include/s2kit/chebyshev_nodes.h:4-6 */

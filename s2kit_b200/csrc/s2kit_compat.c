@@ -260,6 +260,13 @@ void Pmm_L2(const int m, double* eval_points, const int n, double* result) {
     double c = sqrt(m + 0.5);
     for (int i = 0; i < m; ++i) c *= sqrt((m - (i / 2.)) / ((double)m - i));
     if (m) c *= pow(2., -m / 2.);
+    if (!isfinite(c)) {
+        /* m >= 2044: the reference's running product overflows before 2^(-m/2) is applied and it returns NaN.  Only there
+           the factor is folded into the product (as s2k_host_seeds does for the device tables); validated against mpmath
+           (tests/golden/mp_high_orders.npz).  Smaller orders keep the reference's exact arithmetic. */
+        c = sqrt(m + 0.5);
+        for (int i = 0; i < m; ++i) c *= sqrt((m - (i / 2.)) / ((double)m - i)) * M_SQRT1_2;
+    }
     if (m % 2) c *= -1.;
     for (int i = 0; i < n; ++i) result[i] = c * pow(sin(eval_points[i]), m);
 }

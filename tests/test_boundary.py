@@ -84,6 +84,20 @@ def test_host_seeds_bit_identical_to_oracle(s2, oracle_mod):
         assert np.array_equal(s2.GenerateWeightsForDLT(bw), O.weights())
 
 
+def test_pmm_l2_is_finite_where_the_reference_overflows(s2):
+    """Pmm_L2 (pmm.c:21-33) through the drop-in symbol: bit-identical to the reference's expression where that is finite
+    (covered by the table tests); for m >= 2044 the reference's running product overflows to inf -- ours re-associates
+    only there and must reproduce the exact values (mpmath, tests/golden/mp_high_orders.npz)."""
+    mp = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mp_high_orders.npz"))
+    bw = int(mp["bw"])
+    theta = (2 * np.arange(2 * bw) + 1) * np.pi / (4 * bw)
+    for m in range(2040, 2048):
+        got = s2.Pmm_L2(m, theta)
+        want = mp[f"m{m}_pmm"]
+        assert np.isfinite(got).all(), m
+        assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max(), (m, np.abs(got - want).max())
+
+
 def test_compute_fails_loudly_without_gpu(s2):
     import torch
 

@@ -109,6 +109,24 @@ def test_c5_bw2048_dlt_vs_reference(large, plan2048):
         assert relerr(plan2048.inv_dlt_semi(co, m)[0], large[f"bw2048_invdlt_m{m}"]) < TOL, m
 
 
+def test_bw2048_orders_beyond_the_reference_vs_mpmath(plan2048):
+    """Orders m >= 2044 at bw = 2048: the reference's Pmm_L2 overflows (pmm.c:21-33) and its transforms return NaN, so the
+    committed reference samples cannot pin them.  tests/golden/mp_high_orders.npz holds the exact transforms of seeded
+    columns for m = 2040..2047, evaluated with mpmath (60 digits) from the reference's own definitions and cross-checked
+    against the reference where it is finite (make_golden_mp.py: every order at bw = 24 to 3e-15, m = 2042 / 2043 at
+    bw = 2048 to 2e-14 / 1.4e-13)."""
+    mp = np.load(os.path.join(GOLDEN, "mp_high_orders.npz"))
+    bw = int(mp["bw"])
+    for m in (int(v) for v in mp["orders"]):
+        got = plan2048.dlt_semi(mp[f"m{m}_data"], m)[0]
+        assert np.isfinite(got).all(), m
+        assert relerr(got, mp[f"m{m}_dlt"]) < TOL, (m, relerr(got, mp[f"m{m}_dlt"]))
+        back = plan2048.inv_dlt_semi(mp[f"m{m}_coeffs"], m)[0]
+        assert np.isfinite(back).all(), m
+        assert relerr(back, mp[f"m{m}_inv"]) < TOL, (m, relerr(back, mp[f"m{m}_inv"]))
+        assert len(got) == bw - m
+
+
 def test_c5_bw2048_inverse_vs_composed_reference(s2, oracle_mod, large, plan2048):
     """InvFSTSemiMemo at bw = 2048.  The reference's own 2-D inverse is NaN everywhere at this size; the golden is
     composed from its per-order InvDLTSemi for |m| <= 2043 (make_golden_large.py), input = seed-1000 coefficients

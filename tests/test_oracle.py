@@ -148,3 +148,23 @@ def test_port_matches_reference_samples_bw512(oracle_mod):
     # the bw = 2048 fixtures: the reference returns NaN exactly for the eight orders |m| >= 2044 (pmm.c:22-30)
     assert sorted(int(m) for m in large["bw2048_ref_nan_orders"]) == [-2047, -2046, -2045, -2044, 2044, 2045, 2046, 2047]
     assert np.isfinite(large["bw2048_inv_sample_r"]).all()
+
+
+def test_mpmath_fixture_agrees_with_the_reference_where_it_is_finite():
+    """tests/golden/mp_high_orders.npz (make_golden_mp.py) pins the orders the reference cannot compute at bw = 2048.  Its
+    cross-check entries -- the mpmath DLT / inverse DLT of the SAME seeded columns make_golden_large.py fed to the
+    reference's DLTSemi / InvDLTSemi at m = 2042, 2043 -- must agree with the committed reference outputs."""
+    import os
+
+    from conftest import GOLDEN
+
+    mp = np.load(os.path.join(GOLDEN, "mp_high_orders.npz"))
+    large = np.load(os.path.join(GOLDEN, "oracle_vectors_large.npz"))
+    for m in (2042, 2043):
+        a, b = mp[f"crosscheck_m{m}_dlt"], large[f"bw2048_dlt_m{m}"]
+        assert np.abs(a - b).max() / np.abs(a).max() < 1e-11
+        a, b = mp[f"crosscheck_m{m}_inv"], large[f"bw2048_invdlt_m{m}"]
+        assert np.abs(a - b).max() / np.abs(a).max() < 1e-11
+    # the quadrature weights of the fixture are the reference's (weights.c:32-47) to the last bits
+    w = mp["weights"]
+    assert abs(w.sum() - 2.0) < 1e-13  # the weights integrate 1 over [-1, 1]
