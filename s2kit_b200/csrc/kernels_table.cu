@@ -119,6 +119,148 @@ __global__ void __launch_bounds__(NB / 8 * G) k_table_gen(double* __restrict__ t
     }
 }
 
+
+// ---- K7 on the HALF grid (bw >= 1024) ------------------------------------------------------------------------------
+// P~_l^m(cos theta) is symmetric (l - m even) or antisymmetric (l - m odd) about the equator, which is why a table row only
+// keeps every other cosine index.  The reference (cospml.c:203-224) -- and k_table_gen above -- still take a full
+// length-bw DCT-II of every row and throw half of the outputs away.  With a[i] the samples on the first bw/2 nodes:
+//   symmetric row      X[2j]     = 2 * sum_{i < bw/2} a[i] cos(pi j (2i+1) / bw)             = 2 DCT-II_{bw/2}(a)[j]
+//   antisymmetric row  X[2j + 1] = 2 * sum_{i < bw/2} a[i] cos(pi (2j+1)(2i+1) / (2 bw))     = 2 DCT-IV_{bw/2}(a)[j]
+// so the recurrence runs on HALF the nodes and a step of FOUR degrees costs one complex FFT of length bw/2 (the two
+// symmetric rows as real and imaginary part, separated by conjugate symmetry as before) plus two complex FFTs of length
+// bw/4 (one DCT-IV each: u[n] = a[2n] + i a[M-1-2n], pre-twiddle e^{-i pi (4n+1)/(4M)}, FFT, post-twiddle e^{-i pi k/M},
+// D[2k] = Re, D[M-1-2k] = -Im; M = bw/2) instead of two complex FFTs of length bw: 2.4x fewer FFT flops, half the
+// recurrence, a third of the shared-memory traffic (k_table_gen<1024> ran the LSU data pipe at 75 %, the FP64 pipe at
+// 53 %: profiles/r2_fly_bw1024.json).  The samples are the reference's bit for bit (same seeds, same recurrence); what
+// changes is the rounding inside the cosine transform, as it already did against FFTW.
+// Group = bw/16 threads (8 half-grid nodes each, in the even/odd-reordered order the length-bw/2 DCT-II FFT loads); the
+// lower / upper half of the group runs the DCT-IV transform of the first / second antisymmetric row.
+template <int NB, int G>
+__global__ void __launch_bounds__(NB / 16 * G, 512 / (NB / 16 * G)) k_table_gen_half(double* __restrict__ table,
+                                                                const uint64_t* __restrict__ order_start, uint64_t shift,
+                                                                const BlockMeta* __restrict__ meta,
+                                                                const uint32_t* __restrict__ rt_start,
+                                                                const int* __restrict__ units, int unit_lo, int unit_hi,
+                                                                int lch, int transposed, const double* __restrict__ nodes,
+                                                                const double* __restrict__ seeds,
+                                                                const double2* __restrict__ rec,
+                                                                const double2* __restrict__ tw,
+                                                                const double2* __restrict__ qtab) {
+    constexpr int M = NB / 2, K = NB / 4, T = NB / 16, TH = T / 2;
+    constexpr int LA = fft_padded_len(M), LB = fft_padded_len(K);
+    static_assert(TH >= 32, "the DCT-IV transforms are owned by whole warps");
+    extern __shared__ double2 smem2[];
+    const int tid = threadIdx.x, g = tid / T, t = tid % T;
+    const int half = t / TH, th = t % TH;
+    double2* sa = smem2 + g * (LA + 2 * LB);  // exchange row of the length-M transform
+    double2* sb = sa + LA;                    // DCT-IV inputs / exchange rows: first row, then second row
+    int u = unit_lo + blockIdx.x * G + g;
+    const bool live = u < unit_hi;
+    if (!live) u = unit_lo;
+    const int m = units[2 * u], l0 = units[2 * u + 1];
+    const BlockMeta mb0 = meta[2 * m], mb1 = meta[2 * m + 1];
+    const uint64_t tile0 = order_start[m] - shift;
+
+    double x[8], prev[8], cur[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int p = t + e * T;
+        const int i = (p < M / 2) ? 2 * p : 2 * (M - 1 - p) + 1;  // even/odd reordering of the length-M DCT-II input
+        x[e] = __ldg(nodes + i);
+        cur[e] = __ldg(seeds + (long)m * NB + i);
+        prev[e] = 0.0;
+    }
+    const double2* rc = rec + (long)m * NB;
+    {
+        double2 ac = __ldg(rc + m);
+        for (int l = m; l < l0; ++l) {
+            const double2 nx = __ldg(rc + min(l + 1, NB - 1));
+            rec_step(x, prev, cur, ac);
+            ac = nx;
+        }
+    }
+    // pre-twiddles of the DCT-IV inputs n = t + e T, e < 4: (cos, sin)(pi (4n+1) / (2 bw))
+    double2 pre[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) pre[e] = __ldg(qtab + 4 * (t + e * T) + 1);
+    // row in registers -> pre-twiddled DCT-IV input: node 2n sits in register e, node M-1-2n in register e + 4
+    auto stage_antisym = [&](double2* dst, bool have) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const double ur = have ? cur[e] : 0.0, ui = have ? cur[e + 4] : 0.0;
+            dst[fft_pad(t + e * T)] = make_double2(ur * pre[e].x + ui * pre[e].y, ui * pre[e].x - ur * pre[e].y);
+        }
+    };
+
+    const double fudge = 1.0 / sqrt((double)NB);  // cospml.c:206
+    for (int quad = 0; quad < lch / 4; ++quad) {
+        const int l = l0 + 4 * quad;
+        if (l >= NB) break;  // uniform inside the group; every barrier below is the group's own
+        const int ra = (l - m) >> 1;  // row of degree l (parity 0) and of degree l + 1 (parity 1) in their blocks
+        double xr[8], xi[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) xr[e] = cur[e];
+        if (l + 1 < NB) rec_step(x, prev, cur, __ldg(rc + l));
+        stage_antisym(sb, l + 1 < NB);
+        if (l + 2 < NB) rec_step(x, prev, cur, __ldg(rc + l + 1));
+#pragma unroll
+        for (int e = 0; e < 8; ++e) xi[e] = (l + 2 < NB) ? cur[e] : 0.0;
+        if (l + 3 < NB) rec_step(x, prev, cur, __ldg(rc + l + 2));
+        stage_antisym(sb + LB, l + 3 < NB);
+        if (l + 4 < NB) rec_step(x, prev, cur, __ldg(rc + l + 3));
+
+        // ---- the two symmetric rows: one complex FFT of length M
+        fft_block<M, 2>(xr, xi, sa, t, g, tw);
+        fft_sync<M>(g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sa[fft_pad(fft_out_index<M>(e, t))] = make_double2(xr[e], xi[e]);
+        fft_sync<M>(g);
+        if (live) {
+            const int len_a = mb0.len0 + ra, len_b = (l + 2 < NB) ? mb0.len0 + ra + 1 : 0;
+            for (int j = t; j < M; j += T) {
+                if (j >= len_a && j >= len_b) break;
+                const int nj = (M - j) & (M - 1);
+                const double2 za = sa[fft_pad(j)], zb = sa[fft_pad(nj)];
+                const double2 q = __ldg(qtab + 2 * j);  // (cos, sin)(pi j / 2M)
+                double scale = 2.0 * fudge;
+                if (j == 0) scale *= 0.70710678118654752440;  // cospml.c:205
+                if (j < len_a)
+                    tile_store(table, tile0, mb0, rt_start, ra, j, (q.x * (za.x + zb.x) + q.y * (za.y - zb.y)) * scale, transposed);
+                if (j < len_b)
+                    tile_store(table, tile0, mb0, rt_start, ra + 1, j, (q.x * (za.y + zb.y) - q.y * (za.x - zb.x)) * scale,
+                               transposed);
+            }
+        }
+        // ---- the two antisymmetric rows: one DCT-IV each, lower / upper half of the group.  (The barriers inside the
+        // transform above came after every thread's stage_antisym stores.)
+        {
+            double2* sx = sb + half * LB;
+            double yr[8], yi[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const double2 v = sx[fft_pad(th + e * (K / 8))];
+                yr[e] = v.x;
+                yi[e] = v.y;
+            }
+            fft_block<K, 4>(yr, yi, sx, th, G + 2 * g + half, tw);
+            const int lrow = l + 1 + 2 * half, rrow = ra + half;
+            if (live && lrow < NB) {
+                const int len = mb1.len0 + rrow;
+                const double scale = 4.0 * fudge;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int k = fft_out_index<K>(e, th);
+                    const double2 q = __ldg(qtab + 4 * k);  // (cos, sin)(pi k / M)
+                    const int c0 = 2 * k, c1 = M - 1 - 2 * k;
+                    if (c0 < len) tile_store(table, tile0, mb1, rt_start, rrow, c0, (yr[e] * q.x + yi[e] * q.y) * scale, transposed);
+                    if (c1 < len) tile_store(table, tile0, mb1, rt_start, rrow, c1, (yr[e] * q.y - yi[e] * q.x) * scale, transposed);
+                }
+            }
+        }
+        fft_sync<M>(g);  // sa / sb are rewritten by the next step
+    }
+}
+
 // Any bandwidth: one CTA per order, thread i owns the nodes i, i + blockDim, ... (two per thread above bw = 1024), DCT by
 // the O(bw^2) definition.  Used for bandwidths that are not powers of two (the reference accepts any bw).
 constexpr int DIRECT_NODES = 2;
@@ -233,6 +375,23 @@ static cudaError_t table_gen_nb(s2kit_cuda_plan* p, double* table, uint64_t shif
         if (e != cudaSuccess) return e;
     }
     int nunits = unit_hi - unit_lo;
+    if constexpr (NB >= 1024) {
+        // half-grid generator (S2KIT_CUDA_TABLE_FULL=1 keeps the full-length transforms for comparison)
+        static const int full = [] {
+            const char* e = getenv("S2KIT_CUDA_TABLE_FULL");
+            return (e && e[0] == '1') ? 1 : 0;
+        }();
+        if (!full && lch % 4 == 0) {
+            constexpr int TG = NB / 16, GH = 128 / TG < 1 ? 1 : 128 / TG;
+            const size_t smem_h = sizeof(double2) * GH * (fft_padded_len(NB / 2) + 2 * fft_padded_len(NB / 4));
+            cudaError_t e = ensure_smem(reinterpret_cast<const void*>(k_table_gen_half<NB, GH>), smem_h);
+            if (e != cudaSuccess) return e;
+            k_table_gen_half<NB, GH><<<(nunits + GH - 1) / GH, TG * GH, smem_h, p->stream>>>(
+                table, p->d_order_start, shift, p->d_meta, p->d_rt_start, p->d_units, unit_lo, unit_hi, lch, transposed,
+                p->d_nodes, p->d_seeds, p->d_rec, p->d_tw_b, p->d_q_b);
+            return cudaGetLastError();
+        }
+    }
     k_table_gen<NB, G><<<(nunits + G - 1) / G, T8 * G, smem, p->stream>>>(
         table, p->d_order_start, shift, p->d_meta, p->d_rt_start, p->d_units, unit_lo, unit_hi, lch, transposed, p->d_nodes,
         p->d_seeds, p->d_rec, p->d_tw_b, p->d_q_b);

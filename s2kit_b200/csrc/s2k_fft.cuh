@@ -110,10 +110,11 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
 // Twiddles: ONE table load per butterfly (w = W^(k*STEP)); the higher powers w^2..w^7 are formed by at most
 // three chained complex multiplications.  (Loading all seven from the table cost 7 scattered 16-byte L1
 // requests per thread and pass and saturated the LSU data pipe -- profiles/r1_ncu_summary.md.)
-template <int N, int NS, int R>
+// TWMUL: the table passed in belongs to a transform TWMUL times longer (W_N^q = table[q * TWMUL])
+template <int N, int NS, int R, int TWMUL = 1>
 __device__ __forceinline__ void fft_pass_compute(double (&xr)[8], double (&xi)[8], int t,
                                                  const double2* __restrict__ tw) {
-    constexpr int T8 = N / 8, NB = 8 / R, STEP = N / (NS * R);
+    constexpr int T8 = N / 8, NB = 8 / R, STEP = TWMUL * (N / (NS * R));
 #pragma unroll
     for (int q = 0; q < NB; ++q) {
         if constexpr (NS > 1) {
@@ -167,7 +168,7 @@ __device__ __forceinline__ void fft_pass_read(double (&xr)[8], double (&xi)[8], 
     }
 }
 
-template <int N, int NS, int LEFT>
+template <int N, int NS, int LEFT, int TWMUL = 1>
 struct FftRest {
     // LEFT = number of radix-8 passes still to run after the first one
     __device__ static __forceinline__ void run(double (&xr)[8], double (&xi)[8], double2* sx, int t, int group,
@@ -177,15 +178,15 @@ struct FftRest {
             fft_pass_write<N, NS / 8, 8>(xr, xi, sx, t);
             fft_sync<N>(group);
             fft_pass_read<N, 8>(xr, xi, sx, t);
-            fft_pass_compute<N, NS, 8>(xr, xi, t, tw);
-            FftRest<N, NS * 8, LEFT - 1>::run(xr, xi, sx, t, group, tw);
+            fft_pass_compute<N, NS, 8, TWMUL>(xr, xi, t, tw);
+            FftRest<N, NS * 8, LEFT - 1, TWMUL>::run(xr, xi, sx, t, group, tw);
         } else if constexpr (NS < N) {
             constexpr int R = N / NS;  // 2 or 4
             fft_sync<N>(group);
             fft_pass_write<N, NS / 8, 8>(xr, xi, sx, t);
             fft_sync<N>(group);
             fft_pass_read<N, R>(xr, xi, sx, t);
-            fft_pass_compute<N, NS, R>(xr, xi, t, tw);
+            fft_pass_compute<N, NS, R, TWMUL>(xr, xi, t, tw);
         }
     }
 };
@@ -206,12 +207,12 @@ __device__ __forceinline__ double2 quarter_rot(double2 q0, int s) {
 // holds X[fft_out_index<N>(e, t)].  sx: this transform's padded exchange row (fft_padded_len(N) double2).
 // Synchronises with fft_sync<N>(group): all N/8 threads of the transform must call it (for N < 256 every thread
 // of the CTA, the same number of times).
-template <int N>
+template <int N, int TWMUL = 1>
 __device__ __forceinline__ void fft_block(double (&xr)[8], double (&xi)[8], double2* sx, int t, int group,
                                           const double2* __restrict__ tw) {
     static_assert(N >= 8 && (N & (N - 1)) == 0, "power of two >= 8");
-    fft_pass_compute<N, 1, 8>(xr, xi, t, tw);
-    FftRest<N, 8, fft_num_r8(N) - 1>::run(xr, xi, sx, t, group, tw);
+    fft_pass_compute<N, 1, 8, TWMUL>(xr, xi, t, tw);
+    FftRest<N, 8, fft_num_r8(N) - 1, TWMUL>::run(xr, xi, sx, t, group, tw);
 }
 
 }  // namespace s2k
