@@ -17,6 +17,7 @@
 
 #include "s2k_fft.cuh"
 #include "s2k_internal.cuh"
+#include "s2k_legendre.cuh"
 
 namespace s2k {
 
@@ -135,17 +136,20 @@ __global__ void __launch_bounds__(NB / 8 * G) k_table_gen(double* __restrict__ t
 // changes is the rounding inside the cosine transform, as it already did against FFTW.
 // Group = bw/16 threads (8 half-grid nodes each, in the even/odd-reordered order the length-bw/2 DCT-II FFT loads); the
 // lower / upper half of the group runs the DCT-IV transform of the first / second antisymmetric row.
+// first tile (relative to the order's first tile) of the row tile holding row r of parity block `par`, in closed form
+// (s2k_legendre.cuh: row_tile_start_of / block_tiles_of -- the same numbers build_layout tabulates in rt_start[])
+__device__ __forceinline__ uint32_t half_row_tile0(const BlockMeta& mb0, const BlockMeta& mb, int par, int r) {
+    return (par ? block_tiles_of(mb0) : 0u) + row_tile_start_of(mb, r >> 3);
+}
+// entries of row r including the zero padding up to the end of its last tile
+__device__ __forceinline__ int half_padded_len(const BlockMeta& mb, int r) { return 8 * tiles_in_row(mb, r >> 3); }
+
 template <int NB, int G>
-__global__ void __launch_bounds__(NB / 16 * G, 512 / (NB / 16 * G)) k_table_gen_half(double* __restrict__ table,
-                                                                const uint64_t* __restrict__ order_start, uint64_t shift,
-                                                                const BlockMeta* __restrict__ meta,
-                                                                const uint32_t* __restrict__ rt_start,
-                                                                const int* __restrict__ units, int unit_lo, int unit_hi,
-                                                                int lch, int transposed, const double* __restrict__ nodes,
-                                                                const double* __restrict__ seeds,
-                                                                const double2* __restrict__ rec,
-                                                                const double2* __restrict__ tw,
-                                                                const double2* __restrict__ qtab) {
+__global__ void __launch_bounds__(NB / 16 * G, 512 / (NB / 16 * G)) k_table_gen_half(
+    double* __restrict__ table, const uint64_t* __restrict__ order_start, uint64_t shift, const BlockMeta* __restrict__ meta,
+    const int* __restrict__ units, int unit_lo, int unit_hi, int lch, int transposed, const double* __restrict__ nodes,
+    const double* __restrict__ seeds, const double2* __restrict__ rec, const double2* __restrict__ tw,
+    const double2* __restrict__ qtab) {
     constexpr int M = NB / 2, K = NB / 4, T = NB / 16, TH = T / 2;
     constexpr int LA = fft_padded_len(M), LB = fft_padded_len(K);
     static_assert(TH >= 32, "the DCT-IV transforms are owned by whole warps");
@@ -158,8 +162,13 @@ __global__ void __launch_bounds__(NB / 16 * G, 512 / (NB / 16 * G)) k_table_gen_
     const bool live = u < unit_hi;
     if (!live) u = unit_lo;
     const int m = units[2 * u], l0 = units[2 * u + 1];
-    const BlockMeta mb0 = meta[2 * m], mb1 = meta[2 * m + 1];
-    const uint64_t tile0 = order_start[m] - shift;
+    const BlockMeta mb0 = block_meta_of(m, 0, NB), mb1 = block_meta_of(m, 1, NB);
+    double* const otab = table + (order_start[m] - shift) * 64;
+    // element (r, c) of parity block `par`: every tile element of the launch's orders is written exactly once (values,
+    // or zeros in the padding), so the scratch table needs no memset
+    auto put = [&](const BlockMeta& mb, uint32_t rt0, int r, int c, double v) {
+        otab[((uint64_t)rt0 + (uint32_t)(c >> 3)) * 64 + (transposed ? tile_elem_offset(c & 7, r & 7) : tile_elem_offset(r & 7, c & 7))] = v;
+    };
 
     double x[8], prev[8], cur[8];
 #pragma unroll
@@ -179,10 +188,12 @@ __global__ void __launch_bounds__(NB / 16 * G, 512 / (NB / 16 * G)) k_table_gen_
             ac = nx;
         }
     }
-    // pre-twiddles of the DCT-IV inputs n = t + e T, e < 4: (cos, sin)(pi (4n+1) / (2 bw))
+    // pre-twiddles of the DCT-IV inputs n = t + e T, e < 4: (cos, sin)(pi (4n+1) / (2 bw)); post-twiddle bases: the
+    // entries for j = t + i T (length-M separation) and k = th + s K/8 (DCT-IV) are these rotated by i pi/16, s pi/16
     double2 pre[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) pre[e] = __ldg(qtab + 4 * (t + e * T) + 1);
+    const double2 qa0 = __ldg(qtab + 2 * t), qb0 = __ldg(qtab + 4 * th);
     // row in registers -> pre-twiddled DCT-IV input: node 2n sits in register e, node M-1-2n in register e + 4
     auto stage_antisym = [&](double2* dst, bool have) {
 #pragma unroll
@@ -193,6 +204,9 @@ __global__ void __launch_bounds__(NB / 16 * G, 512 / (NB / 16 * G)) k_table_gen_
     };
 
     const double fudge = 1.0 / sqrt((double)NB);  // cospml.c:206
+    double2 ac[4];  // recurrence coefficients of the coming four steps, loaded one quad ahead
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ac[i] = __ldg(rc + min(l0 + i, NB - 1));
     for (int quad = 0; quad < lch / 4; ++quad) {
         const int l = l0 + 4 * quad;
         if (l >= NB) break;  // uniform inside the group; every barrier below is the group's own
@@ -200,14 +214,16 @@ __global__ void __launch_bounds__(NB / 16 * G, 512 / (NB / 16 * G)) k_table_gen_
         double xr[8], xi[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) xr[e] = cur[e];
-        if (l + 1 < NB) rec_step(x, prev, cur, __ldg(rc + l));
+        if (l + 1 < NB) rec_step(x, prev, cur, ac[0]);
         stage_antisym(sb, l + 1 < NB);
-        if (l + 2 < NB) rec_step(x, prev, cur, __ldg(rc + l + 1));
+        if (l + 2 < NB) rec_step(x, prev, cur, ac[1]);
 #pragma unroll
         for (int e = 0; e < 8; ++e) xi[e] = (l + 2 < NB) ? cur[e] : 0.0;
-        if (l + 3 < NB) rec_step(x, prev, cur, __ldg(rc + l + 2));
+        if (l + 3 < NB) rec_step(x, prev, cur, ac[2]);
         stage_antisym(sb + LB, l + 3 < NB);
-        if (l + 4 < NB) rec_step(x, prev, cur, __ldg(rc + l + 3));
+        if (l + 4 < NB) rec_step(x, prev, cur, ac[3]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ac[i] = __ldg(rc + min(l + 4 + i, NB - 1));
 
         // ---- the two symmetric rows: one complex FFT of length M
         fft_block<M, 2>(xr, xi, sa, t, g, tw);
@@ -216,19 +232,22 @@ __global__ void __launch_bounds__(NB / 16 * G, 512 / (NB / 16 * G)) k_table_gen_
         for (int e = 0; e < 8; ++e) sa[fft_pad(fft_out_index<M>(e, t))] = make_double2(xr[e], xi[e]);
         fft_sync<M>(g);
         if (live) {
-            const int len_a = mb0.len0 + ra, len_b = (l + 2 < NB) ? mb0.len0 + ra + 1 : 0;
-            for (int j = t; j < M; j += T) {
-                if (j >= len_a && j >= len_b) break;
-                const int nj = (M - j) & (M - 1);
-                const double2 za = sa[fft_pad(j)], zb = sa[fft_pad(nj)];
-                const double2 q = __ldg(qtab + 2 * j);  // (cos, sin)(pi j / 2M)
-                double scale = 2.0 * fudge;
-                if (j == 0) scale *= 0.70710678118654752440;  // cospml.c:205
-                if (j < len_a)
-                    tile_store(table, tile0, mb0, rt_start, ra, j, (q.x * (za.x + zb.x) + q.y * (za.y - zb.y)) * scale, transposed);
-                if (j < len_b)
-                    tile_store(table, tile0, mb0, rt_start, ra + 1, j, (q.x * (za.y + zb.y) - q.y * (za.x - zb.x)) * scale,
-                               transposed);
+            const bool two = l + 2 < NB;
+            const int len_a = mb0.len0 + ra, len_b = two ? len_a + 1 : 0;
+            const int pad_a = half_padded_len(mb0, ra), pad_b = two ? half_padded_len(mb0, ra + 1) : 0;
+            const uint32_t rta = half_row_tile0(mb0, mb0, 0, ra), rtb = half_row_tile0(mb0, mb0, 0, ra + 1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int j = t + i * T;
+                if (j < pad_a || j < pad_b) {
+                    const int nj = (M - j) & (M - 1);
+                    const double2 za = sa[fft_pad(j)], zb = sa[fft_pad(nj)];
+                    const double2 q = quarter_rot(qa0, i);  // (cos, sin)(pi j / 2M)
+                    double scale = 2.0 * fudge;
+                    if (j == 0) scale *= 0.70710678118654752440;  // cospml.c:205
+                    if (j < pad_a) put(mb0, rta, ra, j, j < len_a ? (q.x * (za.x + zb.x) + q.y * (za.y - zb.y)) * scale : 0.0);
+                    if (j < pad_b) put(mb0, rtb, ra + 1, j, j < len_b ? (q.x * (za.y + zb.y) - q.y * (za.x - zb.x)) * scale : 0.0);
+                }
             }
         }
         // ---- the two antisymmetric rows: one DCT-IV each, lower / upper half of the group.  (The barriers inside the
@@ -245,19 +264,33 @@ __global__ void __launch_bounds__(NB / 16 * G, 512 / (NB / 16 * G)) k_table_gen_
             fft_block<K, 4>(yr, yi, sx, th, G + 2 * g + half, tw);
             const int lrow = l + 1 + 2 * half, rrow = ra + half;
             if (live && lrow < NB) {
-                const int len = mb1.len0 + rrow;
+                const int len = mb1.len0 + rrow, pad = half_padded_len(mb1, rrow);
+                const uint32_t rt0 = half_row_tile0(mb0, mb1, 1, rrow);
                 const double scale = 4.0 * fudge;
+                constexpr int R = fft_last_radix(K);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const int k = fft_out_index<K>(e, th);
-                    const double2 q = __ldg(qtab + 4 * k);  // (cos, sin)(pi k / M)
+                    const double2 q = quarter_rot(qb0, fft_slot<R>(e));  // (cos, sin)(pi k / M)
                     const int c0 = 2 * k, c1 = M - 1 - 2 * k;
-                    if (c0 < len) tile_store(table, tile0, mb1, rt_start, rrow, c0, (yr[e] * q.x + yi[e] * q.y) * scale, transposed);
-                    if (c1 < len) tile_store(table, tile0, mb1, rt_start, rrow, c1, (yr[e] * q.y - yi[e] * q.x) * scale, transposed);
+                    if (c0 < pad) put(mb1, rt0, rrow, c0, c0 < len ? (yr[e] * q.x + yi[e] * q.y) * scale : 0.0);
+                    if (c1 < pad) put(mb1, rt0, rrow, c1, c1 < len ? (yr[e] * q.y - yi[e] * q.x) * scale : 0.0);
                 }
             }
         }
         fft_sync<M>(g);  // sa / sb are rewritten by the next step
+    }
+    // the unit that ends the order clears the padding rows of both blocks' last row tiles
+    if (live && l0 + lch >= NB) {
+#pragma unroll
+        for (int par = 0; par < 2; ++par) {
+            const BlockMeta& mb = par ? mb1 : mb0;
+            if (mb.nrt == 0) continue;
+            const int pad = half_padded_len(mb, mb.rows - 1);
+            const uint32_t rt0 = half_row_tile0(mb0, mb, par, mb.rows - 1);
+            for (int r = mb.rows; r < 8 * mb.nrt; ++r)
+                for (int c = t; c < pad; c += T) put(mb, rt0, r, c, 0.0);
+        }
     }
 }
 
@@ -363,6 +396,15 @@ __global__ void k_table_unpack(const double* __restrict__ table, const uint64_t*
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
+// half-grid generator at bw >= 1024 (S2KIT_CUDA_TABLE_FULL=1 keeps the full-length transforms for comparison)
+static bool table_gen_half_used(const s2kit_cuda_plan* p) {
+    static const int full = [] {
+        const char* e = getenv("S2KIT_CUDA_TABLE_FULL");
+        return (e && e[0] == '1') ? 1 : 0;
+    }();
+    return !full && p->fast && p->bw >= 1024 && table_unit_rows(p->bw) % 4 == 0;
+}
+
 template <int NB>
 static cudaError_t table_gen_nb(s2kit_cuda_plan* p, double* table, uint64_t shift, int unit_lo, int unit_hi, int lch,
                                 int transposed) {
@@ -376,19 +418,14 @@ static cudaError_t table_gen_nb(s2kit_cuda_plan* p, double* table, uint64_t shif
     }
     int nunits = unit_hi - unit_lo;
     if constexpr (NB >= 1024) {
-        // half-grid generator (S2KIT_CUDA_TABLE_FULL=1 keeps the full-length transforms for comparison)
-        static const int full = [] {
-            const char* e = getenv("S2KIT_CUDA_TABLE_FULL");
-            return (e && e[0] == '1') ? 1 : 0;
-        }();
-        if (!full && lch % 4 == 0) {
+        if (table_gen_half_used(p)) {
             constexpr int TG = NB / 16, GH = 128 / TG < 1 ? 1 : 128 / TG;
             const size_t smem_h = sizeof(double2) * GH * (fft_padded_len(NB / 2) + 2 * fft_padded_len(NB / 4));
             cudaError_t e = ensure_smem(reinterpret_cast<const void*>(k_table_gen_half<NB, GH>), smem_h);
             if (e != cudaSuccess) return e;
             k_table_gen_half<NB, GH><<<(nunits + GH - 1) / GH, TG * GH, smem_h, p->stream>>>(
-                table, p->d_order_start, shift, p->d_meta, p->d_rt_start, p->d_units, unit_lo, unit_hi, lch, transposed,
-                p->d_nodes, p->d_seeds, p->d_rec, p->d_tw_b, p->d_q_b);
+                table, p->d_order_start, shift, p->d_meta, p->d_units, unit_lo, unit_hi, lch, transposed, p->d_nodes, p->d_seeds,
+                p->d_rec, p->d_tw_b, p->d_q_b);
             return cudaGetLastError();
         }
     }
@@ -413,7 +450,9 @@ int table_unit_rows(int bw) {
 cudaError_t launch_table_gen(s2kit_cuda_plan* p, double* table, uint64_t shift, int m_lo, int m_hi, int transposed) {
     if (m_hi <= m_lo) return cudaSuccess;
     uint64_t t0 = p->h_order_start[m_lo], t1 = p->h_order_start[m_hi];
-    cudaError_t e = cudaMemsetAsync(table + (t0 - shift) * 64, 0, (t1 - t0) * 64 * sizeof(double), p->stream);
+    cudaError_t e = cudaSuccess;
+    // the half-grid generator writes every tile element (padding included); the others only the entries they compute
+    if (!table_gen_half_used(p)) e = cudaMemsetAsync(table + (t0 - shift) * 64, 0, (t1 - t0) * 64 * sizeof(double), p->stream);
     if (e != cudaSuccess) return e;
     int slot = prof_begin(p, S2KIT_K_TABLE_GEN);
     if (p->fast) {

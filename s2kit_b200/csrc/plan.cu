@@ -508,7 +508,11 @@ static int plan_build(s2kit_cuda_plan* p, int bw, int variant, int max_batch, in
         // tiles through HBM costs far less than the idle SMs did: bw = 1024 forward 5.7 -> 3.1 ms (64 MiB -> 1 GiB).
         uint64_t biggest = 0;
         for (int m = 0; m < bw; ++m) biggest = std::max(biggest, p->h_order_start[m + 1] - p->h_order_start[m]);
-        uint64_t ring_mb = 1024;
+        // bw >= 512: the inverse contraction reads A-order tiles too (the narrow-panel reader of the one-copy Memo plans), so
+        // both directions generate the same layout and the generator's stores stay 64-byte runs (in B-fragment order a
+        // table row is scattered over eight sectors: bw = 1024 inverse generation 1.9 vs 1.4 ms)
+        p->table_single = bw >= 512;
+        uint64_t ring_mb = 2048;
         if (const char* e = getenv("S2KIT_CUDA_FLY_RING_MB")) ring_mb = std::max(1L, atol(e));
         uint64_t cap = std::max<uint64_t>(biggest, (ring_mb << 20) / 512);
         p->fly_tiles = std::min<uint64_t>(cap, total_tiles);
@@ -726,7 +730,7 @@ static int inv_fst_sub(s2kit_cuda_plan* p, const double* rc, const double* ic, d
     const bool flow = !uni && s2k::inv_flow_supported(p, nf, fmt);
     for (const OrderGroup& g : order_groups(p, 0, bw)) {
         const double* tt = p->variant == S2KIT_CUDA_FLY ? p->d_table : p->d_table_t;
-        if (p->variant == S2KIT_CUDA_FLY) CK(s2k::launch_table_gen(p, p->d_table, g.shift, g.lo, g.hi, 1));
+        if (p->variant == S2KIT_CUDA_FLY) CK(s2k::launch_table_gen(p, p->d_table, g.shift, g.lo, g.hi, p->table_single ? 0 : 1));
         if (uni)
             CK(s2k::launch_inv_uni(p, tt, g.shift, rc, ic, coef_stride, dS, nf, g.lo, g.hi, fmt, pv.lat_perm));
         else if (flow)
@@ -1143,7 +1147,7 @@ extern "C" int s2kit_cuda_inv_dlt_semi(s2kit_cuda_plan* p, const double* coeffs,
                                 where == S2KIT_CUDA_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                                 p->stream);
         for (const OrderGroup& g : order_groups(p, m, m + 1)) {
-            if (e == cudaSuccess && p->variant == S2KIT_CUDA_FLY) e = s2k::launch_table_gen(p, p->d_table, g.shift, g.lo, g.hi, 1);
+            if (e == cudaSuccess && p->variant == S2KIT_CUDA_FLY) e = s2k::launch_table_gen(p, p->d_table, g.shift, g.lo, g.hi, p->table_single ? 0 : 1);
             if (e == cudaSuccess)
                 e = s2k::launch_legendre_inv(p, p->variant == S2KIT_CUDA_FLY ? p->d_table : p->d_table_t, g.shift, dcoef, dcoef + cs, cs, p->d_X, 1, m, m + 1,
                                              S2KIT_REAL);
