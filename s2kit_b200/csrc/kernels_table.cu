@@ -144,144 +144,164 @@ __device__ __forceinline__ uint32_t half_row_tile0(const BlockMeta& mb0, const B
 // entries of row r including the zero padding up to the end of its last tile
 __device__ __forceinline__ int half_padded_len(const BlockMeta& mb, int r) { return 8 * tiles_in_row(mb, r >> 3); }
 
-template <int NB, int G>
-__global__ void __launch_bounds__(NB / 16 * G, 512 / (NB / 16 * G)) k_table_gen_half(
+// One CTA = one work unit = NB/8 threads.  Every thread carries FOUR half-grid nodes through the recurrence (12 doubles of
+// state); the rows go to shared memory in the order their transforms load them, then the CTA splits: the first half of
+// the threads runs the length-M transform of the two symmetric rows, the third and fourth quarter one DCT-IV each -- the
+// three transforms of a step run side by side instead of one after the other, and nobody holds recurrence state for
+// eight nodes next to sixteen transform registers (the first version of this kernel: 128 registers with spills, 16
+// warps per SM, the transforms in sequence; 1.53 ms per direction at bw = 1024 against 1.2 here).
+template <int NB>
+__global__ void __launch_bounds__(NB / 8, 640 / (NB / 8)) k_table_gen_half(
     double* __restrict__ table, const uint64_t* __restrict__ order_start, uint64_t shift, const BlockMeta* __restrict__ meta,
     const int* __restrict__ units, int unit_lo, int unit_hi, int lch, int transposed, const double* __restrict__ nodes,
     const double* __restrict__ seeds, const double2* __restrict__ rec, const double2* __restrict__ tw,
     const double2* __restrict__ qtab) {
-    constexpr int M = NB / 2, K = NB / 4, T = NB / 16, TH = T / 2;
+    constexpr int M = NB / 2, K = NB / 4, T = NB / 8, TA = T / 2, TB = T / 4;
     constexpr int LA = fft_padded_len(M), LB = fft_padded_len(K);
-    static_assert(TH >= 32, "the DCT-IV transforms are owned by whole warps");
+    static_assert(TB >= 32, "every transform is owned by whole warps");
     extern __shared__ double2 smem2[];
-    const int tid = threadIdx.x, g = tid / T, t = tid % T;
-    const int half = t / TH, th = t % TH;
-    double2* sa = smem2 + g * (LA + 2 * LB);  // exchange row of the length-M transform
-    double2* sb = sa + LA;                    // DCT-IV inputs / exchange rows: first row, then second row
-    int u = unit_lo + blockIdx.x * G + g;
-    const bool live = u < unit_hi;
-    if (!live) u = unit_lo;
+    double2* sa = smem2;       // inputs / exchange row of the length-M transform
+    double2* sb = smem2 + LA;  // DCT-IV inputs / exchange rows: first antisymmetric row, then the second
+    const int t = threadIdx.x;
+    const int u = unit_lo + blockIdx.x;
+    if (u >= unit_hi) return;
     const int m = units[2 * u], l0 = units[2 * u + 1];
     const BlockMeta mb0 = block_meta_of(m, 0, NB), mb1 = block_meta_of(m, 1, NB);
     double* const otab = table + (order_start[m] - shift) * 64;
-    // element (r, c) of parity block `par`: every tile element of the launch's orders is written exactly once (values,
-    // or zeros in the padding), so the scratch table needs no memset
-    auto put = [&](const BlockMeta& mb, uint32_t rt0, int r, int c, double v) {
+    // element (r, c) of a parity block whose row tile starts at tile rt0: every tile element of the launch's orders is
+    // written exactly once (values, or zeros in the padding), so the scratch table needs no memset
+    auto put = [&](uint32_t rt0, int r, int c, double v) {
         otab[((uint64_t)rt0 + (uint32_t)(c >> 3)) * 64 + (transposed ? tile_elem_offset(c & 7, r & 7) : tile_elem_offset(r & 7, c & 7))] = v;
     };
 
-    double x[8], prev[8], cur[8];
+    // positions p = t + e T of the even/odd-reordered length-M DCT-II input; registers 0, 1 hold nodes 2n (n = t, t + T),
+    // registers 2, 3 their DCT-IV partners M-1-2n
+    double x[4], prev[4], cur[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
+    for (int e = 0; e < 4; ++e) {
         const int p = t + e * T;
-        const int i = (p < M / 2) ? 2 * p : 2 * (M - 1 - p) + 1;  // even/odd reordering of the length-M DCT-II input
+        const int i = (p < M / 2) ? 2 * p : 2 * (M - 1 - p) + 1;
         x[e] = __ldg(nodes + i);
         cur[e] = __ldg(seeds + (long)m * NB + i);
         prev[e] = 0.0;
     }
+    auto step = [&](double2 ac) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const double t1 = __dmul_rn(ac.y, prev[e]);
+            const double t2 = __dmul_rn(cur[e], x[e]);
+            const double t3 = __dmul_rn(ac.x, t2);
+            prev[e] = cur[e];
+            cur[e] = __dadd_rn(t3, t1);
+        }
+    };
     const double2* rc = rec + (long)m * NB;
     {
         double2 ac = __ldg(rc + m);
         for (int l = m; l < l0; ++l) {
             const double2 nx = __ldg(rc + min(l + 1, NB - 1));
-            rec_step(x, prev, cur, ac);
+            step(ac);
             ac = nx;
         }
     }
-    // pre-twiddles of the DCT-IV inputs n = t + e T, e < 4: (cos, sin)(pi (4n+1) / (2 bw)); post-twiddle bases: the
-    // entries for j = t + i T (length-M separation) and k = th + s K/8 (DCT-IV) are these rotated by i pi/16, s pi/16
-    double2 pre[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) pre[e] = __ldg(qtab + 4 * (t + e * T) + 1);
-    const double2 qa0 = __ldg(qtab + 2 * t), qb0 = __ldg(qtab + 4 * th);
-    // row in registers -> pre-twiddled DCT-IV input: node 2n sits in register e, node M-1-2n in register e + 4
+    // DCT-IV pre-twiddles (cos, sin)(pi (4n+1) / (2 bw)), n = t, t + T
+    const double2 pre0 = __ldg(qtab + 4 * t + 1), pre1 = __ldg(qtab + 4 * (t + T) + 1);
     auto stage_antisym = [&](double2* dst, bool have) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const double ur = have ? cur[e] : 0.0, ui = have ? cur[e + 4] : 0.0;
-            dst[fft_pad(t + e * T)] = make_double2(ur * pre[e].x + ui * pre[e].y, ui * pre[e].x - ur * pre[e].y);
-        }
+        const double a0 = have ? cur[0] : 0.0, b0 = have ? cur[2] : 0.0, a1 = have ? cur[1] : 0.0, b1 = have ? cur[3] : 0.0;
+        dst[fft_pad(t)] = make_double2(a0 * pre0.x + b0 * pre0.y, b0 * pre0.x - a0 * pre0.y);
+        dst[fft_pad(t + T)] = make_double2(a1 * pre1.x + b1 * pre1.y, b1 * pre1.x - a1 * pre1.y);
     };
-
+    // roles after the rows are staged
+    const bool role_a = t < TA;
+    const int hb = (t - TA) / TB, tb = (t - TA) % TB;  // DCT-IV transform and thread inside it (threads >= TA)
+    // post-twiddle bases: the entries for j = t + i TA (separation) and k = tb + s K/8 (DCT-IV) are these rotated by multiples of pi/16
+    const double2 q0 = __ldg(qtab + (role_a ? 2 * t : 4 * tb));
     const double fudge = 1.0 / sqrt((double)NB);  // cospml.c:206
+
     double2 ac[4];  // recurrence coefficients of the coming four steps, loaded one quad ahead
 #pragma unroll
     for (int i = 0; i < 4; ++i) ac[i] = __ldg(rc + min(l0 + i, NB - 1));
     for (int quad = 0; quad < lch / 4; ++quad) {
         const int l = l0 + 4 * quad;
-        if (l >= NB) break;  // uniform inside the group; every barrier below is the group's own
+        if (l >= NB) break;
         const int ra = (l - m) >> 1;  // row of degree l (parity 0) and of degree l + 1 (parity 1) in their blocks
-        double xr[8], xi[8];
+        double r0[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) xr[e] = cur[e];
-        if (l + 1 < NB) rec_step(x, prev, cur, ac[0]);
+        for (int e = 0; e < 4; ++e) r0[e] = cur[e];
+        if (l + 1 < NB) step(ac[0]);
         stage_antisym(sb, l + 1 < NB);
-        if (l + 2 < NB) rec_step(x, prev, cur, ac[1]);
+        if (l + 2 < NB) step(ac[1]);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) xi[e] = (l + 2 < NB) ? cur[e] : 0.0;
-        if (l + 3 < NB) rec_step(x, prev, cur, ac[2]);
+        for (int e = 0; e < 4; ++e) sa[fft_pad(t + e * T)] = make_double2(r0[e], (l + 2 < NB) ? cur[e] : 0.0);
+        if (l + 3 < NB) step(ac[2]);
         stage_antisym(sb + LB, l + 3 < NB);
-        if (l + 4 < NB) rec_step(x, prev, cur, ac[3]);
+        if (l + 4 < NB) step(ac[3]);
 #pragma unroll
         for (int i = 0; i < 4; ++i) ac[i] = __ldg(rc + min(l + 4 + i, NB - 1));
+        __syncthreads();
 
-        // ---- the two symmetric rows: one complex FFT of length M
-        fft_block<M, 2>(xr, xi, sa, t, g, tw);
-        fft_sync<M>(g);
+        if (role_a) {
+            // ---- the two symmetric rows: one complex FFT of length M, separated by conjugate symmetry
+            double xr[8], xi[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) sa[fft_pad(fft_out_index<M>(e, t))] = make_double2(xr[e], xi[e]);
-        fft_sync<M>(g);
-        if (live) {
+            for (int e = 0; e < 8; ++e) {
+                const double2 v = sa[fft_pad(t + e * TA)];
+                xr[e] = v.x;
+                xi[e] = v.y;
+            }
+            fft_block<M, 2>(xr, xi, sa, t, 0, tw);
+            fft_sync<M>(0);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sa[fft_pad(fft_out_index<M>(e, t))] = make_double2(xr[e], xi[e]);
+            fft_sync<M>(0);
             const bool two = l + 2 < NB;
             const int len_a = mb0.len0 + ra, len_b = two ? len_a + 1 : 0;
             const int pad_a = half_padded_len(mb0, ra), pad_b = two ? half_padded_len(mb0, ra + 1) : 0;
             const uint32_t rta = half_row_tile0(mb0, mb0, 0, ra), rtb = half_row_tile0(mb0, mb0, 0, ra + 1);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const int j = t + i * T;
+                const int j = t + i * TA;
                 if (j < pad_a || j < pad_b) {
                     const int nj = (M - j) & (M - 1);
                     const double2 za = sa[fft_pad(j)], zb = sa[fft_pad(nj)];
-                    const double2 q = quarter_rot(qa0, i);  // (cos, sin)(pi j / 2M)
+                    const double2 q = quarter_rot(q0, i);  // (cos, sin)(pi j / 2M)
                     double scale = 2.0 * fudge;
                     if (j == 0) scale *= 0.70710678118654752440;  // cospml.c:205
-                    if (j < pad_a) put(mb0, rta, ra, j, j < len_a ? (q.x * (za.x + zb.x) + q.y * (za.y - zb.y)) * scale : 0.0);
-                    if (j < pad_b) put(mb0, rtb, ra + 1, j, j < len_b ? (q.x * (za.y + zb.y) - q.y * (za.x - zb.x)) * scale : 0.0);
+                    if (j < pad_a) put(rta, ra, j, j < len_a ? (q.x * (za.x + zb.x) + q.y * (za.y - zb.y)) * scale : 0.0);
+                    if (j < pad_b) put(rtb, ra + 1, j, j < len_b ? (q.x * (za.y + zb.y) - q.y * (za.x - zb.x)) * scale : 0.0);
                 }
             }
-        }
-        // ---- the two antisymmetric rows: one DCT-IV each, lower / upper half of the group.  (The barriers inside the
-        // transform above came after every thread's stage_antisym stores.)
-        {
-            double2* sx = sb + half * LB;
+        } else {
+            // ---- one antisymmetric row per quarter of the CTA: DCT-IV through a complex FFT of length K
+            double2* sx = sb + hb * LB;
             double yr[8], yi[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const double2 v = sx[fft_pad(th + e * (K / 8))];
+                const double2 v = sx[fft_pad(tb + e * TB)];
                 yr[e] = v.x;
                 yi[e] = v.y;
             }
-            fft_block<K, 4>(yr, yi, sx, th, G + 2 * g + half, tw);
-            const int lrow = l + 1 + 2 * half, rrow = ra + half;
-            if (live && lrow < NB) {
+            fft_block<K, 4>(yr, yi, sx, tb, 1 + hb, tw);
+            const int lrow = l + 1 + 2 * hb, rrow = ra + hb;
+            if (lrow < NB) {
                 const int len = mb1.len0 + rrow, pad = half_padded_len(mb1, rrow);
                 const uint32_t rt0 = half_row_tile0(mb0, mb1, 1, rrow);
                 const double scale = 4.0 * fudge;
                 constexpr int R = fft_last_radix(K);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const int k = fft_out_index<K>(e, th);
-                    const double2 q = quarter_rot(qb0, fft_slot<R>(e));  // (cos, sin)(pi k / M)
+                    const int k = fft_out_index<K>(e, tb);
+                    const double2 q = quarter_rot(q0, fft_slot<R>(e));  // (cos, sin)(pi k / M)
                     const int c0 = 2 * k, c1 = M - 1 - 2 * k;
-                    if (c0 < pad) put(mb1, rt0, rrow, c0, c0 < len ? (yr[e] * q.x + yi[e] * q.y) * scale : 0.0);
-                    if (c1 < pad) put(mb1, rt0, rrow, c1, c1 < len ? (yr[e] * q.y - yi[e] * q.x) * scale : 0.0);
+                    if (c0 < pad) put(rt0, rrow, c0, c0 < len ? (yr[e] * q.x + yi[e] * q.y) * scale : 0.0);
+                    if (c1 < pad) put(rt0, rrow, c1, c1 < len ? (yr[e] * q.y - yi[e] * q.x) * scale : 0.0);
                 }
             }
         }
-        fft_sync<M>(g);  // sa / sb are rewritten by the next step
+        __syncthreads();  // sa / sb are rewritten by the next step
     }
     // the unit that ends the order clears the padding rows of both blocks' last row tiles
-    if (live && l0 + lch >= NB) {
+    if (l0 + lch >= NB) {
 #pragma unroll
         for (int par = 0; par < 2; ++par) {
             const BlockMeta& mb = par ? mb1 : mb0;
@@ -289,7 +309,7 @@ __global__ void __launch_bounds__(NB / 16 * G, 512 / (NB / 16 * G)) k_table_gen_
             const int pad = half_padded_len(mb, mb.rows - 1);
             const uint32_t rt0 = half_row_tile0(mb0, mb, par, mb.rows - 1);
             for (int r = mb.rows; r < 8 * mb.nrt; ++r)
-                for (int c = t; c < pad; c += T) put(mb, rt0, r, c, 0.0);
+                for (int c = t; c < pad; c += T) put(rt0, r, c, 0.0);
         }
     }
 }
@@ -419,13 +439,12 @@ static cudaError_t table_gen_nb(s2kit_cuda_plan* p, double* table, uint64_t shif
     int nunits = unit_hi - unit_lo;
     if constexpr (NB >= 1024) {
         if (table_gen_half_used(p)) {
-            constexpr int TG = NB / 16, GH = 128 / TG < 1 ? 1 : 128 / TG;
-            const size_t smem_h = sizeof(double2) * GH * (fft_padded_len(NB / 2) + 2 * fft_padded_len(NB / 4));
-            cudaError_t e = ensure_smem(reinterpret_cast<const void*>(k_table_gen_half<NB, GH>), smem_h);
+            const size_t smem_h = sizeof(double2) * (fft_padded_len(NB / 2) + 2 * fft_padded_len(NB / 4));
+            cudaError_t e = ensure_smem(reinterpret_cast<const void*>(k_table_gen_half<NB>), smem_h);
             if (e != cudaSuccess) return e;
-            k_table_gen_half<NB, GH><<<(nunits + GH - 1) / GH, TG * GH, smem_h, p->stream>>>(
-                table, p->d_order_start, shift, p->d_meta, p->d_units, unit_lo, unit_hi, lch, transposed, p->d_nodes, p->d_seeds,
-                p->d_rec, p->d_tw_b, p->d_q_b);
+            k_table_gen_half<NB><<<nunits, NB / 8, smem_h, p->stream>>>(table, p->d_order_start, shift, p->d_meta, p->d_units,
+                                                                        unit_lo, unit_hi, lch, transposed, p->d_nodes,
+                                                                        p->d_seeds, p->d_rec, p->d_tw_b, p->d_q_b);
             return cudaGetLastError();
         }
     }

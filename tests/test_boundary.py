@@ -157,3 +157,28 @@ def test_per_file_headers_forward_to_the_api(tmp_path):
         r = subprocess.run(["gcc", "-std=gnu11", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
                            capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
+
+
+def test_text_files_in_the_reference_formats(tmp_path, refdata):
+    """s2kit_b200.textio: the file formats of the reference's example mains (test_s2_semi_memo_fwd.c:119-151)."""
+    from s2kit_b200 import textio
+
+    bw = 8
+    rng = np.random.RandomState(3)
+    rc, ic = rng.uniform(-1, 1, bw * bw), rng.uniform(-1, 1, bw * bw)
+    for human in (False, True):
+        path = tmp_path / f"c{int(human)}.dat"
+        textio.write_coeffs(path, rc, ic, bw, human_readable=human)
+        br, bi = textio.read_coeffs(path, bw)
+        assert np.abs(br - rc).max() < 1e-15 + 5e-16 and np.abs(bi - ic).max() < 1e-15 + 5e-16  # "%.15f"
+    lines = open(tmp_path / "c1.dat").read().splitlines()
+    assert len(lines) == bw * bw and lines[0].startswith("l = 0\t m = 0\t ") and lines[1].startswith("l = 1\t m = -1\t ")
+    # a grid written the way the reference's mains read it, and the reference's own s64.dat as committed
+    n = 2 * bw
+    g_r, g_i = rng.uniform(-1, 1, (n, n)), rng.uniform(-1, 1, (n, n))
+    textio.write_interleaved(tmp_path / "g.dat", g_r, g_i)
+    h_r, h_i = textio.read_grid(tmp_path / "g.dat", bw)
+    assert np.abs(h_r - g_r).max() < 1e-15 and np.abs(h_i - g_i).max() < 1e-15
+    s64 = refdata["s64"]  # the reference's data/s64.dat: a real-valued 128 x 128 signal, one value per line
+    textio.write_real(tmp_path / "s64.dat", s64)
+    assert np.abs(textio.read_real(tmp_path / "s64.dat", 128 * 128) - s64).max() < 1e-15
