@@ -174,6 +174,9 @@ __global__ void __launch_bounds__(NB / 8, 640 / (NB / 8)) k_table_gen_half(
         otab[((uint64_t)rt0 + (uint32_t)(c >> 3)) * 64 + (transposed ? tile_elem_offset(c & 7, r & 7) : tile_elem_offset(r & 7, c & 7))] = v;
     };
 
+    // offset of element (r, c) inside its tile
+    auto eoff = [&](int r, int c7) { return transposed ? tile_elem_offset(c7, r & 7) : tile_elem_offset(r & 7, c7); };
+
     // positions p = t + e T of the even/odd-reordered length-M DCT-II input; registers 0, 1 hold nodes 2n (n = t, t + T),
     // registers 2, 3 their DCT-IV partners M-1-2n
     double x[4], prev[4], cur[4];
@@ -258,6 +261,9 @@ __global__ void __launch_bounds__(NB / 8, 640 / (NB / 8)) k_table_gen_half(
             const int len_a = mb0.len0 + ra, len_b = two ? len_a + 1 : 0;
             const int pad_a = half_padded_len(mb0, ra), pad_b = two ? half_padded_len(mb0, ra + 1) : 0;
             const uint32_t rta = half_row_tile0(mb0, mb0, 0, ra), rtb = half_row_tile0(mb0, mb0, 0, ra + 1);
+            // column j = t + i TA: the tile advances by TA/8 per i, the position inside the tile (j & 7 = t & 7) never changes
+            double* const pa = otab + ((uint64_t)rta + (uint32_t)(t >> 3)) * 64 + eoff(ra, t & 7);
+            double* const pb = otab + ((uint64_t)rtb + (uint32_t)(t >> 3)) * 64 + eoff(ra + 1, t & 7);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int j = t + i * TA;
@@ -267,8 +273,8 @@ __global__ void __launch_bounds__(NB / 8, 640 / (NB / 8)) k_table_gen_half(
                     const double2 q = quarter_rot(q0, i);  // (cos, sin)(pi j / 2M)
                     double scale = 2.0 * fudge;
                     if (j == 0) scale *= 0.70710678118654752440;  // cospml.c:205
-                    if (j < pad_a) put(rta, ra, j, j < len_a ? (q.x * (za.x + zb.x) + q.y * (za.y - zb.y)) * scale : 0.0);
-                    if (j < pad_b) put(rtb, ra + 1, j, j < len_b ? (q.x * (za.y + zb.y) - q.y * (za.x - zb.x)) * scale : 0.0);
+                    if (j < pad_a) pa[i * (TA / 8) * 64] = j < len_a ? (q.x * (za.x + zb.x) + q.y * (za.y - zb.y)) * scale : 0.0;
+                    if (j < pad_b) pb[i * (TA / 8) * 64] = j < len_b ? (q.x * (za.y + zb.y) - q.y * (za.x - zb.x)) * scale : 0.0;
                 }
             }
         } else {
@@ -288,13 +294,17 @@ __global__ void __launch_bounds__(NB / 8, 640 / (NB / 8)) k_table_gen_half(
                 const uint32_t rt0 = half_row_tile0(mb0, mb1, 1, rrow);
                 const double scale = 4.0 * fudge;
                 constexpr int R = fft_last_radix(K);
+                // columns 2k and M-1-2k with k = tb + s TB: the tiles move by +- s TB/4, the positions inside the tile stay
+                const int c0b = 2 * tb, c1b = M - 1 - 2 * tb;
+                double* const p0 = otab + ((uint64_t)rt0 + (uint32_t)(c0b >> 3)) * 64 + eoff(rrow, c0b & 7);
+                double* const p1 = otab + ((uint64_t)rt0 + (uint32_t)(c1b >> 3)) * 64 + eoff(rrow, c1b & 7);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const int k = fft_out_index<K>(e, tb);
-                    const double2 q = quarter_rot(q0, fft_slot<R>(e));  // (cos, sin)(pi k / M)
-                    const int c0 = 2 * k, c1 = M - 1 - 2 * k;
-                    if (c0 < pad) put(rt0, rrow, c0, c0 < len ? (yr[e] * q.x + yi[e] * q.y) * scale : 0.0);
-                    if (c1 < pad) put(rt0, rrow, c1, c1 < len ? (yr[e] * q.y - yi[e] * q.x) * scale : 0.0);
+                    const int sl = fft_slot<R>(e);
+                    const double2 q = quarter_rot(q0, sl);  // (cos, sin)(pi k / M)
+                    const int c0 = c0b + 2 * sl * TB, c1 = c1b - 2 * sl * TB;
+                    if (c0 < pad) p0[sl * (TB / 4) * 64] = c0 < len ? (yr[e] * q.x + yi[e] * q.y) * scale : 0.0;
+                    if (c1 < pad) p1[-sl * (TB / 4) * 64] = c1 < len ? (yr[e] * q.y - yi[e] * q.x) * scale : 0.0;
                 }
             }
         }
