@@ -144,6 +144,57 @@ __device__ __forceinline__ uint32_t half_row_tile0(const BlockMeta& mb0, const B
 // entries of row r including the zero padding up to the end of its last tile
 __device__ __forceinline__ int half_padded_len(const BlockMeta& mb, int r) { return 8 * tiles_in_row(mb, r >> 3); }
 
+// Recurrence checkpoints for the half-grid generator: (P~_{l0-1}^m, P~_{l0}^m) on the half grid at the first degree l0 of
+// every work unit, in the generator's own thread order (position p = t + e T).  A unit used to roll the recurrence up
+// from l = m to its l0 on its own -- at m = 0 the eight units of an order repeated 3.5x the order's whole recurrence.  The
+// values are what the roll-up produced, bit for bit (same operations in the same order); one CTA per order writes them
+// once per plan (bw = 1024: 67 MB, 1/22 of the table the Fly variant avoids storing).
+template <int NB>
+__global__ void __launch_bounds__(NB / 8) k_rec_checkpoints(double* __restrict__ ckpt, const int* __restrict__ unit_first,
+                                                           int lch, const double* __restrict__ nodes,
+                                                           const double* __restrict__ seeds,
+                                                           const double2* __restrict__ rec) {
+    constexpr int M = NB / 2, T = NB / 8;
+    const int t = threadIdx.x, m = blockIdx.x;
+    const int u0 = unit_first[m], nu = unit_first[m + 1] - u0;  // units of order m, LAST degrees first
+    double x[4], prev[4], cur[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int p = t + e * T;
+        const int i = (p < M / 2) ? 2 * p : 2 * (M - 1 - p) + 1;
+        x[e] = __ldg(nodes + i);
+        cur[e] = __ldg(seeds + (long)m * NB + i);
+        prev[e] = 0.0;
+    }
+    const double2* rc = rec + (long)m * NB;
+    for (int j = 0; j < nu; ++j) {
+        double* dst = ckpt + (size_t)(u0 + nu - 1 - j) * 2 * M;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            dst[t + e * T] = prev[e];
+            dst[M + t + e * T] = cur[e];
+        }
+        if (j + 1 == nu) break;
+        const int l0 = m + j * lch;
+        double2 ac[4];
+        for (int l = l0; l < l0 + lch; l += 4) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ac[i] = __ldg(rc + l + i);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const double t1 = __dmul_rn(ac[i].y, prev[e]);
+                    const double t2 = __dmul_rn(cur[e], x[e]);
+                    const double t3 = __dmul_rn(ac[i].x, t2);
+                    prev[e] = cur[e];
+                    cur[e] = __dadd_rn(t3, t1);
+                }
+            }
+        }
+    }
+}
+
 // One CTA = one work unit = NB/8 threads.  Every thread carries FOUR half-grid nodes through the recurrence (12 doubles of
 // state); the rows go to shared memory in the order their transforms load them, then the CTA splits: the first half of
 // the threads runs the length-M transform of the two symmetric rows, the third and fourth quarter one DCT-IV each -- the
@@ -154,7 +205,7 @@ template <int NB>
 __global__ void __launch_bounds__(NB / 8, 640 / (NB / 8)) k_table_gen_half(
     double* __restrict__ table, const uint64_t* __restrict__ order_start, uint64_t shift, const BlockMeta* __restrict__ meta,
     const int* __restrict__ units, int unit_lo, int unit_hi, int lch, int transposed, const double* __restrict__ nodes,
-    const double* __restrict__ seeds, const double2* __restrict__ rec, const double2* __restrict__ tw,
+    const double* __restrict__ ckpt, const double2* __restrict__ rec, const double2* __restrict__ tw,
     const double2* __restrict__ qtab) {
     constexpr int M = NB / 2, K = NB / 4, T = NB / 8, TA = T / 2, TB = T / 4;
     constexpr int LA = fft_padded_len(M), LB = fft_padded_len(K);
@@ -180,13 +231,16 @@ __global__ void __launch_bounds__(NB / 8, 640 / (NB / 8)) k_table_gen_half(
     // positions p = t + e T of the even/odd-reordered length-M DCT-II input; registers 0, 1 hold nodes 2n (n = t, t + T),
     // registers 2, 3 their DCT-IV partners M-1-2n
     double x[4], prev[4], cur[4];
+    {
+        const double* ck = ckpt + (size_t)u * 2 * M;  // the recurrence state at the unit's first degree (k_rec_checkpoints)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const int p = t + e * T;
-        const int i = (p < M / 2) ? 2 * p : 2 * (M - 1 - p) + 1;
-        x[e] = __ldg(nodes + i);
-        cur[e] = __ldg(seeds + (long)m * NB + i);
-        prev[e] = 0.0;
+        for (int e = 0; e < 4; ++e) {
+            const int p = t + e * T;
+            const int i = (p < M / 2) ? 2 * p : 2 * (M - 1 - p) + 1;
+            x[e] = __ldg(nodes + i);
+            prev[e] = __ldg(ck + p);
+            cur[e] = __ldg(ck + M + p);
+        }
     }
     auto step = [&](double2 ac) {
 #pragma unroll
@@ -199,14 +253,6 @@ __global__ void __launch_bounds__(NB / 8, 640 / (NB / 8)) k_table_gen_half(
         }
     };
     const double2* rc = rec + (long)m * NB;
-    {
-        double2 ac = __ldg(rc + m);
-        for (int l = m; l < l0; ++l) {
-            const double2 nx = __ldg(rc + min(l + 1, NB - 1));
-            step(ac);
-            ac = nx;
-        }
-    }
     // DCT-IV pre-twiddles (cos, sin)(pi (4n+1) / (2 bw)), n = t, t + T
     const double2 pre0 = __ldg(qtab + 4 * t + 1), pre1 = __ldg(qtab + 4 * (t + T) + 1);
     auto stage_antisym = [&](double2* dst, bool have) {
@@ -452,9 +498,25 @@ static cudaError_t table_gen_nb(s2kit_cuda_plan* p, double* table, uint64_t shif
             const size_t smem_h = sizeof(double2) * (fft_padded_len(NB / 2) + 2 * fft_padded_len(NB / 4));
             cudaError_t e = ensure_smem(reinterpret_cast<const void*>(k_table_gen_half<NB>), smem_h);
             if (e != cudaSuccess) return e;
+            if (!p->d_ckpt) {  // first use: the recurrence state at every unit's first degree
+                const size_t nu = p->h_units.size() / 2;
+                e = cudaMalloc((void**)&p->d_ckpt, sizeof(double) * nu * NB);
+                if (e != cudaSuccess) return e;
+                p->own_ckpt = true;
+                if (!p->d_unit_first) {
+                    e = cudaMalloc((void**)&p->d_unit_first, sizeof(int) * p->h_unit_first.size());
+                    if (e == cudaSuccess)
+                        e = cudaMemcpyAsync(p->d_unit_first, p->h_unit_first.data(), sizeof(int) * p->h_unit_first.size(),
+                                            cudaMemcpyHostToDevice, p->stream);
+                    if (e != cudaSuccess) return e;
+                }
+                k_rec_checkpoints<NB><<<NB, NB / 8, 0, p->stream>>>(p->d_ckpt, p->d_unit_first, lch, p->d_nodes, p->d_seeds, p->d_rec);
+                e = cudaGetLastError();
+                if (e != cudaSuccess) return e;
+            }
             k_table_gen_half<NB><<<nunits, NB / 8, smem_h, p->stream>>>(table, p->d_order_start, shift, p->d_meta, p->d_units,
                                                                         unit_lo, unit_hi, lch, transposed, p->d_nodes,
-                                                                        p->d_seeds, p->d_rec, p->d_tw_b, p->d_q_b);
+                                                                        p->d_ckpt, p->d_rec, p->d_tw_b, p->d_q_b);
             return cudaGetLastError();
         }
     }

@@ -560,6 +560,10 @@ extern "C" int s2kit_cuda_plan_destroy(s2kit_cuda_plan* p) {
     for (void* q : own)
         if (q) cudaFree(q);
     if (p->own_table && p->d_table) cudaFree(p->d_table);
+    if (p->own_ckpt) {  // created on first use by whichever plan object generated tables first (kernels_table.cu)
+        if (p->d_ckpt) cudaFree(p->d_ckpt);
+        if (p->d_unit_first) cudaFree(p->d_unit_first);
+    }
     for (auto& s : p->prof_slots) {
         cudaEventDestroy(s.a);
         cudaEventDestroy(s.b);
@@ -588,6 +592,7 @@ extern "C" int s2kit_cuda_plan_clone(s2kit_cuda_plan** out, const s2kit_cuda_pla
     p->mu = new std::mutex();
     p->shares_tables = true;
     p->own_table = false;
+    p->own_ckpt = false;
     p->stream = nullptr;
     p->own_stream = true;
     p->host_pipe = nullptr;

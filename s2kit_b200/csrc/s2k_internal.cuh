@@ -135,6 +135,10 @@ struct s2kit_cuda_plan {
     int* d_units = nullptr;  // pairs (m, l0)
     std::vector<int> h_units;
     std::vector<int> h_unit_first;  // first unit of each order, [bw+1]
+    // half-grid generator (bw >= 1024): recurrence state at the first degree of every unit, [unit][prev, cur][bw/2]
+    double* d_ckpt = nullptr;
+    int* d_unit_first = nullptr;
+    bool own_ckpt = false;  // this object allocated them (a clone made before the first generation allocates its own)
     // Fly: scratch table for a group of orders
     size_t fly_tiles = 0;
 
