@@ -11,6 +11,8 @@
 // A DCT pair (real and imaginary column of one order) rides on ONE complex FFT of length 2bw: even/odd
 // reordering v[i] = x[2i], v[n-1-i] = x[2i+1] packed as v_re + i v_im, then the two spectra are separated
 // by conjugate symmetry.  Non-power-of-two bandwidths use the direct O(n^2) kernels at the end.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "s2k_fft.cuh"
@@ -261,6 +263,102 @@ __global__ void __launch_bounds__(N) k_phi_fft_inv_tma(double* __restrict__ rdat
         int k = fft_out_index<N>(e, t);
         irow[k] = xr[e];
         rrow[k] = xi[e];
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------ K1 / K6, large n
+// At n >= 2048 a CTA holds one or two rings, so the transposed write of k_phi_fft_fwd (and the gather of k_phi_fft_inv)
+// moves isolated 8- or 16-byte elements 8n bytes apart: 0.34 ms for a 268 MB pass at n = 4096, 0.8 TB/s.  Here the
+// longitude transform of a ring goes to / comes from a ring-major staging plane T[part][ring][order row] with fully
+// coalesced accesses straight from the FFT registers, and a separate tiled transpose moves 256-byte runs between T and
+// the spectral planes (also the exchange blocks of the sharded single-field path: PlaneView::rowbase).
+template <int N>
+__global__ void __launch_bounds__(N / 8) k_phi_rows_fwd(const double* __restrict__ rdata, const double* __restrict__ idata,
+                                                        long stride, double* __restrict__ T, double scale, int nrings,
+                                                        const double2* __restrict__ tw) {
+    constexpr int T8 = N / 8;
+    extern __shared__ double2 smem2[];
+    const int t = threadIdx.x, j = blockIdx.x, f = blockIdx.y;
+    const double* rrow = rdata + (long)f * stride + (long)j * N;
+    const double* irow = idata + (long)f * stride + (long)j * N;
+    double xr[8], xi[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        xr[e] = __ldg(rrow + t + e * T8);
+        xi[e] = __ldg(irow + t + e * T8);
+    }
+    fft_block<N>(xr, xi, smem2, t, 0, tw);
+    double* Tr = T + ((long)f * 2 * nrings + j) * N;
+    double* Ti = Tr + (long)nrings * N;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int k = fft_out_index<N>(e, t);
+        Tr[k] = xr[e] * scale;
+        Ti[k] = xi[e] * scale;
+    }
+}
+
+template <int N>
+__global__ void __launch_bounds__(N / 8) k_phi_rows_inv(const double* __restrict__ T, double* __restrict__ rdata,
+                                                        double* __restrict__ idata, long stride, int real_fmt, int nrings,
+                                                        const double2* __restrict__ tw) {
+    constexpr int T8 = N / 8;
+    extern __shared__ double2 smem2[];
+    const int t = threadIdx.x, j = blockIdx.x, f = blockIdx.y;
+    const double* Tr = T + ((long)f * 2 * nrings + j) * N;
+    const double* Ti = Tr + (long)nrings * N;
+    // inverse DFT through the forward one: feed (im, re), read back (im, re)   (FST_semi_memo.c:350)
+    double xr[8], xi[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int idx = fft_in_index<N>(e, t);
+        const bool mirror = real_fmt && idx > N / 2;  // conjugate mirror of row n - m' (FST_semi_memo.c:333-341)
+        const int row = mirror ? N - idx : idx;
+        double vr = __ldg(Tr + row), vi = __ldg(Ti + row);
+        if (idx == N / 2) vr = vi = 0.0;  // row bw is zero by definition (FST_semi_memo.c:283-284)
+        xr[e] = mirror ? -vi : vi;
+        xi[e] = vr;
+    }
+    fft_block<N>(xr, xi, smem2, t, 0, tw);
+    double* rrow = rdata + (long)f * stride + (long)j * N;
+    double* irow = idata + (long)f * stride + (long)j * N;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int k = fft_out_index<N>(e, t);
+        irow[k] = xr[e];
+        rrow[k] = xi[e];
+    }
+}
+
+// 32 x 32 tiles between T[part][ring j][order row m'] and the spectral planes S[part][row m' (rowbase)][ring j].
+// to_planes = 1: T -> S (forward), 0: S -> T (inverse).  Rows a format does not use are skipped (and never read).
+__global__ void __launch_bounds__(256) k_plane_transpose(double* __restrict__ T, double* __restrict__ S, int n, int nrings,
+                                                         int rows_kept, int to_planes, PlaneView pv) {
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int mp0 = blockIdx.x * 32, j0 = blockIdx.y * 32, part = blockIdx.z & 1, f = blockIdx.z >> 1;
+    double* Tp = T + ((long)f * 2 + part) * nrings * n;
+    double* Sp = S + (long)f * 2 * n * n + (long)part * pv.part_stride;
+    auto kept = [&](int mp) { return rows_kept == n ? (mp != n / 2) : (mp < rows_kept); };
+    if (to_planes) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) tile[ty + 8 * r][tx] = Tp[(long)(j0 + ty + 8 * r) * n + mp0 + tx];
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int mp = mp0 + ty + 8 * r;
+            if (kept(mp)) Sp[(pv.rowbase ? pv.rowbase[mp] : (long)mp * n) + j0 + tx] = tile[tx][ty + 8 * r];
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int mp = mp0 + ty + 8 * r;
+            tile[ty + 8 * r][tx] = kept(mp) ? Sp[(pv.rowbase ? pv.rowbase[mp] : (long)mp * n) + j0 + tx] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 4; ++r) Tp[(long)(j0 + ty + 8 * r) * n + mp0 + tx] = tile[tx][ty + 8 * r];
     }
 }
 
@@ -541,6 +639,20 @@ static cudaError_t set_smem(K kernel, size_t bytes) {
     return ensure_smem(reinterpret_cast<const void*>(kernel), bytes);
 }
 
+// S2KIT_CUDA_PHI_ROWS: 0 = always the transposing single-kernel K1 / K6, otherwise the smallest n that takes the staged path
+static bool phi_rows_enabled(int n) {
+    static const int from = [] {
+        const char* e = getenv("S2KIT_CUDA_PHI_ROWS");
+        return e ? atoi(e) : 4096;  // measured: n = 4096 K1 0.35 -> 0.21 ms, K6 0.30 -> 0.22 ms; n = 2048 no gain, n = 1024 slower
+    }();
+    return from > 0 && n >= from;
+}
+// ring-major staging plane of the large-n longitude transforms, as large as the spectral workspace; created on first use
+static cudaError_t ensure_phi_stage(s2kit_cuda_plan* p) {
+    if (p->d_T) return cudaSuccess;
+    return cudaMalloc((void**)&p->d_T, sizeof(double) * (size_t)p->chunk * 2 * p->n * p->n);
+}
+
 template <int N>
 static cudaError_t phi_fwd_n(s2kit_cuda_plan* p, const double* rdata, const double* idata, long stride, double* S,
                              int nfun, int rows_kept, const PlaneView& pv, int nrings) {
@@ -562,6 +674,20 @@ static cudaError_t phi_fwd_n(s2kit_cuda_plan* p, const double* rdata, const doub
         }
     }
     if (pv.lat_perm) return cudaErrorInvalidValue;  // only the TMA variant writes the reordered latitude layout
+    if constexpr (N >= 1024) {
+        if (phi_rows_enabled(N) && nrings % 32 == 0 && nfun <= p->chunk) {
+            // ring-major staging plane + tiled transpose (see k_phi_rows_fwd)
+            cudaError_t e = ensure_phi_stage(p);
+            if (e != cudaSuccess) return e;
+            const size_t smem_r = sizeof(double2) * fft_padded_len(N);
+            e = set_smem(k_phi_rows_fwd<N>, smem_r);
+            if (e != cudaSuccess) return e;
+            k_phi_rows_fwd<N><<<dim3(nrings, nfun), N / 8, smem_r, p->stream>>>(rdata, idata, stride, p->d_T,
+                                                                                 sqrt(2.0 * M_PI) / (double)N, nrings, p->d_tw_n);
+            k_plane_transpose<<<dim3(N / 32, nrings / 32, 2 * nfun), 256, 0, p->stream>>>(p->d_T, S, N, nrings, rows_kept, 1, pv);
+            return cudaGetLastError();
+        }
+    }
     constexpr int RS = phi_row_stride(N, LT);
     size_t smem = sizeof(double2) * LT * RS;
     cudaError_t e = set_smem(k_phi_fft_fwd<N, LT>, smem);
@@ -591,6 +717,20 @@ static cudaError_t phi_inv_n(s2kit_cuda_plan* p, const double* G, double* rdata,
         }
     }
     if (pv.lat_perm) return cudaErrorInvalidValue;
+    if constexpr (N >= 1024) {
+        if (phi_rows_enabled(N) && nrings % 32 == 0 && nfun <= p->chunk) {
+            cudaError_t e = ensure_phi_stage(p);
+            if (e != cudaSuccess) return e;
+            const size_t smem_r = sizeof(double2) * fft_padded_len(N);
+            e = set_smem(k_phi_rows_inv<N>, smem_r);
+            if (e != cudaSuccess) return e;
+            k_plane_transpose<<<dim3(N / 32, nrings / 32, 2 * nfun), 256, 0, p->stream>>>(p->d_T, const_cast<double*>(G), N, nrings,
+                                                                                          real_fmt ? N / 2 : N, 0, pv);
+            k_phi_rows_inv<N><<<dim3(nrings, nfun), N / 8, smem_r, p->stream>>>(p->d_T, rdata, idata, stride, real_fmt, nrings,
+                                                                                 p->d_tw_n);
+            return cudaGetLastError();
+        }
+    }
     constexpr int RS = phi_row_stride(N, LT);
     size_t smem = sizeof(double2) * LT * RS;
     cudaError_t e = set_smem(k_phi_fft_inv<N, LT>, smem);

@@ -553,7 +553,7 @@ extern "C" int s2kit_cuda_plan_destroy(s2kit_cuda_plan* p) {
     void* shared[] = {p->d_wv, p->d_sv, p->d_weights, p->d_sin, p->d_tw_n, p->d_tw_b, p->d_q_n, p->d_q_b, p->d_nodes,
                       p->d_seeds, p->d_rec, p->d_meta, p->d_rt_start, p->d_order_start, p->d_units,
                       p->d_sub_off,  p->d_sub_list, p->d_isub_off, p->d_isub_list, p->d_iq_off, p->d_iq_list};
-    void* own[] = {p->d_S, p->d_X, p->d_coef, p->d_coef2, p->d_filt, p->d_stage};
+    void* own[] = {p->d_S, p->d_T, p->d_X, p->d_coef, p->d_coef2, p->d_filt, p->d_stage};
     if (!p->shares_tables)
         for (void* q : shared)
             if (q) cudaFree(q);
@@ -598,7 +598,7 @@ extern "C" int s2kit_cuda_plan_clone(s2kit_cuda_plan** out, const s2kit_cuda_pla
     p->host_pipe = nullptr;
     p->aux_stream = nullptr;
     p->ev_fork = p->ev_join = nullptr;
-    p->d_S = p->d_X = p->d_coef = p->d_coef2 = p->d_filt = p->d_stage = nullptr;
+    p->d_S = p->d_T = p->d_X = p->d_coef = p->d_coef2 = p->d_filt = p->d_stage = nullptr;
     p->stage_doubles = 0;
     p->prof_slots.clear();
     p->prof_used = 0;

@@ -146,6 +146,7 @@ struct s2kit_cuda_plan {
     double* d_S = nullptr;  // spectral planes  [chunk][2][n][n]
     CUtensorMap tma_S;      // d_S as a 3-D tensor (latitude, order row, plane) with 8 x 256 x 1 boxes, 64-byte swizzle
     bool tma_S_ok = false;
+    double* d_T = nullptr;  // ring-major staging of the longitude transforms at n = 4096 [chunk][2][rings][n]; on first use
     double* d_X = nullptr;  // cosine planes    [chunk][n][2][bw]
     double* d_coef = nullptr;  // [chunk][2][bw*bw]   conv intermediates / staging
     double* d_coef2 = nullptr;
