@@ -24,6 +24,24 @@ namespace s2k {
 // a double2 row stride == 8/LT (mod 8) makes those 128-bit accesses conflict-free.
 __host__ __device__ constexpr int phi_row_stride(int n, int lt) { return ((fft_padded_len(n) + 7) / 8) * 8 + (8 / lt); }
 
+
+// fft_block, or for the all-radix-8 lengths its variant whose pass twiddles were requested before the data loads
+template <int N>
+struct FftPlan {
+    static constexpr bool R8 = (ilog2(N) % 3 == 0) && N >= 512;
+    FftTw8<R8 ? N : 512> f;
+    __device__ __forceinline__ void prefetch(int t, const double2* __restrict__ tw) {
+        if constexpr (R8) f = fft_r8_twiddles<N>(t, tw);
+    }
+    __device__ __forceinline__ void run(double (&xr)[8], double (&xi)[8], double2* sx, int t, int group,
+                                        const double2* __restrict__ tw) {
+        if constexpr (R8)
+            fft_block_r8<N>(xr, xi, sx, t, group, f);
+        else
+            fft_block<N>(xr, xi, sx, t, group, tw);
+    }
+};
+
 __device__ __forceinline__ void cp_async8_g2s(double* smem_dst, const double* gsrc) {
     unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(a), "l"(gsrc));
@@ -282,13 +300,15 @@ __global__ void __launch_bounds__(N / 8) k_phi_rows_fwd(const double* __restrict
     const int t = threadIdx.x, j = blockIdx.x, f = blockIdx.y;
     const double* rrow = rdata + (long)f * stride + (long)j * N;
     const double* irow = idata + (long)f * stride + (long)j * N;
+    FftPlan<N> fp;
+    fp.prefetch(t, tw);
     double xr[8], xi[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         xr[e] = __ldg(rrow + t + e * T8);
         xi[e] = __ldg(irow + t + e * T8);
     }
-    fft_block<N>(xr, xi, smem2, t, 0, tw);
+    fp.run(xr, xi, smem2, t, 0, tw);
     double* Tr = T + ((long)f * 2 * nrings + j) * N;
     double* Ti = Tr + (long)nrings * N;
 #pragma unroll
@@ -309,6 +329,8 @@ __global__ void __launch_bounds__(N / 8) k_phi_rows_inv(const double* __restrict
     const double* Tr = T + ((long)f * 2 * nrings + j) * N;
     const double* Ti = Tr + (long)nrings * N;
     // inverse DFT through the forward one: feed (im, re), read back (im, re)   (FST_semi_memo.c:350)
+    FftPlan<N> fp;
+    fp.prefetch(t, tw);
     double xr[8], xi[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -320,7 +342,7 @@ __global__ void __launch_bounds__(N / 8) k_phi_rows_inv(const double* __restrict
         xr[e] = mirror ? -vi : vi;
         xi[e] = vr;
     }
-    fft_block<N>(xr, xi, smem2, t, 0, tw);
+    fp.run(xr, xi, smem2, t, 0, tw);
     double* rrow = rdata + (long)f * stride + (long)j * N;
     double* irow = idata + (long)f * stride + (long)j * N;
 #pragma unroll
@@ -384,6 +406,8 @@ __global__ void __launch_bounds__(N / 8 * FPB) k_dct_fwd(const double* __restric
     const long rowoff = (long)(pv.rowlist ? rsel : mp) * pv.lrow_stride;
     const double* Sr = S + (long)f * 2 * N * N + rowoff;
     const double* Si = Sr + pv.part_stride;
+    FftPlan<N> fp;
+    fp.prefetch(t, tw);
     double xr[8], xi[8];
     if constexpr (PEER) {
         // Single field over the GPUs of one process: segment s of the row lives in peer s's memory -- the ring -> order
@@ -423,7 +447,7 @@ __global__ void __launch_bounds__(N / 8 * FPB) k_dct_fwd(const double* __restric
             xi[e] = __ldg(Si + at) * wj;
         }
     }
-    fft_block<N>(xr, xi, sx, t, g, tw);
+    fp.run(xr, xi, sx, t, g, tw);
     // Separation of the two real spectra needs Z[k] and Z[n-k], k < bw: Z[k] is still in this thread's registers, so
     // only the upper half of the spectrum (indices > bw) goes through shared memory -- half a write and half a read
     // per point instead of a full write and two reads.
@@ -489,6 +513,8 @@ __global__ void __launch_bounds__(N / 8 * FPB) k_dct_inv(const double* __restric
     // instead of eight 16-byte loads -- K5 sits at 95 % of the LSU pipe with the FP64 pipe half idle
     // (profiles/r1_ncu_full_metrics_final2.csv)
     const double2 q0 = __ldg(qtab + t);
+    FftPlan<N> fp;
+    fp.prefetch(t, tw);
     double xr[8], xi[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -507,7 +533,7 @@ __global__ void __launch_bounds__(N / 8 * FPB) k_dct_inv(const double* __restric
         xr[e] = wi;  // swapped: inverse DFT through the forward transform
         xi[e] = wr;
     }
-    fft_block<N>(xr, xi, sx, t, g, tw);
+    fp.run(xr, xi, sx, t, g, tw);
     double sign = ((mp > B) && (m & 1)) ? -out_scale : out_scale;  // (-1)^m for negative orders
     const long rowoff = (long)(pv.rowlist ? rsel : mp) * pv.lrow_stride;
     if constexpr (PEER) {

@@ -191,6 +191,67 @@ struct FftRest {
     }
 };
 
+
+// ---- all-radix-8 transforms (N = 512, 4096) with the pass twiddles loaded UP FRONT ---------------------------------
+// In fft_block every pass starts with a table load whose latency (an L2 round trip under load) sits between two
+// barriers, on the critical path of a CTA that owns one long transform.  Here the (at most three) base twiddles of a
+// thread are requested before the first pass, next to the data loads, and are long there when the passes need them.
+template <int N, int NS>
+__device__ __forceinline__ void fft_r8_pass_w(double (&xr)[8], double (&xi)[8], double2 w1) {
+    double2 w[8];
+    w[1] = w1;
+    w[2] = cmul(w[1], w[1]);
+    w[3] = cmul(w[2], w[1]);
+    w[4] = cmul(w[2], w[2]);
+    w[5] = cmul(w[4], w[1]);
+    w[6] = cmul(w[3], w[3]);
+    w[7] = cmul(w[4], w[3]);
+#pragma unroll
+    for (int r = 1; r < 8; ++r) {
+        const double a = xr[r], b = xi[r];
+        xr[r] = a * w[r].x - b * w[r].y;
+        xi[r] = a * w[r].y + b * w[r].x;
+    }
+    dft8(xr, xi);
+}
+template <int N>
+struct FftTw8 {
+    double2 w[3];
+};
+template <int N>
+__device__ __forceinline__ FftTw8<N> fft_r8_twiddles(int t, const double2* __restrict__ tw) {
+    static_assert(ilog2(N) % 3 == 0 && N >= 64 && N <= 4096, "N = 64, 512 or 4096");
+    FftTw8<N> f;
+    f.w[0] = __ldg(&tw[(t & 7) * (N / 64)]);
+    f.w[1] = (N >= 512) ? __ldg(&tw[(t & 63) * (N / 512)]) : make_double2(1.0, 0.0);
+    f.w[2] = (N >= 4096) ? __ldg(&tw[(t & 511) * (N / 4096)]) : make_double2(1.0, 0.0);
+    return f;
+}
+template <int N>
+__device__ __forceinline__ void fft_block_r8(double (&xr)[8], double (&xi)[8], double2* sx, int t, int group,
+                                             const FftTw8<N>& f) {
+    dft8(xr, xi);
+    fft_sync<N>(group);
+    fft_pass_write<N, 1, 8>(xr, xi, sx, t);
+    fft_sync<N>(group);
+    fft_pass_read<N, 8>(xr, xi, sx, t);
+    fft_r8_pass_w<N, 8>(xr, xi, f.w[0]);
+    if constexpr (N >= 512) {
+        fft_sync<N>(group);
+        fft_pass_write<N, 8, 8>(xr, xi, sx, t);
+        fft_sync<N>(group);
+        fft_pass_read<N, 8>(xr, xi, sx, t);
+        fft_r8_pass_w<N, 64>(xr, xi, f.w[1]);
+    }
+    if constexpr (N >= 4096) {
+        fft_sync<N>(group);
+        fft_pass_write<N, 64, 8>(xr, xi, sx, t);
+        fft_sync<N>(group);
+        fft_pass_read<N, 8>(xr, xi, sx, t);
+        fft_r8_pass_w<N, 512>(xr, xi, f.w[2]);
+    }
+}
+
 // (cos, sin)(pi k / 2n) for k = t + s n/8 is (cos, sin)(pi t / 2n) rotated by pi s / 16: the DCT kernels load one entry
 // of the quarter-wave table per thread and rotate it by these constants instead of loading eight entries (K5 sat at
 // 95 % of the LSU pipe with the FP64 pipe half idle, profiles/r1_ncu_full_metrics_final2.csv).
