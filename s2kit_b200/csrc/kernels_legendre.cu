@@ -290,15 +290,20 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_inv(
         int f = f0 + fl;
         double* d0 = Cs + col * CS;
         double* d1 = Cs + (PC + col) * CS;
+        // The contraction reads panel rows < 8 ceil(h / 8) only (whole row tiles): just the (at most 7) rows between a
+        // column's last degree and the end of its last row tile have to be cleared -- they meet zero table padding, which
+        // must not see NaN garbage.  (Clearing up to CS cost 10 % of the kernel's samples at high orders: short columns,
+        // long tails -- profiles/r2_dram_traffic.json capture, source view.)
+        const int cnt = bw - m, h0 = (cnt + 1) / 2, h1 = cnt / 2;  // entries of parity 0 / 1
+        const int e0 = (h0 + 7) & ~7, e1 = (h1 + 7) & ~7;
         if (f >= nfun || (sgn && m == 0)) {
-            for (int c = lane; c < CS; c += 32) d0[c] = d1[c] = 0.0;
+            for (int c = lane; c < e0; c += 32) d0[c] = d1[c] = 0.0;
             continue;
         }
         const double* src = (part ? ico : rco) + (long)f * coef_stride + (sgn ? base_neg : base_pos);
-        const int cnt = bw - m, h0 = (cnt + 1) / 2, h1 = cnt / 2;  // entries of parity 0 / 1
         for (int o = lane; o < cnt; o += 32) cp_async8(((o & 1) ? d1 : d0) + (o >> 1), src + o);
-        for (int c = h0 + lane; c < CS; c += 32) d0[c] = 0.0;
-        for (int c = h1 + lane; c < CS; c += 32) d1[c] = 0.0;
+        if (h0 + lane < e0) d0[h0 + lane] = 0.0;
+        if (h1 + lane < e1) d1[h1 + lane] = 0.0;
     }
     cp_async_wait_all();
     __syncthreads();
