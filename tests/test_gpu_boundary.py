@@ -298,3 +298,18 @@ def test_large_bandwidth_switches_keep_parity(env):
                        text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "1 passed" in r.stdout, r.stdout[-500:]
+
+
+@pytest.mark.parametrize("env", [{"S2KIT_CUDA_TABLE_FULL": "1"}, {"S2KIT_CUDA_PHI_ROWS": "2048"}, {"S2KIT_CUDA_PHI_ROWS": "0"},
+                                 {"S2KIT_CUDA_TABLE_LCH": "32"}])
+def test_bw1024_switches_keep_parity(env):
+    """Switches that only matter at bw >= 1024: the full-length table generator instead of the half-grid one, the staged
+    longitude transforms (ring-major plane + tiled transpose) switched on at n = 2048 / off everywhere, and smaller
+    generator work units (checkpoint spacing).  The bw = 1024 Memo and Fly reference tests in a child process."""
+    e = dict(os.environ, **env)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_large.py"),
+                        os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-q", "-x", "-m", "gpu", "-k",
+                        "(test_memo_large_bw_vs_reference_samples and 1024) or test_single_field_bw1024_fly"], env=e, cwd=ROOT,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "2 passed" in r.stdout, r.stdout[-500:]
