@@ -392,7 +392,7 @@ template <int N, int FPB, bool PEER>
 __global__ void __launch_bounds__(N / 8 * FPB) k_dct_fwd(const double* __restrict__ S, double* __restrict__ X,
                                                          const double* __restrict__ weights, int ridx_lo, int ridx_hi,
                                                          const double2* __restrict__ tw,
-                                                         const double2* __restrict__ qtab, PlaneView pv, PeerSegs peers) {
+                                                         const double2* __restrict__ qtab, PlaneView pv, const __grid_constant__ PeerSegs peers) {
     constexpr int T8 = N / 8, B = N / 2, NP = fft_padded_len(N);
     extern __shared__ double2 smem2[];
     const int tid = threadIdx.x, g = tid / T8, t = tid % T8;
@@ -495,7 +495,7 @@ template <int N, int FPB, bool PEER>
 __global__ void __launch_bounds__(N / 8 * FPB) k_dct_inv(const double* __restrict__ V, double* __restrict__ G,
                                                          const double* __restrict__ sinv, int ridx_lo, int ridx_hi,
                                                          double out_scale, const double2* __restrict__ tw,
-                                                         const double2* __restrict__ qtab, PlaneView pv, PeerSegs peers) {
+                                                         const double2* __restrict__ qtab, PlaneView pv, const __grid_constant__ PeerSegs peers) {
     constexpr int T8 = N / 8, B = N / 2, NP = fft_padded_len(N);
     extern __shared__ double2 smem2[];
     const int tid = threadIdx.x, g = tid / T8, t = tid % T8;
