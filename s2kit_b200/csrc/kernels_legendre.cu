@@ -393,6 +393,148 @@ __global__ void __launch_bounds__(LEG_WARPS * 32, 3) k_legendre_inv(
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------ K4, quad units
+// The batched contraction with the inner loop of k_inv_flow (kernels_flow.cu) inside the ordinary one-CTA-per-(order, 32
+// columns) grid: a warp owns FOUR adjacent column tiles of one parity block (16 accumulator fragments, 32 DMMAs per
+// row-tile step, every coefficient fragment feeds four DMMAs instead of two) and its four table tiles of a step -- 2 KB,
+// contiguous -- arrive by ONE cp.async.bulk copy (TMA) into a two-stage ring.  Eight units per CTA = eight warps; the
+// units are dealt so that the two warps of a sub-partition get a long and a short one.
+constexpr int LQ = 4, LQ_STAGES = 2;
+
+__global__ void __launch_bounds__(LEG_WARPS * 32, 2) k_legendre_inv_q(
+    const double* __restrict__ table, const uint64_t* __restrict__ order_start, uint64_t table_shift,
+    const double* __restrict__ rco, const double* __restrict__ ico, long coef_stride, double* __restrict__ V, int bw, int nfun,
+    int m_lo, int real_fmt, unsigned l2pf_cap) {
+    constexpr int NC = 32;
+    extern __shared__ __align__(128) double smem[];
+    const int n = 2 * bw, CS = panel_stride(bw);
+    const int m = m_lo + blockIdx.y;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q4 = lane & 3;
+    const int cols_per_fn = real_fmt ? 2 : 4, NF = NC / cols_per_fn;
+    const int f0 = blockIdx.x * NF;
+    double* Cs = smem;  // [2][NC][CS], row index r = (l-m)>>1
+    double2* ring = reinterpret_cast<double2*>(Cs + 2 * NC * CS) + warp * LQ_STAGES * LQ * 32;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<double2*>(Cs + 2 * NC * CS) + LEG_WARPS * LQ_STAGES * LQ * 32);
+    const unsigned bar0 = static_cast<unsigned>(__cvta_generic_to_shared(bars + warp * LQ_STAGES));
+    if (lane == 0) {
+        for (int s = 0; s < LQ_STAGES; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * s) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    prefetch_order_l2(table + (order_start[m] - table_shift) * 64, order_start[m + 1] - order_start[m], tid, blockDim.x, l2pf_cap);
+    const int base_pos = coef_base(m, bw), base_neg = coef_base(-m, bw);
+    for (int col = warp; col < NC; col += LEG_WARPS) {
+        const int fl = col / cols_per_fn, sub = col % cols_per_fn;
+        const int sgn = real_fmt ? 0 : (sub >> 1), part = sub & 1, f = f0 + fl;
+        double* d0 = Cs + col * CS;
+        double* d1 = Cs + (NC + col) * CS;
+        const int cnt = bw - m, h0 = (cnt + 1) / 2, h1 = cnt / 2;  // entries of parity 0 / 1
+        const int e0 = (h0 + 7) & ~7, e1 = (h1 + 7) & ~7;
+        if (f >= nfun || (sgn && m == 0)) {
+            for (int c = lane; c < e0; c += 32) d0[c] = d1[c] = 0.0;
+            continue;
+        }
+        const double* src = (part ? ico : rco) + (long)f * coef_stride + (sgn ? base_neg : base_pos);
+        for (int o = lane; o < cnt; o += 32) cp_async8(((o & 1) ? d1 : d0) + (o >> 1), src + o);
+        if (h0 + lane < e0) d0[h0 + lane] = 0.0;
+        if (h1 + lane < e1) d1[h1 + lane] = 0.0;
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    // unit of this warp: parity p, column tiles ct0 .. ct0 + 3.  Quads 0 (most row tiles) .. 3 (fewest) dealt as 0 0 1 1 3 3 2 2:
+    // warps w and w + 4 share a sub-partition and get quads (0, 3) or (1, 2)
+    const int p = warp & 1;
+    const int quad = (0x22331100 >> (4 * warp)) & 0xf;
+    const int nct = (((bw + 1) / 2) + 7) >> 3;
+    const int ct0 = LQ * quad;
+    if (ct0 >= nct) return;
+    const BlockMeta mb0 = block_meta_of(m, 0, bw);
+    const BlockMeta mb = p ? block_meta_of(m, 1, bw) : mb0;
+    const double* tblk = table + ((order_start[m] - table_shift) + (p ? block_tiles_of(mb0) : 0u)) * 64;
+    const int rt_min = first_row_tile_reaching(mb, ct0);
+    const int cnt = mb.nrt - rt_min;
+    double acc[LQ][NC / 8][2];
+#pragma unroll
+    for (int c = 0; c < LQ; ++c)
+#pragma unroll
+        for (int j = 0; j < NC / 8; ++j) acc[c][j][0] = acc[c][j][1] = 0.0;
+    const double* cp = Cs + (p * NC + g) * CS + q4;
+    auto tiles_at = [&](int rt) {
+        const int t = tiles_in_row(mb, rt) - ct0;
+        return t < LQ ? t : LQ;
+    };
+    auto issue = [&](int i) {
+        const int rt = rt_min + i, s = i % LQ_STAGES;
+        bulk_tile_copy(ring + s * LQ * 32, tblk + ((uint64_t)row_tile_start_of(mb, rt) + ct0) * 64, 512u * (unsigned)tiles_at(rt),
+                       bar0 + 8 * s);
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < LQ_STAGES; ++s)
+            if (s < cnt) issue(s);
+    }
+    unsigned phases = 0;
+#pragma unroll 1
+    for (int i = 0; i < cnt; ++i) {
+        const int rt = rt_min + i, s = i % LQ_STAGES;
+        const int nv = tiles_at(rt);
+        double av[NC / 8][2];
+#pragma unroll
+        for (int j = 0; j < NC / 8; ++j) {
+            av[j][0] = cp[j * 8 * CS + 8 * rt];
+            av[j][1] = cp[j * 8 * CS + 8 * rt + 4];
+        }
+        bulk_wait(bar0 + 8 * s, (phases >> s) & 1u);
+        phases ^= 1u << s;
+        double2 bv[LQ];
+#pragma unroll
+        for (int c = 0; c < LQ; ++c) bv[c] = ring[(s * LQ + c) * 32 + lane];
+        if (nv == LQ) {
+#pragma unroll
+            for (int c = 0; c < LQ; ++c)
+#pragma unroll
+                for (int j = 0; j < NC / 8; ++j) dmma(acc[c][j], av[j][0], bv[c].x);
+#pragma unroll
+            for (int c = 0; c < LQ; ++c)
+#pragma unroll
+                for (int j = 0; j < NC / 8; ++j) dmma(acc[c][j], av[j][1], bv[c].y);
+        } else {
+#pragma unroll
+            for (int c = 0; c < LQ - 1; ++c)
+                if (c < nv) {
+#pragma unroll
+                    for (int j = 0; j < NC / 8; ++j) dmma(acc[c][j], av[j][0], bv[c].x);
+#pragma unroll
+                    for (int j = 0; j < NC / 8; ++j) dmma(acc[c][j], av[j][1], bv[c].y);
+                }
+        }
+        if (i + LQ_STAGES < cnt) {
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(i + LQ_STAGES);
+            }
+        }
+    }
+    // epilogue: lane holds column 8j + g, cosine slots 8 (ct0 + c) + 2 q4 + {0, 1} of parity p
+    const int sgn = real_fmt ? 0 : ((g >> 1) & 1), part = g & 1;
+    const int fl0 = real_fmt ? (g >> 1) : (g >> 2), flstep = real_fmt ? 4 : 2;
+    if (sgn && m == 0) return;
+    const int mp = sgn ? n - m : m, hp = p ? bw / 2 : (bw + 1) / 2;
+#pragma unroll
+    for (int j = 0; j < NC / 8; ++j) {
+        const int f = f0 + fl0 + j * flstep;
+        if (f >= nfun) continue;
+        double* d = V + (((long)f * n + mp) * 2 + part) * bw + p * ((bw + 1) / 2) + 8 * ct0 + 2 * q4;
+#pragma unroll
+        for (int c = 0; c < LQ; ++c) {
+            const int c0 = 8 * (ct0 + c) + 2 * q4;
+            if (c0 + 1 < hp) *reinterpret_cast<double2*>(d + 8 * c) = make_double2(acc[c][j][0], acc[c][j][1]);
+        }
+    }
+}
+
 // Orders up to this many bytes are pulled into L2 by one bulk prefetch at CTA start.  Larger orders (single large-bw
 // fields) are streamed by the register ring alone: with hundreds of CTAs in flight a whole-order prefetch of
 // megabytes each overruns L2 and the data is fetched twice.
@@ -516,6 +658,22 @@ cudaError_t launch_legendre_inv(s2kit_cuda_plan* p, const double* table, uint64_
     int rs = pick_rowsplit(p->bw, (nfun + NF - 1) / NF, m_hi - m_lo);
     int slot = prof_begin(p, S2KIT_K_LEGENDRE_INV);
     cudaError_t e;
+    static const int quad = [] {  // S2KIT_CUDA_K4_QUAD=1: four-column-tile units with TMA-staged table tiles
+        const char* ev = getenv("S2KIT_CUDA_K4_QUAD");
+        return (ev && ev[0] == '1') ? 1 : 0;
+    }();
+    if (quad && nc == 32 && p->bw == 256 && !order_list && !(p->table_single && table == p->d_table)) {
+        const size_t smem = sizeof(double) * 2 * 32 * panel_stride(p->bw) + sizeof(double2) * LEG_WARPS * LQ_STAGES * LQ * 32 +
+                            8 * LEG_WARPS * LQ_STAGES;
+        e = ensure_smem(reinterpret_cast<const void*>(k_legendre_inv_q), smem);
+        if (e == cudaSuccess) {
+            k_legendre_inv_q<<<dim3((nfun + NF - 1) / NF, m_hi - m_lo), LEG_WARPS * 32, smem, p->stream>>>(
+                table, p->d_order_start, shift, rco, ico, coef_stride, V, p->bw, nfun, m_lo, real_fmt, l2_prefetch_cap(32));
+            e = cudaGetLastError();
+        }
+        prof_end(p, slot);
+        return e;
+    }
     switch (nc) {
         case 4: e = leg_inv_nc<8, 4>(p, table, shift, rco, ico, coef_stride, V, nfun, m_lo, m_hi, real_fmt, rs, order_list); break;
         case 8: e = leg_inv_nc<8>(p, table, shift, rco, ico, coef_stride, V, nfun, m_lo, m_hi, real_fmt, rs, order_list); break;
