@@ -127,6 +127,32 @@ def test_bw2048_orders_beyond_the_reference_vs_mpmath(plan2048):
         assert len(got) == bw - m
 
 
+@pytest.mark.parametrize("bw", [1024, 2048])
+def test_real_format_agrees_with_complex_format_at_large_bw(s2, oracle_mod, plan2048, bw):
+    """REAL data format at the large bandwidths (FST_semi_memo.c:110-145, 300-341: only the orders m >= 0 are transformed,
+    the others follow from the symmetry of a real field).  The committed reference samples are COMPLEX; here the REAL path
+    -- at n = 4096 the staged longitude transforms with half of the spectral rows, the conjugate mirror on the way back --
+    must agree with the COMPLEX path on a real field, in both directions."""
+    n = 2 * bw
+    P = plan2048 if bw == 2048 else s2.Plan(bw, s2.MEMO, max_batch=1)
+    rng = np.random.RandomState(bw + 1)
+    rd, zero = rng.uniform(-1, 1, (n, n)), np.zeros((n, n))
+    cr, ci = P.forward(rd, zero, 0)
+    gr, gi = P.forward(rd, zero, 1)
+    scale = max(np.abs(cr).max(), np.abs(ci).max())
+    assert np.isfinite(gr).all() and np.isfinite(gi).all()
+    assert max(np.abs(gr - cr).max(), np.abs(gi - ci).max()) / scale < TOL
+    # inverse of the coefficients of a real field (test_s2_semi_memo.c:156-172 symmetry)
+    rc, ic = seeded_coeffs(oracle_mod, bw, seed=77)
+    xr, xi = P.inverse(rc, ic, 0)
+    yr, _ = P.inverse(rc, ic, 1)
+    gscale = np.abs(xr).max()
+    assert np.abs(xi).max() / gscale < 1e-9  # a real field
+    assert np.abs(yr - xr).max() / gscale < TOL
+    if bw != 2048:
+        P.close()
+
+
 def test_c5_bw2048_inverse_vs_composed_reference(s2, oracle_mod, large, plan2048):
     """InvFSTSemiMemo at bw = 2048.  The reference's own 2-D inverse is NaN everywhere at this size; the golden is
     composed from its per-order InvDLTSemi for |m| <= 2043 (make_golden_large.py), input = seed-1000 coefficients
