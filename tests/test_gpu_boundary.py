@@ -301,11 +301,12 @@ def test_large_bandwidth_switches_keep_parity(env):
 
 
 @pytest.mark.parametrize("env", [{"S2KIT_CUDA_TABLE_FULL": "1"}, {"S2KIT_CUDA_PHI_ROWS": "2048"}, {"S2KIT_CUDA_PHI_ROWS": "0"},
-                                 {"S2KIT_CUDA_TABLE_LCH": "32"}])
+                                 {"S2KIT_CUDA_TABLE_LCH": "32"}, {"S2KIT_CUDA_FLY_RING_MB": "256"}])
 def test_bw1024_switches_keep_parity(env):
     """Switches that only matter at bw >= 1024: the full-length table generator instead of the half-grid one, the staged
     longitude transforms (ring-major plane + tiled transpose) switched on at n = 2048 / off everywhere, and smaller
-    generator work units (checkpoint spacing).  The bw = 1024 Memo and Fly reference tests in a child process."""
+    generator work units (checkpoint spacing), and several Fly order groups per transform.  The bw = 1024 Memo and Fly
+    reference tests in a child process."""
     e = dict(os.environ, **env)
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_large.py"),
                         os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-q", "-x", "-m", "gpu", "-k",

@@ -153,6 +153,26 @@ def test_real_format_agrees_with_complex_format_at_large_bw(s2, oracle_mod, plan
         P.close()
 
 
+def test_fly_equals_memo_at_bw2048(s2, oracle_mod, plan2048):
+    """FSTSemiFly / InvFSTSemiFly at bw = 2048: the tables are generated per call in six order groups (2 GiB scratch,
+    FST_semi_fly.c:96,259-261) by the half-grid generator with a tile offset per group, and both directions read A-order
+    tiles.  Same tables as the resident (Memo) plan, so the results must agree to rounding."""
+    bw = 2048
+    n = 2 * bw
+    F = s2.Plan(bw, s2.FLY, max_batch=1)
+    rng = np.random.RandomState(4096)
+    rd, idt = rng.uniform(-1, 1, (n, n)), rng.uniform(-1, 1, (n, n))
+    mr, mi = plan2048.forward(rd, idt, 0)
+    fr, fi = F.forward(rd, idt, 0)
+    scale = max(np.abs(mr).max(), np.abs(mi).max())
+    assert max(np.abs(fr - mr).max(), np.abs(fi - mi).max()) / scale < 1e-12
+    rc, ic = seeded_coeffs(oracle_mod, bw, seed=5)
+    xr, xi = plan2048.inverse(rc, ic, 0)
+    yr, yi = F.inverse(rc, ic, 0)
+    assert max(np.abs(yr - xr).max(), np.abs(yi - xi).max()) / np.abs(xr).max() < 1e-12
+    F.close()
+
+
 def test_c5_bw2048_inverse_vs_composed_reference(s2, oracle_mod, large, plan2048):
     """InvFSTSemiMemo at bw = 2048.  The reference's own 2-D inverse is NaN everywhere at this size; the golden is
     composed from its per-order InvDLTSemi for |m| <= 2043 (make_golden_large.py), input = seed-1000 coefficients
