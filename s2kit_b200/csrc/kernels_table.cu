@@ -299,29 +299,61 @@ __global__ void __launch_bounds__(NB / 8, 640 / (NB / 8)) k_table_gen_half(
                 xi[e] = v.y;
             }
             fft_block<M, 2>(xr, xi, sa, t, 0, tw);
+            // Separation needs Z[k] and Z[M-k].  A thread keeps the lower half of its outputs (k < M/2) in registers and
+            // fetches their partners from the upper half, which alone goes through shared memory (at k - M/2); it then
+            // finishes BOTH columns k and M - k of the two rows: (cos, sin)(pi (M-k)/2M) = (sin, cos)(pi k/2M).
+            constexpr int RA = fft_last_radix(M);
             fft_sync<M>(0);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) sa[fft_pad(fft_out_index<M>(e, t))] = make_double2(xr[e], xi[e]);
+            for (int e = 0; e < 8; ++e)
+                if (fft_slot<RA>(e) >= 4) sa[fft_pad(fft_out_index<M>(e, t) - M / 2)] = make_double2(xr[e], xi[e]);
             fft_sync<M>(0);
             const bool two = l + 2 < NB;
             const int len_a = mb0.len0 + ra, len_b = two ? len_a + 1 : 0;
             const int pad_a = half_padded_len(mb0, ra), pad_b = two ? half_padded_len(mb0, ra + 1) : 0;
             const uint32_t rta = half_row_tile0(mb0, mb0, 0, ra), rtb = half_row_tile0(mb0, mb0, 0, ra + 1);
-            // column j = t + i TA: the tile advances by TA/8 per i, the position inside the tile (j & 7 = t & 7) never changes
+            // column k = t + s TA: the tile advances by TA/8 per s, the position inside the tile (t & 7) never changes;
+            // column M - k: tile (M - t)/8 - s TA/8, position (M - t) & 7
+            const int cm = M - t;
             double* const pa = otab + ((uint64_t)rta + (uint32_t)(t >> 3)) * 64 + eoff(ra, t & 7);
             double* const pb = otab + ((uint64_t)rtb + (uint32_t)(t >> 3)) * 64 + eoff(ra + 1, t & 7);
+            double* const pam = otab + ((uint64_t)rta + (uint32_t)(cm >> 3)) * 64 + eoff(ra, cm & 7);
+            double* const pbm = otab + ((uint64_t)rtb + (uint32_t)(cm >> 3)) * 64 + eoff(ra + 1, cm & 7);
+            const double scale = 2.0 * fudge;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int j = t + i * TA;
-                if (j < pad_a || j < pad_b) {
-                    const int nj = (M - j) & (M - 1);
-                    const double2 za = sa[fft_pad(j)], zb = sa[fft_pad(nj)];
-                    const double2 q = quarter_rot(q0, i);  // (cos, sin)(pi j / 2M)
-                    double scale = 2.0 * fudge;
-                    if (j == 0) scale *= 0.70710678118654752440;  // cospml.c:205
-                    if (j < pad_a) pa[i * (TA / 8) * 64] = j < len_a ? (q.x * (za.x + zb.x) + q.y * (za.y - zb.y)) * scale : 0.0;
-                    if (j < pad_b) pb[i * (TA / 8) * 64] = j < len_b ? (q.x * (za.y + zb.y) - q.y * (za.x - zb.x)) * scale : 0.0;
+            for (int e = 0; e < 8; ++e) {
+                const int sl = fft_slot<RA>(e);
+                if (sl >= 4) continue;
+                const int k = t + sl * TA, km = M - k;  // k < M/2 < km (km = M for k = 0: no such column)
+                if (k >= pad_a && k >= pad_b && km >= pad_a && km >= pad_b) continue;
+                const double ar = xr[e], ai = xi[e];
+                double br = ar, bi = ai;  // k = 0: Z[M] = Z[0]
+                if (k != 0) {
+                    const double2 zb = sa[fft_pad(M / 2 - k)];
+                    br = zb.x;
+                    bi = zb.y;
                 }
+                const double2 q = quarter_rot(q0, sl);  // (cos, sin)(pi k / 2M)
+                const double sr = ar + br, dr = ar - br, si = ai + bi, di = ai - bi;
+                const double sc0 = (k == 0) ? scale * 0.70710678118654752440 : scale;  // cospml.c:205
+                if (k < pad_a) pa[sl * (TA / 8) * 64] = k < len_a ? (q.x * sr + q.y * di) * sc0 : 0.0;
+                if (k < pad_b) pb[sl * (TA / 8) * 64] = k < len_b ? (q.x * si - q.y * dr) * sc0 : 0.0;
+                if (k != 0) {
+                    if (km < pad_a) pam[-sl * (TA / 8) * 64] = km < len_a ? (q.y * sr - q.x * di) * scale : 0.0;
+                    if (km < pad_b) pbm[-sl * (TA / 8) * 64] = km < len_b ? (q.y * si + q.x * dr) * scale : 0.0;
+                }
+            }
+            // column M/2 pairs with itself; it lives in the upper half (slot 4 of thread 0)
+            if (t == 0) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    if (fft_slot<RA>(e) == 4) {
+                        const int k = M / 2;
+                        const double h = 0.70710678118654752440 * 2.0 * scale;  // cos = sin = sqrt(1/2), ar + br = 2 ar
+                        const uint32_t ta = rta + (uint32_t)(k >> 3), tb2 = rtb + (uint32_t)(k >> 3);
+                        if (k < pad_a) otab[(uint64_t)ta * 64 + eoff(ra, 0)] = k < len_a ? xr[e] * h : 0.0;
+                        if (k < pad_b) otab[(uint64_t)tb2 * 64 + eoff(ra + 1, 0)] = k < len_b ? xi[e] * h : 0.0;
+                    }
             }
         } else {
             // ---- one antisymmetric row per quarter of the CTA: DCT-IV through a complex FFT of length K
