@@ -314,3 +314,25 @@ def test_bw1024_switches_keep_parity(env):
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "2 passed" in r.stdout, r.stdout[-500:]
+
+
+def test_sub_batch_split_over_two_streams():
+    """S2KIT_CUDA_SPLIT=2 (plan.cu, run_split: a chunk cut into sub-batches that alternate between two streams -- measured
+    slower than one stream, kept as an experiment): the split path must give the results of the unsplit one.  Child
+    processes, because the switch is read once per plan."""
+    code = (
+        "import sys, numpy as np, torch; sys.path.insert(0, %r); import s2kit_b200 as s2; from bench import synth_coeffs\n"
+        "bw, batch = 256, 256; n = 2 * bw; dev = torch.device('cuda', 0)\n"
+        "P = s2.Plan(bw, s2.MEMO, max_batch=batch)\n"
+        "rc, ic = synth_coeffs(torch, bw, batch, dev, 7)\n"
+        "rd = torch.empty(batch, n, n, device=dev, dtype=torch.float64); idt = torch.empty_like(rd)\n"
+        "P.inv_fst(rc, ic, rd, idt, 0); rc2, ic2 = torch.empty_like(rc), torch.empty_like(ic); P.fst(rd, idt, rc2, ic2, 0); P.synchronize()\n"
+        "print('SUM %%.17g %%.17g %%.3e' %% (float(rd.double().sum()), float(rc2.abs().sum()), float((rc2 - rc).abs().max())))\n" % ROOT)
+    outs = []
+    for split in ("1", "2"):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, S2KIT_CUDA_SPLIT=split), cwd=ROOT,
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        outs.append([ln for ln in r.stdout.splitlines() if ln.startswith("SUM")][-1].split())
+    assert outs[0][1] == outs[1][1] and outs[0][2] == outs[1][2]  # bit-identical: same kernels on the same data
+    assert float(outs[1][3]) < 1e-10
