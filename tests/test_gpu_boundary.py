@@ -173,11 +173,13 @@ def test_reference_api_routes_large_fields_to_all_gpus(s2, oracle_mod):
         "e1 = np.abs(g[0].ravel()[::gs] - large['bw512_inv_sample_r']).max() / np.abs(large['bw512_inv_sample_r']).max()\n"
         "e2 = np.abs(c[0][::cs] - large['bw512_fwd_sample_r']).max() / np.abs(large['bw512_fwd_sample_r']).max()\n"
         "print('ERR', e1, e2); s2.release()\n" % (ROOT, ROOT, ROOT))
-    env = dict(os.environ, S2KIT_CUDA_NGPU=str(ngpu), S2KIT_CUDA_MULTI_MIN_BW="512")
+    env = dict(os.environ, S2KIT_CUDA_NGPU=str(ngpu), S2KIT_CUDA_MULTI_MIN_BW="512", S2KIT_CUDA_MULTI_PROF="1")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
     e1, e2 = (float(v) for v in r.stdout.split("ERR")[1].split()[:2])
     assert e1 < TOL and e2 < TOL
+    if ngpu > 1:  # S2KIT_CUDA_MULTI_PROF: the per-stage event times of every GPU on stderr
+        assert "[s2kit multi] gpu 0:" in r.stderr and "K3" in r.stderr and "K6" in r.stderr
 
 
 # ------------------------------------------------------------------------------------------------ any bandwidth
