@@ -658,9 +658,12 @@ cudaError_t launch_legendre_inv(s2kit_cuda_plan* p, const double* table, uint64_
     int rs = pick_rowsplit(p->bw, (nfun + NF - 1) / NF, m_hi - m_lo);
     int slot = prof_begin(p, S2KIT_K_LEGENDRE_INV);
     cudaError_t e;
-    static const int quad = [] {  // S2KIT_CUDA_K4_QUAD=1: four-column-tile units with TMA-staged table tiles
+    // batched bw = 256: four-column-tile units with TMA-staged table tiles (k_legendre_inv_q).  Default: 1.17-1.21 ms per
+    // 1024 functions against 1.18-1.22 ms for k_legendre_inv<32,32> (three alternating runs on one box), with the LSU data pipe
+    // at 47 % instead of 70 %.  S2KIT_CUDA_K4_QUAD=0 selects the pair kernel.
+    static const int quad = [] {
         const char* ev = getenv("S2KIT_CUDA_K4_QUAD");
-        return (ev && ev[0] == '1') ? 1 : 0;
+        return (ev && ev[0] == '0') ? 0 : 1;
     }();
     if (quad && nc == 32 && p->bw == 256 && !order_list && !(p->table_single && table == p->d_table)) {
         const size_t smem = sizeof(double) * 2 * 32 * panel_stride(p->bw) + sizeof(double2) * LEG_WARPS * LQ_STAGES * LQ * 32 +

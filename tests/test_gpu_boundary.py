@@ -276,7 +276,7 @@ def test_table_builders_match_reference_layout(s2, oracle_mod):
 # ------------------------------------------------------------------------------------------------ tuning switches
 @pytest.mark.parametrize("env", [{"S2KIT_CUDA_NO_TMA": "1"}, {"S2KIT_CUDA_FFT16": "0"}, {"S2KIT_CUDA_L2PERSIST": "1"},
                                  {"S2KIT_CUDA_NC": "16"}, {"S2KIT_CUDA_L2PF_MAX": "0"}, {"S2KIT_CUDA_UNI": "0"},
-                                 {"S2KIT_CUDA_UNI_INV": "1"}, {"S2KIT_CUDA_FLOW": "1"}, {"S2KIT_CUDA_K4_QUAD": "1"}, {"S2KIT_CUDA_UNI_LEAD": "2", "S2KIT_CUDA_UNI_SLEEP": "0", "S2KIT_CUDA_UNI_CAP": "8"},
+                                 {"S2KIT_CUDA_UNI_INV": "1"}, {"S2KIT_CUDA_FLOW": "1"}, {"S2KIT_CUDA_K4_QUAD": "0"}, {"S2KIT_CUDA_UNI_LEAD": "2", "S2KIT_CUDA_UNI_SLEEP": "0", "S2KIT_CUDA_UNI_CAP": "8"},
                                  {"S2KIT_CUDA_TMA_TABLES": "1"},
                                  {"S2KIT_CUDA_TABLE_LCH": "64", "S2KIT_CUDA_FLY_RING_MB": "8"}])
 def test_tuning_switches_keep_parity(env):
